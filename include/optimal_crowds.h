@@ -1,0 +1,162 @@
+/* optimal_crowds.h -- C ABI of liboc_b200.so, the B200 (sm_100a) implementation of the two
+ * data-parallel hot paths of matteobutano/optimal_crowds.
+ *
+ * The reference is pure Python and has no FFI of its own; the boundary this
+ * library replaces is the Python-internal one between simulations.py / optimals.py / pedestrians.py
+ * and numpy/scipy.  Each entry point names the reference code it stands in for (file:line under
+ * /root/reference, or scipy 1.18.1 for the un-vendored integrator).  The Python shim in
+ * optimal_crowds_b200/{optimals,simulations,pedestrians}.py binds these with ctypes
+ * (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every call returns OC_OK (0) or a negative oc_status; oc_last_error() gives the text.
+ *   - one oc_ctx per (GPU, grid); a context is not thread-safe.
+ *   - "d_" pointers are DEVICE pointers owned by the caller (e.g. torch tensors); all others are host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls that return a
+ *     host-visible scalar (solve statistics, exit log) synchronise that stream before returning;
+ *     the others are asynchronous on it.
+ *   - grid arrays are C-order (Ny,Nx) float64, y the slow axis, exactly like the reference's numpy arrays.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with OC_ERR_CUDA.
+ */
+#ifndef OPTIMAL_CROWDS_H
+#define OPTIMAL_CROWDS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_ABI_VERSION 1
+
+typedef enum {
+    OC_OK = 0,
+    OC_ERR_CUDA = -1,           /* CUDA runtime error (text in oc_last_error) */
+    OC_ERR_ARG = -2,            /* invalid argument */
+    OC_ERR_NOMEM = -3,          /* device or host allocation failed */
+    OC_ERR_SAMPLER_RANGE = -4,  /* an agent position would make the reference's sampler raise IndexError
+                                   or wrap a negative index (optimals.py:234-248) */
+    OC_ERR_STEP_TOO_SMALL = -5, /* RK45 TOO_SMALL_STEP (scipy rk.py:133-134): solve_ivp status -1 */
+    OC_ERR_NCCL = -6
+} oc_status;
+
+typedef struct oc_ctx oc_ctx;
+
+int oc_abi_version(void);
+const char *oc_last_error(void);
+/* number of this library's kernels launched since the last call with reset != 0 (bench.py gpu_launches) */
+long long oc_launch_count(int reset);
+
+/* Grid context.  X (Nx) and Y (Ny) are the np.linspace node coordinates of simulations.py:69-70 /
+ * optimals.py:61-62, computed by the host with numpy so they are bit-identical to the reference's. */
+int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length, double room_height,
+                  const double *X, const double *Y, oc_ctx **out);
+void oc_ctx_destroy(oc_ctx *ctx);
+
+/* ------------------------------------------------------------------ room rasteriser (K8)
+ * Replaces simulation.create_potential (simulations.py:516-576) followed by the value remap of
+ * optimals.__init__ (optimals.py:89-91) when remap != 0 (V<0 -> wall_value, V>0 -> target_value).
+ * Shapes are flat host arrays in JSON order: walls/holes/targets (n,4) = cx,cy,w,h; cylinders (n,3) = cx,cy,r. */
+int oc_rasterise(oc_ctx *ctx, const double *walls, int n_walls, const double *holes, int n_holes,
+                 const double *cyls, int n_cyls, const double *targets, int n_targets, int remap,
+                 double wall_value, double target_value, double *d_V, void *stream);
+
+/* ------------------------------------------------------------------ HJB solve (K1, K2, K3)
+ * Replaces optimals.compute_optimal_velocity (optimals.py:124-206) including scipy's
+ * solve_ivp(method='RK45', t_eval=...) (scipy rk.py / common.py / ivp.py, see oracle/oc_oracle_hjb.c). */
+typedef struct {
+    double sigma, mu, g;  /* config.json hjb_params            optimals.py:66-70 */
+    double rtol, atol;    /* solve_ivp defaults 1e-3 / 1e-6    optimals.py:196 */
+    double lim;           /* 10e-3                             optimals.py:95 */
+    int fused;            /* 0: one kernel per RK stage; 1: stage-fused step kernel (temporal blocking) */
+    int reserved;
+} oc_hjb_params;
+
+typedef struct {
+    int nfev;        /* RHS evaluations, = 6*attempts + 2 (scipy's sol.nfev) */
+    int n_accepted;  /* accepted steps */
+    int n_rejected;  /* rejected step attempts */
+    int status;      /* solve_ivp status: 0 finished, -1 step too small */
+    int n_out;       /* t_eval samples emitted (== nt on success) */
+    int launches;    /* kernels launched by this solve */
+    double h0;       /* select_initial_step result */
+    double gpu_ms;   /* CUDA-event time of the whole solve on `stream` */
+} oc_hjb_stats;
+
+/* d_V: remapped potential {wall_value,0,target_value}; d_m: density or NULL (== zeros).
+ * t_eval: nt decreasing host values, np.linspace(T,0,nt) (optimals.py:194).
+ * Outputs (each nullable): d_phi (nt,Ny,Nx): slice k = sol.y[:,k];
+ *   d_vx,d_vy (nt-1,Ny-2,Nx-2): slice s = vels(sol.y[:,nt-1-s]) = the reference's vx_opt[s] (optimals.py:200-204).
+ * trace_h/trace_err (nullable, capacity trace_cap): signed h and error norm of every step attempt. */
+int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, const oc_hjb_params *prm, double T,
+                 const double *t_eval, int nt, double *d_phi, double *d_vx, double *d_vy, oc_hjb_stats *stats,
+                 double *trace_h, double *trace_err, int trace_cap, int *trace_n, void *stream);
+
+/* One RHS evaluation, the `hjb` closure (optimals.py:144-164). d_phi,d_out: (Ny,Nx). */
+int oc_hjb_rhs(oc_ctx *ctx, const double *d_phi, const double *d_V, const double *d_m, const oc_hjb_params *prm,
+               double *d_out, void *stream);
+/* `vels` (optimals.py:168-186): d_phi (Ny,Nx) -> d_vx,d_vy (Ny-2,Nx-2). */
+int oc_hjb_vels(oc_ctx *ctx, const double *d_phi, const oc_hjb_params *prm, double *d_vx, double *d_vy,
+                void *stream);
+
+/* ------------------------------------------------------------------ GCFM step (K4, K5, K6)
+ * Replaces simulation.step (simulations.py:252-339) with ped.agents_repulsion / wall_repulsion /
+ * check_status / evolve (pedestrians.py:121-136,166-191,216-334) and
+ * optimals.choose_optimal_velocity (optimals.py:212-250), keeping the sequential random-order
+ * in-place sweep semantics.  Scalars are computed by the host with the reference's own Python
+ * expressions (dt**2, noise_intensity/2, np.cos(0.7*np.pi)). */
+typedef struct {
+    double dt, dt2, half_noise, relaxation, v_max, cutoff;
+    double a_min, tau_a, b_min, b_max, eta, eta_walls;
+    double cos_fov, one_minus_cos_fov;
+    double dx, dy, room_length, room_height;
+    int Ny, Nx;
+} oc_gcfm_params;
+
+typedef struct {
+    const double *d_V;            /* (Ny,Nx) remapped potential of this target set (simulation.Vs[key]) */
+    const uint8_t *d_wall_tiles;  /* oc_wall_tiles() occupancy map of d_V (accelerates the exact argmin) */
+    double v_min;                 /* min(V) over the grid, from oc_wall_tiles() */
+    const double *d_vx, *d_vy;    /* (n_slices,Ny-2,Nx-2) optimal velocity field */
+    int nt_opt;                   /* optimals.nt_opt (optimals.py:140,231) */
+    int n_slices;
+    const double *doors;          /* host (n_doors,4): cx,cy,w,h of the box's targets (pedestrians.py:132-135) */
+    int n_doors;
+} oc_key;
+
+/* Occupancy map used by the exact nearest-wall search (pedestrians.py:311-313): one byte per
+ * OC_WALL_TILE x OC_WALL_TILE block of nodes, 1 if the block holds a node with V < 0.
+ * d_tiles: device buffer of oc_wall_tiles_bytes(ctx) bytes, caller-owned.  Synchronises `stream`. */
+#define OC_WALL_TILE 16
+long long oc_wall_tiles_bytes(oc_ctx *ctx);
+int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, double *v_min, void *stream);
+
+/* Agent state is SoA on the device: d_x,d_y,d_vx,d_vy,d_time (N doubles), d_status (N bytes, 1 inside),
+ * d_vdes (N), d_key (N ints: index into keys).  perm (N) and noise (n_noise,2) are host arrays drawn by the
+ * host from numpy's legacy global RNG exactly as simulations.py:271,303 would (n_noise = agents inside at
+ * step start).  exit_log (host, capacity N) receives the ids of agents that left during this step, in
+ * sweep order; *n_exit their count.  Returns OC_ERR_SAMPLER_RANGE (state still advanced with a zero
+ * desired velocity for the offending agents) if the reference would have raised/wrapped. */
+int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx,
+                 double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
+                 const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
+                 int simu_step, int *exit_log, int *n_exit, void *stream);
+
+/* Nearest-wall search + wall force only (pedestrians.py:282-334) for N independent probes (unit parity):
+ * d_ind (nullable, N int64): the np.argmin flat index. */
+int oc_wall_force(oc_ctx *ctx, const oc_gcfm_params *prm, const double *d_V, int N, const double *d_x,
+                  const double *d_y, const double *d_vx, const double *d_vy, const double *d_vdes, double *d_fx,
+                  double *d_fy, long long *d_ind, void *stream);
+/* Pair force only (pedestrians.py:216-280) for N independent (i,j) probes (unit parity). */
+int oc_pair_force(oc_ctx *ctx, const oc_gcfm_params *prm, int N, const double *d_pi, const double *d_vi,
+                  const double *d_vdes, const double *d_pj, const double *d_vj, double *d_f, void *stream);
+
+/* ------------------------------------------------------------------ Gaussian density (K7)
+ * Replaces simulation.gaussian_density (simulations.py:453-487). C = sqrt(4*pi**2*sigma**2) from the host. */
+int oc_density(oc_ctx *ctx, int N, const double *d_x, const double *d_y, const uint8_t *d_status, double sigma,
+               double C, const double *d_Vglobal, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTIMAL_CROWDS_H */

@@ -1,0 +1,296 @@
+"""ctypes binding of liboc_b200.so (include/optimal_crowds.h).
+
+The library is built in-tree by optimal_crowds_b200/build.py.  There is no CPU fallback: if the shared
+object is missing, or no CUDA device is present when a compute entry point is called, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboc_b200.so")
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+u8p = C.POINTER(C.c_uint8)
+
+
+class OcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liboc_b200 error {code}: {msg}")
+        self.code = code
+
+
+OC_ERR_SAMPLER_RANGE = -4
+OC_ERR_STEP_TOO_SMALL = -5
+
+
+class HjbParams(C.Structure):
+    _fields_ = [("sigma", C.c_double), ("mu", C.c_double), ("g", C.c_double), ("rtol", C.c_double),
+                ("atol", C.c_double), ("lim", C.c_double), ("fused", C.c_int), ("reserved", C.c_int)]
+
+
+class HjbStats(C.Structure):
+    _fields_ = [("nfev", C.c_int), ("n_accepted", C.c_int), ("n_rejected", C.c_int), ("status", C.c_int),
+                ("n_out", C.c_int), ("launches", C.c_int), ("h0", C.c_double), ("gpu_ms", C.c_double)]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class GcfmParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("dt", "dt2", "half_noise", "relaxation", "v_max", "cutoff", "a_min", "tau_a", "b_min", "b_max",
+                 "eta", "eta_walls", "cos_fov", "one_minus_cos_fov", "dx", "dy", "room_length", "room_height")] + \
+               [("Ny", C.c_int), ("Nx", C.c_int)]
+
+
+class Key(C.Structure):
+    _fields_ = [("d_V", C.c_void_p), ("d_wall_tiles", C.c_void_p), ("v_min", C.c_double), ("d_vx", C.c_void_p),
+                ("d_vy", C.c_void_p), ("nt_opt", C.c_int), ("n_slices", C.c_int), ("doors", dp), ("n_doors", C.c_int)]
+
+
+_lib = None
+
+EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
+           "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
+           "oc_wall_force", "oc_pair_force", "oc_density"]
+
+
+def load():
+    """Load the shared library (raises if it has not been built -- there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python -m optimal_crowds_b200.build` "
+                          "(the CUDA library is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.oc_last_error.restype = C.c_char_p
+    lib.oc_launch_count.restype = C.c_longlong
+    lib.oc_wall_tiles_bytes.restype = C.c_longlong
+    lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
+    lib.oc_ctx_destroy.restype = None
+    lib.oc_ctx_destroy.argtypes = [C.c_void_p]
+    lib.oc_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp,
+                                  C.POINTER(C.c_void_p)]
+    lib.oc_rasterise.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_void_p, C.c_void_p]
+    lib.oc_hjb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_double, dp, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbStats), dp, dp, C.c_int, ip,
+                                 C.c_void_p]
+    lib.oc_hjb_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p,
+                               C.c_void_p]
+    lib.oc_hjb_vels.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oc_wall_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, dp, C.c_void_p]
+    lib.oc_gcfm_step.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 8 + \
+                                [C.POINTER(Key), C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, C.c_void_p]
+    lib.oc_wall_force.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_void_p, C.c_int] + [C.c_void_p] * 8 + \
+                                 [C.c_void_p]
+    lib.oc_pair_force.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 6 + [C.c_void_p]
+    lib.oc_density.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise OcError(rc, load().oc_last_error().decode())
+    return rc
+
+
+def _hp(a):
+    """host pointer of a contiguous float64 numpy array (or NULL)"""
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def _dev(t):
+    """device pointer of a torch CUDA tensor (or NULL)"""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def grid_shape(room_length, room_height, grid_step):
+    """simulations.py:63-64 / optimals.py:55-56 (float floor division quirk kept)."""
+    return int(room_height // grid_step + 1), int(room_length // grid_step + 1)
+
+
+class Context:
+    """One (GPU, grid) context; owns the library workspace."""
+
+    def __init__(self, room_length, room_height, grid_step, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("optimal_crowds_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        lib = load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.Ny, self.Nx = grid_shape(room_length, room_height, grid_step)
+        self.dx = self.dy = grid_step
+        self.room_length, self.room_height = room_length, room_height
+        self.X = np.linspace(0, room_length, self.Nx)  # simulations.py:69
+        self.Y = np.linspace(0, room_height, self.Ny)  # simulations.py:70
+        h = C.c_void_p()
+        check(lib.oc_ctx_create(self.device, self.Ny, self.Nx, self.dx, self.dy, float(room_length),
+                                float(room_height), _hp(self.X), _hp(self.Y), C.byref(h)))
+        self.h = h
+        self.torch_device = torch.device("cuda", self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().oc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers
+    def empty(self, *shape, dtype=None):
+        import torch
+        return torch.empty(*shape, dtype=dtype or torch.float64, device=self.torch_device)
+
+    def to_device(self, a, dtype=None):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.torch_device)
+
+    # ---- K8
+    def rasterise(self, walls, holes, cyls, targets, remap=False, wall_value=-100.0, target_value=1.0, out=None):
+        w, h, c, t = (np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, k))
+                      for a, k in ((walls, 4), (holes, 4), (cyls, 3), (targets, 4)))
+        V = out if out is not None else self.empty(self.Ny, self.Nx)
+        check(load().oc_rasterise(self.h, _hp(w), len(w), _hp(h), len(h), _hp(c), len(c), _hp(t), len(t),
+                                  int(bool(remap)), float(wall_value), float(target_value), _dev(V), _stream()))
+        return V
+
+    # ---- HJB
+    def hjb_solve(self, V, m, prm: HjbParams, T, nt, want_phi=False, want_vel=True, trace=False, out_vx=None,
+                  out_vy=None):
+        t_eval = np.linspace(T, 0, nt)  # optimals.py:194
+        n = self.Ny * self.Nx
+        phi = self.empty(nt, self.Ny, self.Nx) if want_phi else None
+        vx = vy = None
+        if want_vel:
+            vx = out_vx if out_vx is not None else self.empty(max(nt - 1, 0), self.Ny - 2, self.Nx - 2)
+            vy = out_vy if out_vy is not None else self.empty(max(nt - 1, 0), self.Ny - 2, self.Nx - 2)
+        st = HjbStats()
+        cap = 1 << 16 if trace else 0
+        th = np.empty(max(cap, 1)); te = np.empty(max(cap, 1))
+        ntr = C.c_int()
+        rc = load().oc_hjb_solve(self.h, _dev(V), _dev(m), C.byref(prm), float(T), _hp(t_eval), int(nt), _dev(phi),
+                                 _dev(vx), _dev(vy), C.byref(st), _hp(th) if trace else None,
+                                 _hp(te) if trace else None, cap, C.byref(ntr), _stream())
+        check(rc, allow=(OC_ERR_STEP_TOO_SMALL,))
+        res = {"stats": st.asdict(), "phi": phi, "vx": vx, "vy": vy, "rc": rc}
+        if trace:
+            k = min(ntr.value, cap)
+            res["trace_h"], res["trace_err"] = th[:k].copy(), te[:k].copy()
+        return res
+
+    def hjb_rhs(self, phi, V, m, prm: HjbParams):
+        out = self.empty(self.Ny, self.Nx)
+        check(load().oc_hjb_rhs(self.h, _dev(phi), _dev(V), _dev(m), C.byref(prm), _dev(out), _stream()))
+        return out
+
+    def hjb_vels(self, phi, prm: HjbParams):
+        vx = self.empty(self.Ny - 2, self.Nx - 2); vy = self.empty(self.Ny - 2, self.Nx - 2)
+        check(load().oc_hjb_vels(self.h, _dev(phi), C.byref(prm), _dev(vx), _dev(vy), _stream()))
+        return vx, vy
+
+    # ---- GCFM
+    def wall_tiles(self, V):
+        import torch
+        nb = load().oc_wall_tiles_bytes(self.h)
+        tiles = torch.empty(nb, dtype=torch.uint8, device=self.torch_device)
+        vmin = C.c_double()
+        check(load().oc_wall_tiles(self.h, _dev(V), _dev(tiles), C.byref(vmin), _stream()))
+        return tiles, vmin.value
+
+    def gcfm_step(self, prm: GcfmParams, state, vdes, key_id, keys, perm, noise, simu_step):
+        """state: dict of CUDA tensors x,y,vx,vy,time (float64) and status (uint8), updated in place.
+        keys: list of dicts(V, tiles, v_min, vx, vy, nt_opt, doors(np (n,4)))."""
+        N = state["x"].numel()
+        karr = (Key * len(keys))()
+        keep = []
+        for q, k in enumerate(keys):
+            doors = np.ascontiguousarray(np.asarray(k["doors"], dtype=np.float64).reshape(-1, 4))
+            keep.append(doors)
+            karr[q] = Key(k["V"].data_ptr(), k["tiles"].data_ptr(), float(k["v_min"]),
+                          k["vx"].data_ptr() if k.get("vx") is not None else None,
+                          k["vy"].data_ptr() if k.get("vy") is not None else None, int(k["nt_opt"]),
+                          int(k["vx"].shape[0]) if k.get("vx") is not None else 0, _hp(doors), len(doors))
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 2)
+        exit_log = np.empty(max(N, 1), dtype=np.int32)
+        n_exit = C.c_int()
+        rc = load().oc_gcfm_step(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]), _dev(state["vx"]),
+                                 _dev(state["vy"]), _dev(state["time"]), _dev(state["status"]), _dev(vdes),
+                                 _dev(key_id), karr, len(keys), perm.ctypes.data_as(ip), _hp(noise), len(noise),
+                                 int(simu_step), exit_log.ctypes.data_as(ip), C.byref(n_exit), _stream())
+        check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
+        return exit_log[: n_exit.value].copy(), rc
+
+    def wall_force(self, prm: GcfmParams, V, x, y, vx, vy, vdes):
+        import torch
+        N = x.numel()
+        fx = self.empty(N); fy = self.empty(N)
+        ind = torch.empty(N, dtype=torch.int64, device=self.torch_device)
+        check(load().oc_wall_force(self.h, C.byref(prm), _dev(V), N, _dev(x), _dev(y), _dev(vx), _dev(vy), _dev(vdes),
+                                   _dev(fx), _dev(fy), _dev(ind), _stream()))
+        return fx, fy, ind
+
+    def pair_force(self, prm: GcfmParams, pi, vi, vdes, pj, vj):
+        N = vdes.numel()
+        f = self.empty(N, 2)
+        check(load().oc_pair_force(self.h, C.byref(prm), N, _dev(pi), _dev(vi), _dev(vdes), _dev(pj), _dev(vj),
+                                   _dev(f), _stream()))
+        return f
+
+    def density(self, x, y, status, sigma, Vglobal, out=None):
+        N = 0 if x is None else x.numel()
+        d = out if out is not None else self.empty(self.Ny, self.Nx)
+        Cn = float(np.sqrt(4 * np.pi ** 2 * sigma ** 2))  # simulations.py:482
+        check(load().oc_density(self.h, N, _dev(x), _dev(y), _dev(status), float(sigma), Cn, _dev(Vglobal), _dev(d),
+                                _stream()))
+        return d
+
+
+def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: int) -> GcfmParams:
+    """Scalars evaluated with the reference's own Python expressions
+    (simulations.py:81-97,303,314; pedestrians.py:74,262) so they are bit-identical."""
+    p = GcfmParams()
+    dt = cfg["dt"]
+    p.dt, p.dt2 = dt, dt ** 2
+    p.half_noise = cfg["hjb_params"]["sigma"] / 2
+    p.relaxation, p.v_max, p.cutoff = cfg["relaxation"], cfg["v_max"], cfg["repulsion_cutoff"]
+    p.a_min, p.tau_a, p.b_min, p.b_max = cfg["b_min"], cfg["tau_a"], cfg["b_min"], cfg["b_max"]
+    p.eta, p.eta_walls = cfg["eta"], cfg["eta_walls"]
+    c = float(np.cos(0.7 * np.pi))
+    p.cos_fov, p.one_minus_cos_fov = c, 1 - c
+    p.dx = p.dy = cfg["grid_step"]
+    p.room_length, p.room_height, p.Ny, p.Nx = room_length, room_height, Ny, Nx
+    return p
+
+
+def hjb_params(cfg: dict, fused: int = 0) -> HjbParams:
+    h = cfg["hjb_params"]
+    return HjbParams(h["sigma"], h["mu"], h["g"], 1e-3, 1e-6, 10e-3, int(fused), 0)
+
+
+def launch_count(reset=False):
+    return int(load().oc_launch_count(int(bool(reset))))

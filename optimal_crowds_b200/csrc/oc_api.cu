@@ -1,0 +1,172 @@
+// oc_api.cu -- context management, error text, rasteriser (K8) and density (K7) of liboc_b200.so.
+#include <cmath>
+#include <mutex>
+
+#include "oc_common.h"
+#include "oc_math.h"
+
+namespace oc {
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace oc
+
+extern "C" int oc_abi_version(void) { return OC_ABI_VERSION; }
+extern "C" const char *oc_last_error(void) { return oc::g_err; }
+extern "C" long long oc_launch_count(int reset) {
+    return reset ? oc::g_launches.exchange(0) : oc::g_launches.load();
+}
+
+extern "C" int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length,
+                             double room_height, const double *X, const double *Y, oc_ctx **out) {
+    OC_ARG(out != nullptr, "out is NULL");
+    OC_ARG(Ny >= 3 && Nx >= 3, "grid must be at least 3x3");
+    OC_ARG(X != nullptr && Y != nullptr, "X/Y linspace arrays required");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        oc::set_error("no CUDA device available (%s); liboc_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return OC_ERR_CUDA;
+    }
+    OC_ARG(device >= 0 && device < ndev, "device index out of range");
+    OC_CUDA(cudaSetDevice(device));
+    oc_ctx *c = new oc_ctx();
+    c->device = device;
+    c->Ny = Ny;
+    c->Nx = Nx;
+    c->dx = dx;
+    c->dy = dy;
+    c->room_length = room_length;
+    c->room_height = room_height;
+    c->X.assign(X, X + Nx);
+    c->Y.assign(Y, Y + Ny);
+    OC_CUDA(cudaMalloc(&c->d_X, sizeof(double) * Nx));
+    OC_CUDA(cudaMalloc(&c->d_Y, sizeof(double) * Ny));
+    OC_CUDA(cudaMemcpy(c->d_X, X, sizeof(double) * Nx, cudaMemcpyHostToDevice));
+    OC_CUDA(cudaMemcpy(c->d_Y, Y, sizeof(double) * Ny, cudaMemcpyHostToDevice));
+    OC_CUDA(cudaEventCreate(&c->ev0));
+    OC_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return OC_OK;
+}
+
+extern "C" void oc_ctx_destroy(oc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_X);
+    cudaFree(c->d_Y);
+    cudaFree(c->hjb_ws);
+    cudaFree(c->hjb_partial);
+    cudaFree(c->gcfm_ws);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 rasteriser: one thread per node, shapes staged in shared memory in chunks.
+// simulations.py:536-576: walls add -1 (:538-547), holes set 0 (:549-555), cylinders add -1 (:557-563),
+// frame = -1 (:565-568), targets = 1 (:570-574); strict '<' on the linspace coordinates.
+// optimals.py:89-91 remap: V<0 -> pot, V>0 -> pot_target.
+namespace {
+constexpr int RAST_CHUNK = 512;
+
+struct RastArgs {
+    const double *walls, *holes, *cyls, *targets;  // device copies
+    int n_walls, n_holes, n_cyls, n_targets;
+    int remap;
+    double wall_value, target_value;
+};
+
+__global__ void __launch_bounds__(256) rasterise_kernel(const double *__restrict__ X, const double *__restrict__ Y,
+                                                        int Ny, int Nx, RastArgs a, double *__restrict__ V) {
+    __shared__ double sh[RAST_CHUNK * 4];
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool in = (i < Ny && j < Nx);
+    const double x = in ? X[j] : 0.0, y = in ? Y[i] : 0.0;
+    double v = 0.0;
+    for (int base = 0; base < a.n_walls; base += RAST_CHUNK) {
+        int n = min(RAST_CHUNK, a.n_walls - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.walls[base * 4 + k];
+        __syncthreads();
+        for (int k = 0; k < n; k++)
+            if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v += -1.0;
+    }
+    for (int base = 0; base < a.n_holes; base += RAST_CHUNK) {
+        int n = min(RAST_CHUNK, a.n_holes - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.holes[base * 4 + k];
+        __syncthreads();
+        for (int k = 0; k < n; k++)
+            if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v = 0.0;
+    }
+    for (int base = 0; base < a.n_cyls; base += RAST_CHUNK) {
+        int n = min(RAST_CHUNK, a.n_cyls - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * 3; k += 256) sh[k] = a.cyls[base * 3 + k];
+        __syncthreads();
+        for (int k = 0; k < n; k++) {
+            double ddx = x - sh[3 * k], ddy = y - sh[3 * k + 1];
+            if (sqrt(ddx * ddx + ddy * ddy) < sh[3 * k + 2]) v += -1.0;
+        }
+    }
+    if (in && (j == 0 || j == Nx - 1 || i == 0 || i == Ny - 1)) v = -1.0;
+    for (int base = 0; base < a.n_targets; base += RAST_CHUNK) {
+        int n = min(RAST_CHUNK, a.n_targets - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.targets[base * 4 + k];
+        __syncthreads();
+        for (int k = 0; k < n; k++)
+            if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v = 1.0;
+    }
+    if (!in) return;
+    if (a.remap) {
+        if (v < 0) v = a.wall_value;
+        else if (v > 0) v = a.target_value;
+    }
+    V[(size_t)i * Nx + j] = v;
+}
+}  // namespace
+
+extern "C" int oc_rasterise(oc_ctx *ctx, const double *walls, int n_walls, const double *holes, int n_holes,
+                            const double *cyls, int n_cyls, const double *targets, int n_targets, int remap,
+                            double wall_value, double target_value, double *d_V, void *stream) {
+    OC_ARG(ctx && d_V, "ctx/d_V NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    OC_CUDA(cudaSetDevice(ctx->device));
+    size_t nd = (size_t)4 * n_walls + 4 * n_holes + 3 * n_cyls + 4 * n_targets;
+    double *d_sh = nullptr;
+    std::vector<double> h(nd ? nd : 1);
+    size_t o = 0;
+    RastArgs a{};
+    if (nd) OC_CUDA(cudaMalloc(&d_sh, nd * sizeof(double)));
+    auto put = [&](const double *src, int n, int w, const double *&dst) {
+        dst = d_sh + o;
+        if (n) memcpy(h.data() + o, src, sizeof(double) * n * w);
+        o += (size_t)n * w;
+    };
+    put(walls, n_walls, 4, a.walls);
+    put(holes, n_holes, 4, a.holes);
+    put(cyls, n_cyls, 3, a.cyls);
+    put(targets, n_targets, 4, a.targets);
+    a.n_walls = n_walls; a.n_holes = n_holes; a.n_cyls = n_cyls; a.n_targets = n_targets;
+    a.remap = remap; a.wall_value = wall_value; a.target_value = target_value;
+    if (nd) OC_CUDA(cudaMemcpyAsync(d_sh, h.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    dim3 grid((ctx->Nx + 31) / 32, (ctx->Ny + 7) / 8);
+    rasterise_kernel<<<grid, 256, 0, st>>>(ctx->d_X, ctx->d_Y, ctx->Ny, ctx->Nx, a, d_V);
+    oc::count_launch();
+    OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaStreamSynchronize(st));  // h / d_sh lifetimes
+    if (d_sh) cudaFree(d_sh);
+    return OC_OK;
+}

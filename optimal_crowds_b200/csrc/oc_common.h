@@ -1,0 +1,56 @@
+// oc_common.h -- shared host-side plumbing of liboc_b200.so (context, error text, launch counter).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/optimal_crowds.h"
+
+struct oc_ctx {
+    int device;
+    int Ny, Nx;
+    double dx, dy, room_length, room_height;
+    double *d_X = nullptr, *d_Y = nullptr;  // linspace node coordinates (device copies)
+    std::vector<double> X, Y;               // host copies
+    // HJB workspace (lazily allocated, reused across solves)
+    double *hjb_ws = nullptr;
+    size_t hjb_ws_bytes = 0;
+    double *hjb_partial = nullptr;  // per-tile error partial sums
+    size_t hjb_partial_n = 0;
+    double *h_pinned = nullptr;  // pinned host scratch (row-group sums, flags)
+    size_t h_pinned_n = 0;
+    // GCFM workspace
+    void *gcfm_ws = nullptr;
+    size_t gcfm_ws_bytes = 0;
+    int gcfm_N = -1, gcfm_nbins = -1, gcfm_nkeys = -1, gcfm_ndoors = -1;  // layout the workspace was carved for
+    void *gcfm_pinned = nullptr;
+    size_t gcfm_pinned_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace oc {
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace oc
+
+#define OC_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            oc::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return OC_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define OC_ARG(cond, msg)                  \
+    do {                                   \
+        if (!(cond)) {                     \
+            oc::set_error("bad argument: %s", msg); \
+            return OC_ERR_ARG;             \
+        }                                  \
+    } while (0)

@@ -1,0 +1,796 @@
+// oc_gcfm.cu -- GCFM pedestrian update on sm_100a (K4 wall search, K5 per-agent prepare, K6 sweep) and the
+// Gaussian density splat (K7).  Compile with -fmad=false: every formula is evaluated with exactly the
+// operations written here, in the reference's order, so results are bit-identical to the CPU restatement
+// used by the tests (two-oracle protocol).
+//
+// Reference: simulations.py:252-339 (step), pedestrians.py:216-280 (agents_repulsion), :282-334
+// (wall_repulsion), :121-136 (check_status), :166-191 (evolve), optimals.py:212-250 (sampler),
+// simulations.py:453-487 (gaussian_density).
+//
+// Sweep semantics.  The reference visits agents one by one in a random permutation and updates them in
+// place, so agent i sees the NEW state of every agent earlier in the permutation and the OLD state of the
+// others.  The sweep kernel keeps those semantics exactly while running thousands
+// of agents concurrently: warps draw tickets in permutation order; an agent only needs the new state of
+// earlier agents that can be within the interaction cutoff, and spins on their per-agent "done" flags
+// (release/acquire).  A warp only ever waits on lower tickets, which are held by resident warps or
+// finished, so the schedule cannot deadlock.  The pair sum runs in ascending agent index like the
+// reference's `for j in range(N)` loop (simulations.py:287-295).
+#include <cmath>
+#include <cstdint>
+#include <algorithm>
+#include <vector>
+
+#include "oc_common.h"
+#include "oc_math.h"
+
+namespace {
+
+constexpr int WT = OC_WALL_TILE;
+constexpr double DISP_MARGIN = 1.0;  // max displacement per step assumed by the candidate search (checked)
+constexpr int SWEEP_WARPS = 4;       // warps per block in the sweep
+constexpr int LIST_CAP = 512;        // interacting neighbours per agent held in shared memory
+
+struct KeyDev {
+    const double *V;
+    const uint8_t *tiles;
+    const double *vx, *vy;
+    int nt_opt, n_slices, door_off, n_doors;
+    double off_min;  // v_min * 10e3
+};
+
+struct Ws {  // device workspace carved out of ctx->gcfm_ws
+    double *x0, *y0, *vx0, *vy0;            // snapshot at step start
+    double *des_x, *des_y, *wfx, *wfy;      // per-agent precomputed terms
+    double *noise;                          // (N,2) device copy, consumption order
+    double *doors;                          // flattened door rectangles of all keys
+    int *perm, *rank, *nzidx, *flags, *exit_mark, *agent_bin, *cell_agents, *bin_start, *bin_cursor;
+    uint8_t *status0;
+    KeyDev *keys;
+    int *counters;  // [0] ticket [1] flags: bit0 sampler range, bit1 list overflow, bit2 displacement > margin
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// CPython / numpy float floor division (exact floor of the real quotient; fmod is exact)
+__device__ __forceinline__ double py_floordiv(double vx, double wx) {
+    double mod = fmod(vx, wx);
+    double div = (vx - mod) / wx;
+    if (mod != 0.0) {
+        if ((wx < 0) != (mod < 0)) div -= 1.0;
+    }
+    if (div != 0.0) {
+        double fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+        return fl;
+    }
+    return copysign(0.0, vx / wx);
+}
+
+// optimals.py:212-250 -- returns 1 if the reference would raise IndexError / wrap a negative index
+__device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double x, double y, int t, double &ox,
+                               double &oy) {
+    ox = 0.0;
+    oy = 0.0;
+    if (t >= k.nt_opt - 1) return 0;
+    long long j0, j1, i0, i1;
+    if (x < p.room_length - p.dx) {
+        j0 = (long long)py_floordiv(x, p.dx);
+        j1 = (x > p.dx) ? j0 + 1 : j0;
+    } else {
+        j0 = j1 = p.Nx - 3;
+    }
+    if (y < p.room_height - p.dy) {
+        i0 = (long long)py_floordiv(y, p.dy);
+        i1 = (y > p.dy) ? i0 + 1 : i0;
+    } else {
+        i0 = i1 = p.Ny - 3;
+    }
+    const int W = p.Nx - 2, H = p.Ny - 2;
+    if (j0 < 0 || j1 >= W || i0 < 0 || i1 >= H || t < 0 || t >= k.n_slices) return 1;
+    const double *sx = k.vx + (size_t)t * W * H, *sy = k.vy + (size_t)t * W * H;
+    if (j0 == j1 && i0 == i1) {
+        ox = sx[i0 * W + j0];
+        oy = sy[i0 * W + j0];
+    } else {  // two fancy-index lists pair up element-wise: (i0,j0),(i1,j1); np.mean = (a+b)/2
+        ox = (sx[i0 * W + j0] + sx[i1 * W + j1]) / 2.0;
+        oy = (sy[i0 * W + j0] + sy[i1 * W + j1]) / 2.0;
+    }
+    return 0;
+}
+
+struct AgentEllipse {  // quantities of agent i that do not depend on the partner (pedestrians.py:242-243,267)
+    double ni, a_i, b_i, beta_i;
+};
+__device__ __forceinline__ AgentEllipse ellipse_of(const oc_gcfm_params &p, double vx, double vy, double v_des) {
+    AgentEllipse e;
+    e.ni = ocm_norm2(vx, vy);
+    e.a_i = p.a_min + p.tau_a * e.ni;
+    e.b_i = p.b_max - (p.b_max - p.b_min) * fmin(e.ni / v_des, 1.0);
+    e.beta_i = ocm_atan2(vy, vx);
+    return e;
+}
+
+// pedestrians.py:237-280
+__device__ void pair_force(const oc_gcfm_params &p, const AgentEllipse &ei, double xi, double yi, double vxi,
+                           double vyi, double v_des_i, double xj, double yj, double vxj, double vyj, double &fx,
+                           double &fy) {
+    double nj = ocm_norm2(vxj, vyj);
+    double a_j = p.a_min + p.tau_a * nj;
+    double b_j = p.b_max - (p.b_max - p.b_min) * fmin(nj / v_des_i, 1.0);  // v_des of i: pedestrians.py:245
+    double Rx = xj - xi, Ry = yj - yi;
+    double nR = ocm_norm2(Rx, Ry);
+    double ex = Rx / nR, ey = Ry / nR;
+    double wx = vxj - vxi, wy = vyj - vyi;
+    double d = wx * (-ex) + wy * (-ey);
+    double v_rel = 0.5 * (d + fabs(d));
+    double k = 0.0;
+    if (ei.ni > 0) k = fmax((vxi * ex + vyi * ey) / ei.ni - p.cos_fov, 0.0) / p.one_minus_cos_fov;
+    double alpha_i = ocm_atan2(Ry, Rx);
+    double alpha_j = ocm_atan2(-Ry, -Rx), beta_j = ocm_atan2(vyj, vxj);
+    double ci = ocm_cos(alpha_i - ei.beta_i) / ei.a_i, si = ocm_sin(alpha_i - ei.beta_i) / ei.b_i;
+    double q_i = sqrt(1.0 / (ci * ci + si * si));
+    double cj = ocm_cos(alpha_j - beta_j) / a_j, sj = ocm_sin(alpha_j - beta_j) / b_j;
+    double q_j = sqrt(1.0 / (cj * cj + sj * sj));
+    double dist = nR - q_i - q_j;
+    double rep = fmin(k * ocm_exp(-dist / (p.eta * (1.0 + v_rel))), 1.0);
+    fx = -rep * Rx;
+    fy = -rep * Ry;
+}
+
+// pedestrians.py:315-334 given the nearest wall node (wxp, wyp)
+__device__ void wall_force_from_node(const oc_gcfm_params &p, const AgentEllipse &ei, double xi, double yi,
+                                     double vxi, double vyi, double wxp, double wyp, double &fx, double &fy) {
+    double Rx = wxp - xi, Ry = wyp - yi;
+    double nR = ocm_norm2(Rx, Ry);
+    double ex = Rx / nR, ey = Ry / nR;
+    double d = vxi * ex + vyi * ey;
+    double v_rel = 0.5 * (d + fabs(d));
+    double alpha = ocm_atan2(Ry, Rx);
+    double c = ocm_cos(alpha - ei.beta_i) / ei.a_i, s = ocm_sin(alpha - ei.beta_i) / ei.b_i;
+    double q_i = 1.0 / (c * c + s * s);  // no sqrt: pedestrians.py:328
+    double dist = nR - q_i;
+    double rep = fmin(ocm_exp(-dist / (p.eta_walls * (1.0 + v_rel))), 1.0);
+    fx = -3.0 * rep * Rx;
+    fy = -3.0 * rep * Ry;
+}
+
+// K4: exact np.argmin(sqrt((X-x)^2+(Y-y)^2) + V*10e3) (pedestrians.py:311-313), one warp per agent.
+// Only nodes with V<0 can win (their offset is <= -|pot|*1e4, the host checks that this exceeds the room
+// diagonal).  Rings of WT x WT node tiles around the agent are scanned, skipping tiles without wall
+// nodes, until no node outside the scanned square can reach the best key.  Returns the flat index
+// (first index among equal keys, like np.argmin) on every lane.
+__device__ long long wall_argmin_warp(const double *__restrict__ X, const double *__restrict__ Y,
+                                      const double *__restrict__ V, const uint8_t *__restrict__ tiles, int Ny,
+                                      int Nx, double x, double y, double off_min) {
+    const int lane = threadIdx.x & 31;
+    const int ntx = (Nx + WT - 1) / WT, nty = (Ny + WT - 1) / WT;
+    // tile containing the node nearest to (x,y); any centre is correct, a near one is fast
+    const double sx = X[1] - X[0], sy = Y[1] - Y[0];
+    int cx = (int)fmin(fmax(x / sx, 0.0), (double)(Nx - 1)), cy = (int)fmin(fmax(y / sy, 0.0), (double)(Ny - 1));
+    const int tcx = cx / WT, tcy = cy / WT;
+    double best = INFINITY;
+    long long best_i = (long long)Ny * Nx;
+    const int kmax = max(max(tcx, ntx - 1 - tcx), max(tcy, nty - 1 - tcy));
+    for (int k = 0; k <= kmax; k++) {
+        const int ty_lo = tcy - k, ty_hi = tcy + k, tx_lo = tcx - k, tx_hi = tcx + k;
+        // ring k = border of the (2k+1)^2 tile square
+        const int side = 2 * k + 1;
+        const int ring_n = (k == 0) ? 1 : 8 * k;
+        for (int r = 0; r < ring_n; r++) {
+            int tx, ty;
+            if (k == 0) { tx = tcx; ty = tcy; }
+            else if (r < side) { tx = tx_lo + r; ty = ty_lo; }
+            else if (r < 2 * side) { tx = tx_lo + (r - side); ty = ty_hi; }
+            else if (r < 2 * side + (side - 2)) { tx = tx_lo; ty = ty_lo + 1 + (r - 2 * side); }
+            else { tx = tx_hi; ty = ty_lo + 1 + (r - 2 * side - (side - 2)); }
+            if (tx < 0 || tx >= ntx || ty < 0 || ty >= nty) continue;
+            if (!tiles[ty * ntx + tx]) continue;
+            for (int c = lane; c < WT * WT; c += 32) {
+                int iy = ty * WT + c / WT, ix = tx * WT + (c % WT);
+                if (iy < Ny && ix < Nx) {
+                    double v = V[(size_t)iy * Nx + ix];
+                    if (v < 0) {
+                        double ddx = X[ix] - x, ddy = Y[iy] - y;
+                        double key = sqrt(ddx * ddx + ddy * ddy) + v * 10e3;
+                        long long fi = (long long)iy * Nx + ix;
+                        if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
+                    }
+                }
+            }
+        }
+        // lower bound of the distance to any node outside the scanned square
+        double lb = INFINITY;
+        int ix_lo = tx_lo * WT - 1, ix_hi = (tx_hi + 1) * WT, iy_lo = ty_lo * WT - 1, iy_hi = (ty_hi + 1) * WT;
+        if (ix_lo >= 0) lb = fmin(lb, x - X[ix_lo]);
+        if (ix_hi < Nx) lb = fmin(lb, X[ix_hi] - x);
+        if (iy_lo >= 0) lb = fmin(lb, y - Y[iy_lo]);
+        if (iy_hi < Ny) lb = fmin(lb, Y[iy_hi] - y);
+        double wbest = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wbest = fmin(wbest, __shfl_xor_sync(0xffffffffu, wbest, o));
+        // strict: an outside node with an equal key and a lower flat index would win the tie
+        if (lb == INFINITY || wbest < lb * (1.0 - 0x1p-50) + off_min) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob < best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    return best_i;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void tiles_kernel(const double *__restrict__ V, int Ny, int Nx, uint8_t *__restrict__ tiles,
+                             double *__restrict__ vmin_out) {
+    // one warp per tile
+    const int ntx = (Nx + WT - 1) / WT, nty = (Ny + WT - 1) / WT;
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ntx * nty) return;
+    int ty = w / ntx, tx = w % ntx;
+    int any = 0;
+    double vm = INFINITY;
+    for (int c = lane; c < WT * WT; c += 32) {
+        int iy = ty * WT + c / WT, ix = tx * WT + (c % WT);
+        if (iy < Ny && ix < Nx) {
+            double v = V[(size_t)iy * Nx + ix];
+            any |= (v < 0);
+            vm = fmin(vm, v);
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vm = fmin(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+    if (lane == 0) {
+        tiles[w] = (uint8_t)any;
+        vmin_out[w] = vm;
+    }
+}
+
+// rank = inverse permutation; snapshot; bin histogram
+__global__ void setup_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ vx, const double *__restrict__ vy,
+                             const uint8_t *__restrict__ status, Ws w, double inv_cs, int nbx, int nby) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    w.rank[w.perm[i]] = i;
+    double xi = x[i], yi = y[i];
+    w.x0[i] = xi; w.y0[i] = yi; w.vx0[i] = vx[i]; w.vy0[i] = vy[i];
+    uint8_t s = status[i];
+    w.status0[i] = s;
+    int bx = min(max((int)floor(xi * inv_cs), 0), nbx - 1), by = min(max((int)floor(yi * inv_cs), 0), nby - 1);
+    int b = by * nbx + bx;
+    w.agent_bin[i] = b;
+    if (s) atomicAdd(&w.bin_start[b + 1], 1);  // histogram shifted by one: scanned in place afterwards
+}
+
+// single-block inclusive scan in place over a[0..n) (a[0] must be 0 => exclusive offsets)
+__global__ void __launch_bounds__(1024) scan_kernel(int *a, int n) {
+    __shared__ int tot[1024];
+    int t = threadIdx.x;
+    int per = (n + 1023) / 1024;
+    int lo = min(t * per, n), hi = min(lo + per, n);
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += a[i];
+    tot[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = (t >= o) ? tot[t - o] : 0;
+        __syncthreads();
+        tot[t] += v;
+        __syncthreads();
+    }
+    int run = tot[t] - s;
+    for (int i = lo; i < hi; i++) { run += a[i]; a[i] = run; }
+}
+
+__global__ void scatter_kernel(int N, Ws w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !w.status0[i]) return;
+    int b = w.agent_bin[i];
+    int pos = w.bin_start[b] + atomicAdd(&w.bin_cursor[b], 1);
+    w.cell_agents[pos] = i;
+}
+
+// nzidx[agent] = number of agents active at step start that precede it in the sweep (simulations.py:303
+// draws one normal pair per active agent in sweep order).  Single block.
+__global__ void __launch_bounds__(1024) noise_index_kernel(int N, Ws w) {
+    __shared__ int tot[1024];
+    int t = threadIdx.x;
+    int per = (N + 1023) / 1024;
+    int lo = min(t * per, N), hi = min(lo + per, N);
+    int s = 0;
+    for (int r = lo; r < hi; r++) s += w.status0[w.perm[r]];
+    tot[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = (t >= o) ? tot[t - o] : 0;
+        __syncthreads();
+        tot[t] += v;
+        __syncthreads();
+    }
+    int run = tot[t] - s;
+    for (int r = lo; r < hi; r++) {
+        int a = w.perm[r];
+        w.nzidx[a] = run;
+        run += w.status0[a];
+    }
+}
+
+// K5: per-agent terms that depend only on the agent's own old state: desired velocity (sampler) and wall
+// force.  One warp per agent.
+__global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, Ws w,
+                                                      const double *__restrict__ X, const double *__restrict__ Y,
+                                                      const double *__restrict__ vdes, const int *__restrict__ key_id,
+                                                      int simu_step) {
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= N || !w.status0[i]) return;
+    const int lane = threadIdx.x & 31;
+    const KeyDev k = w.keys[key_id[i]];
+    double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i];
+    long long ind = wall_argmin_warp(X, Y, k.V, k.tiles, p.Ny, p.Nx, xi, yi, k.off_min);
+    if (lane == 0) {
+        double ux, uy;
+        int bad = choose_velocity(p, k, xi, yi, simu_step, ux, uy);
+        if (bad) atomicOr(&w.counters[1], 1);
+        w.des_x[i] = vdes[i] * ux;  // simulations.py:281
+        w.des_y[i] = vdes[i] * uy;
+        AgentEllipse ei = ellipse_of(p, vxi, vyi, vdes[i]);
+        double fx, fy;
+        wall_force_from_node(p, ei, xi, yi, vxi, vyi, X[ind % p.Nx], Y[ind / p.Nx], fx, fy);
+        w.wfx[i] = fx;
+        w.wfy[i] = fy;
+    }
+}
+
+// K6: the sweep (simulations.py:271-332)
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
+             double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
+             uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
+             double inv_cs, int nbx, int nby) {
+    __shared__ int s_j[SWEEP_WARPS][LIST_CAP];
+    __shared__ double s_fx[SWEEP_WARPS][LIST_CAP];
+    __shared__ double s_fy[SWEEP_WARPS][LIST_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *lj = s_j[wid];
+    double *lfx = s_fx[wid], *lfy = s_fy[wid];
+    const double reach = p.cutoff + DISP_MARGIN;
+    const double reach2 = reach * reach;
+    const int span = (int)ceil(reach * inv_cs);
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&w.counters[0], 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= N) break;
+        const int i = w.perm[r];
+        if (!w.status0[i]) continue;  // simulations.py:277
+        const double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i], vd = vdes[i];
+        const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
+        int cnt = 0;
+        const int b = w.agent_bin[i];
+        const int bix = b % nbx, biy = b / nbx;
+        for (int by = max(biy - span, 0); by <= min(biy + span, nby - 1); by++) {
+            const int c0 = by * nbx + max(bix - span, 0), c1 = by * nbx + min(bix + span, nbx - 1);
+            const int beg = w.bin_start[c0], end = w.bin_start[c1 + 1];  // bins of one row are contiguous
+            for (int base = beg; base < end; base += 32) {
+                int kk = base + lane;
+                bool hit = false;
+                double fx = 0.0, fy = 0.0;
+                int j = -1;
+                if (kk < end) {
+                    j = w.cell_agents[kk];
+                    double ox = w.x0[j] - xi, oy = w.y0[j] - yi;
+                    if (j != i && ox * ox + oy * oy < reach2) {  // symmetric prefilter on old positions
+                        double xj, yj, vxj, vyj;
+                        bool alive = true;
+                        if (w.rank[j] < r) {  // earlier in the sweep: needs j's NEW state
+                            while (ld_acquire(&w.flags[j]) != tag) __nanosleep(32);
+                            xj = __ldcg(x + j); yj = __ldcg(y + j); vxj = __ldcg(vx + j); vyj = __ldcg(vy + j);
+                            alive = __ldcg(status + j) != 0;
+                        } else {  // later: still in its old state
+                            xj = w.x0[j]; yj = w.y0[j]; vxj = w.vx0[j]; vyj = w.vy0[j];
+                        }
+                        if (alive) {
+                            double ddx = xj - xi, ddy = yj - yi;
+                            if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
+                                pair_force(p, ei, xi, yi, vxi, vyi, vd, xj, yj, vxj, vyj, fx, fy);
+                                hit = true;
+                            }
+                        }
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    int pos = cnt + __popc(m & ((1u << lane) - 1));
+                    if (pos < LIST_CAP) { lj[pos] = j; lfx[pos] = fx; lfy[pos] = fy; }
+                }
+                cnt += __popc(m);
+            }
+        }
+        if (cnt > LIST_CAP) {
+            if (lane == 0) atomicOr(&w.counters[1], 2);
+            cnt = LIST_CAP;
+        }
+        // sort the interacting neighbours by agent index (bitonic, in shared memory)
+        int m2 = 1;
+        while (m2 < cnt) m2 <<= 1;
+        for (int t = cnt + lane; t < m2; t += 32) lj[t] = 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= m2; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = lane; t < m2; t += 32) {
+                    int u = t ^ jj;
+                    if (u > t) {
+                        bool up = ((t & k) == 0);
+                        int a = lj[t], bb = lj[u];
+                        if ((a > bb) == up) {
+                            lj[t] = bb; lj[u] = a;
+                            double q = lfx[t]; lfx[t] = lfx[u]; lfx[u] = q;
+                            q = lfy[t]; lfy[t] = lfy[u]; lfy[u] = q;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        // ascending-j sum (simulations.py:285-295): lane 0 -> x component, lane 1 -> y component
+        double acc = 0.0;
+        if (lane < 2) {
+            const double *src = lane == 0 ? lfx : lfy;
+            for (int t = 0; t < cnt; t++) acc = acc + src[t];
+        }
+        const double rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1);
+        if (lane == 0) {
+            const int nz = w.nzidx[i];
+            double cx = vxi + p.half_noise * w.noise[2 * nz] + rx + w.wfx[i];  // simulations.py:303
+            double cy = vyi + p.half_noise * w.noise[2 * nz + 1] + ry + w.wfy[i];
+            double ax = (w.des_x[i] - cx) / p.relaxation, ay = (w.des_y[i] - cy) / p.relaxation;  // :307-308
+            double nx_ = xi + cx * p.dt + 0.5 * ax * p.dt2;  // :314-315
+            double ny_ = yi + cy * p.dt + 0.5 * ay * p.dt2;
+            double nvx = cx + ax * p.dt, nvy = cy + ay * p.dt;  // :316-317
+            double nr = sqrt(nvx * nvx + nvy * nvy);            // :321
+            if (!(nr < p.v_max)) {                              // :323-326
+                double sc = p.v_max / nr;
+                nvx = nvx * sc;
+                nvy = nvy * sc;
+            }
+            if (!(fabs(nx_ - xi) <= DISP_MARGIN * 0.5) || !(fabs(ny_ - yi) <= DISP_MARGIN * 0.5))
+                atomicOr(&w.counters[1], 4);
+            const KeyDev k = w.keys[key_id[i]];
+            bool out = false;
+            for (int d = 0; d < k.n_doors; d++) {  // pedestrians.py:132-136
+                const double *door = w.doors + 4 * (k.door_off + d);
+                if (fabs(nx_ - door[0]) < door[2] * 0.5 && fabs(ny_ - door[1]) < door[3] * 0.5) out = true;
+            }
+            x[i] = nx_; y[i] = ny_; vx[i] = nvx; vy[i] = nvy;
+            tim[i] = tim[i] + p.dt;  // pedestrians.py:191
+            if (out) {
+                status[i] = 0;
+                w.exit_mark[r] = i + 1;  // simulations.py:331-332, ordered by sweep position
+            }
+            __threadfence();
+            st_release(&w.flags[i], tag);
+        }
+        __syncwarp();
+    }
+}
+
+// ordered compaction of the exit marks (by sweep position) into host-visible memory: out[0]=count, out[1]=flags
+__global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
+    __shared__ int tot[1024];
+    int t = threadIdx.x;
+    int per = (N + 1023) / 1024;
+    int lo = min(t * per, N), hi = min(lo + per, N);
+    int s = 0;
+    for (int r = lo; r < hi; r++) s += (w.exit_mark[r] != 0);
+    tot[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = (t >= o) ? tot[t - o] : 0;
+        __syncthreads();
+        tot[t] += v;
+        __syncthreads();
+    }
+    int run = tot[t] - s;
+    for (int r = lo; r < hi; r++)
+        if (w.exit_mark[r]) out[2 + run++] = w.exit_mark[r] - 1;
+    if (t == 1023) out[0] = tot[1023];
+    if (t == 0) out[1] = w.counters[1];
+}
+
+// unit-probe kernels ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+wall_probe_kernel(oc_gcfm_params p, int N, const double *__restrict__ X, const double *__restrict__ Y,
+                  const double *__restrict__ V, const uint8_t *__restrict__ tiles, double off_min,
+                  const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pvx,
+                  const double *__restrict__ pvy, const double *__restrict__ vdes, double *__restrict__ fx,
+                  double *__restrict__ fy, long long *__restrict__ ind_out) {
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= N) return;
+    long long ind = wall_argmin_warp(X, Y, V, tiles, p.Ny, p.Nx, px[i], py[i], off_min);
+    if ((threadIdx.x & 31) == 0) {
+        AgentEllipse ei = ellipse_of(p, pvx[i], pvy[i], vdes[i]);
+        double ax, ay;
+        wall_force_from_node(p, ei, px[i], py[i], pvx[i], pvy[i], X[ind % p.Nx], Y[ind / p.Nx], ax, ay);
+        fx[i] = ax;
+        fy[i] = ay;
+        if (ind_out) ind_out[i] = ind;
+    }
+}
+
+__global__ void pair_probe_kernel(oc_gcfm_params p, int N, const double *__restrict__ pi, const double *__restrict__ vi,
+                                  const double *__restrict__ vdes, const double *__restrict__ pj,
+                                  const double *__restrict__ vj, double *__restrict__ f) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    AgentEllipse ei = ellipse_of(p, vi[2 * q], vi[2 * q + 1], vdes[q]);
+    double fx, fy;
+    pair_force(p, ei, pi[2 * q], pi[2 * q + 1], vi[2 * q], vi[2 * q + 1], vdes[q], pj[2 * q], pj[2 * q + 1],
+               vj[2 * q], vj[2 * q + 1], fx, fy);
+    f[2 * q] = fx;
+    f[2 * q + 1] = fy;
+}
+
+// K7 density (simulations.py:469-487): per node, sum over active agents in agent order.  exp underflows to
+// exactly 0 beyond r_zero, so agents farther than that from the whole tile are culled without changing a bit.
+constexpr int DN_TX = 32, DN_TY = 8, DN_CHUNK = 256;
+__global__ void __launch_bounds__(256)
+density_kernel(int N, const double *__restrict__ ax, const double *__restrict__ ay, const uint8_t *__restrict__ status,
+               const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Vg, int Ny,
+               int Nx, double two_s2, double C, double r_zero, double *__restrict__ out) {
+    __shared__ double lx[DN_CHUNK], ly[DN_CHUNK];
+    __shared__ int wcnt[8];
+    const int ix = blockIdx.x * DN_TX + (threadIdx.x & 31), iy = blockIdx.y * DN_TY + (threadIdx.x >> 5);
+    const bool in = ix < Nx && iy < Ny;
+    const double x = in ? X[ix] : 0.0, y = in ? Y[iy] : 0.0;
+    const int jx0 = blockIdx.x * DN_TX, jx1 = min(jx0 + DN_TX, Nx) - 1, jy0 = blockIdx.y * DN_TY,
+              jy1 = min(jy0 + DN_TY, Ny) - 1;
+    const double bx0 = X[jx0] - r_zero, bx1 = X[jx1] + r_zero, by0 = Y[jy0] - r_zero, by1 = Y[jy1] + r_zero;
+    double d = 0.0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < N; base += DN_CHUNK) {
+        int a = base + threadIdx.x;
+        bool keep = false;
+        double px = 0, py = 0;
+        if (a < N && status[a]) {
+            px = ax[a]; py = ay[a];
+            keep = (px >= bx0 && px <= bx1 && py >= by0 && py <= by1) || !(px == px) || !(py == py);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[wid] = __popc(m);
+        __syncthreads();
+        int off = 0, total = 0;
+        for (int q = 0; q < 8; q++) { if (q < wid) off += wcnt[q]; total += wcnt[q]; }
+        if (keep) {
+            int pos = off + __popc(m & ((1u << lane) - 1));  // preserves agent order
+            lx[pos] = px; ly[pos] = py;
+        }
+        __syncthreads();
+        if (in)
+            for (int q = 0; q < total; q++) {
+                double cx = x - lx[q], cy = y - ly[q];
+                d += ocm_exp(-(cx * cx + cy * cy) / two_s2) / C;  // :480-483
+            }
+        __syncthreads();
+    }
+    if (in) {
+        size_t g = (size_t)iy * Nx + ix;
+        out[g] = (Vg[g] < 0) ? 0.0 : d;  // :485
+    }
+}
+
+template <class T>
+T *carve(char *&p, size_t n) {
+    T *r = reinterpret_cast<T *>(p);
+    p += ((n * sizeof(T) + 255) / 256) * 256;
+    return r;
+}
+
+}  // namespace
+
+extern "C" long long oc_wall_tiles_bytes(oc_ctx *ctx) {
+    if (!ctx) return 0;
+    return (long long)((ctx->Nx + WT - 1) / WT) * ((ctx->Ny + WT - 1) / WT);
+}
+
+extern "C" int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, double *v_min, void *stream) {
+    OC_ARG(ctx && d_V && d_tiles, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int nt = (int)oc_wall_tiles_bytes(ctx);
+    double *d_vm = nullptr;
+    OC_CUDA(cudaMalloc(&d_vm, sizeof(double) * nt));
+    tiles_kernel<<<(nt * 32 + 127) / 128, 128, 0, st>>>(d_V, ctx->Ny, ctx->Nx, d_tiles, d_vm);
+    oc::count_launch();
+    std::vector<double> h(nt);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d_vm, sizeof(double) * nt, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_vm);
+    OC_CUDA(e);
+    double vm = INFINITY;
+    for (double v : h) vm = std::min(vm, v);
+    if (v_min) *v_min = vm;
+    return OC_OK;
+}
+
+static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins, Ws &w, int **pinned) {
+    size_t need = 0;
+    auto al = [&](size_t b) { need += ((b + 255) / 256) * 256; };
+    for (int q = 0; q < 8; q++) al(sizeof(double) * N);
+    al(sizeof(double) * 2 * N);
+    al(sizeof(double) * 4 * std::max(n_doors, 1));
+    for (int q = 0; q < 7; q++) al(sizeof(int) * N);
+    al(sizeof(int) * (nbins + 1));
+    al(sizeof(int) * (nbins + 1));
+    al(N);
+    al(sizeof(KeyDev) * std::max(n_keys, 1));
+    al(sizeof(int) * 8);
+    if (ctx->gcfm_ws_bytes < need) {
+        if (ctx->gcfm_ws) cudaFree(ctx->gcfm_ws);
+        ctx->gcfm_ws = nullptr;
+        ctx->gcfm_ws_bytes = 0;
+        OC_CUDA(cudaMalloc(&ctx->gcfm_ws, need));
+        OC_CUDA(cudaMemset(ctx->gcfm_ws, 0, need));  // done-flags start at 0; tags are never 0
+        ctx->gcfm_ws_bytes = need;
+    } else if (ctx->gcfm_N != N || ctx->gcfm_nbins != nbins || ctx->gcfm_nkeys != n_keys || ctx->gcfm_ndoors != n_doors) {
+        OC_CUDA(cudaMemset(ctx->gcfm_ws, 0, ctx->gcfm_ws_bytes));  // layout changes: done-flags must restart at 0
+    }
+    ctx->gcfm_N = N; ctx->gcfm_nbins = nbins; ctx->gcfm_nkeys = n_keys; ctx->gcfm_ndoors = n_doors;
+    char *p = (char *)ctx->gcfm_ws;
+    // flags first so that it keeps its place (and contents) while N is unchanged
+    w.flags = carve<int>(p, N);
+    w.x0 = carve<double>(p, N); w.y0 = carve<double>(p, N); w.vx0 = carve<double>(p, N); w.vy0 = carve<double>(p, N);
+    w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
+    w.noise = carve<double>(p, 2 * (size_t)N);
+    w.doors = carve<double>(p, 4 * (size_t)std::max(n_doors, 1));
+    w.perm = carve<int>(p, N); w.rank = carve<int>(p, N); w.nzidx = carve<int>(p, N);
+    w.exit_mark = carve<int>(p, N); w.agent_bin = carve<int>(p, N); w.cell_agents = carve<int>(p, N);
+    w.bin_start = carve<int>(p, nbins + 1); w.bin_cursor = carve<int>(p, nbins + 1);
+    w.status0 = carve<uint8_t>(p, N);
+    w.keys = carve<KeyDev>(p, std::max(n_keys, 1));
+    w.counters = carve<int>(p, 8);
+    size_t pin = sizeof(int) * ((size_t)N + 8);
+    if (ctx->gcfm_pinned_bytes < pin) {
+        if (ctx->gcfm_pinned) cudaFreeHost(ctx->gcfm_pinned);
+        OC_CUDA(cudaMallocHost(&ctx->gcfm_pinned, pin));
+        ctx->gcfm_pinned_bytes = pin;
+    }
+    *pinned = (int *)ctx->gcfm_pinned;
+    return OC_OK;
+}
+
+static int g_tag = 0;
+
+extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx,
+                            double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
+                            const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
+                            int simu_step, int *exit_log, int *n_exit, void *stream) {
+    OC_ARG(ctx && prm && d_x && d_y && d_vx && d_vy && d_time && d_status && d_vdes && d_key && keys && perm,
+           "NULL argument");
+    OC_ARG(N >= 1 && n_keys >= 1 && n_noise >= 0 && n_noise <= N, "bad sizes");
+    OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // candidate bins: cell size (cutoff + margin)/2, search +-2 cells
+    const double reach = prm->cutoff + DISP_MARGIN;
+    const double cs = reach / 2.0, inv_cs = 1.0 / cs;
+    const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
+              nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
+    const int nbins = nbx * nby;
+    int n_doors = 0;
+    for (int k = 0; k < n_keys; k++) n_doors += keys[k].n_doors;
+    Ws w{};
+    int *pinned = nullptr;
+    int rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned);
+    if (rc) return rc;
+    // upload keys, doors, perm, noise
+    std::vector<KeyDev> hk(n_keys);
+    std::vector<double> hd(4 * (size_t)std::max(n_doors, 1));
+    int off = 0;
+    for (int k = 0; k < n_keys; k++) {
+        OC_ARG(keys[k].d_V && keys[k].d_wall_tiles, "key without potential / wall tiles");
+        hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy, keys[k].nt_opt,
+                       keys[k].d_vx ? keys[k].n_slices : 0, off, keys[k].n_doors, keys[k].v_min * 10e3};
+        for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
+        off += keys[k].n_doors;
+    }
+    OC_CUDA(cudaMemcpyAsync(w.keys, hk.data(), sizeof(KeyDev) * n_keys, cudaMemcpyHostToDevice, st));
+    OC_CUDA(cudaMemcpyAsync(w.doors, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
+    OC_CUDA(cudaMemcpyAsync(w.perm, perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    if (n_noise) OC_CUDA(cudaMemcpyAsync(w.noise, noise, sizeof(double) * 2 * n_noise, cudaMemcpyHostToDevice, st));
+    OC_CUDA(cudaMemsetAsync(w.bin_start, 0, sizeof(int) * (nbins + 1), st));
+    OC_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int) * (nbins + 1), st));
+    OC_CUDA(cudaMemsetAsync(w.exit_mark, 0, sizeof(int) * N, st));
+    OC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * 8, st));
+    if (++g_tag == 0x7fffffff) g_tag = 1;
+    const int tag = g_tag;
+    const int nb = (N + 255) / 256;
+    setup_kernel<<<nb, 256, 0, st>>>(N, d_x, d_y, d_vx, d_vy, d_status, w, inv_cs, nbx, nby);
+    scan_kernel<<<1, 1024, 0, st>>>(w.bin_start, nbins + 1);
+    scatter_kernel<<<nb, 256, 0, st>>>(N, w);
+    noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
+    prepare_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(*prm, N, w, ctx->d_X, ctx->d_Y, d_vdes, d_key, simu_step);
+    int n_sm = 0;
+    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    int occ = 0;
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, 0));
+    int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
+    sweep_kernel<<<grid, SWEEP_WARPS * 32, 0, st>>>(*prm, N, w, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key,
+                                                    tag, inv_cs, nbx, nby);
+    exit_compact_kernel<<<1, 1024, 0, st>>>(N, w, pinned);
+    oc::count_launch(7);
+    OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaStreamSynchronize(st));  // hk/hd lifetimes + host-visible exit log
+    int ne = pinned[0], fl = pinned[1];
+    if (n_exit) *n_exit = ne;
+    if (exit_log)
+        for (int q = 0; q < ne; q++) exit_log[q] = pinned[2 + q];
+    if (fl & 2) {
+        oc::set_error("more than %d agents within the repulsion cutoff of one agent", LIST_CAP);
+        return OC_ERR_ARG;
+    }
+    if (fl & 4) {
+        oc::set_error("an agent moved more than %.2f m in one step: outside the sweep's candidate search margin",
+                      DISP_MARGIN * 0.5);
+        return OC_ERR_ARG;
+    }
+    if (fl & 1) {
+        oc::set_error("agent position outside the sampler's index range (reference: IndexError / negative wrap)");
+        return OC_ERR_SAMPLER_RANGE;
+    }
+    return OC_OK;
+}
+
+extern "C" int oc_wall_force(oc_ctx *ctx, const oc_gcfm_params *prm, const double *d_V, int N, const double *d_x,
+                             const double *d_y, const double *d_vx, const double *d_vy, const double *d_vdes,
+                             double *d_fx, double *d_fy, long long *d_ind, void *stream) {
+    OC_ARG(ctx && prm && d_V && d_x && d_y && d_vx && d_vy && d_vdes && d_fx && d_fy, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *d_tiles = nullptr;
+    OC_CUDA(cudaMalloc(&d_tiles, (size_t)oc_wall_tiles_bytes(ctx)));
+    double vmin = 0;
+    int rc = oc_wall_tiles(ctx, d_V, d_tiles, &vmin, stream);
+    if (rc == OC_OK) {
+        wall_probe_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(*prm, N, ctx->d_X, ctx->d_Y, d_V, d_tiles, vmin * 10e3,
+                                                                 d_x, d_y, d_vx, d_vy, d_vdes, d_fx, d_fy, d_ind);
+        oc::count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { oc::set_error("wall_probe_kernel: %s", cudaGetErrorString(e)); rc = OC_ERR_CUDA; }
+    }
+    cudaFree(d_tiles);
+    return rc;
+}
+
+extern "C" int oc_pair_force(oc_ctx *ctx, const oc_gcfm_params *prm, int N, const double *d_pi, const double *d_vi,
+                             const double *d_vdes, const double *d_pj, const double *d_vj, double *d_f, void *stream) {
+    OC_ARG(ctx && prm && d_pi && d_vi && d_vdes && d_pj && d_vj && d_f, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    pair_probe_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, N, d_pi, d_vi, d_vdes, d_pj, d_vj, d_f);
+    oc::count_launch();
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+
+extern "C" int oc_density(oc_ctx *ctx, int N, const double *d_x, const double *d_y, const uint8_t *d_status,
+                          double sigma, double C, const double *d_Vglobal, double *d_out, void *stream) {
+    OC_ARG(ctx && d_Vglobal && d_out && (N == 0 || (d_x && d_y && d_status)), "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    const double two_s2 = 2 * (sigma * sigma);
+    // ocm_exp(x) == 0 exactly for x < -745.14: r^2/two_s2 > 745.2  =>  contribution is exactly 0.0
+    const double r_zero = std::sqrt(745.2 * two_s2) * (1.0 + 1e-9) + 1e-9;
+    dim3 grid((ctx->Nx + DN_TX - 1) / DN_TX, (ctx->Ny + DN_TY - 1) / DN_TY);
+    density_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(N, d_x, d_y, d_status, ctx->d_X, ctx->d_Y, d_Vglobal,
+                                                           ctx->Ny, ctx->Nx, two_s2, C, r_zero, d_out);
+    oc::count_launch();
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}

@@ -1,0 +1,596 @@
+// oc_hjb.cu -- HJB solve on sm_100a: RHS stencil (K1), RK45 stage kernels with the stage combination
+// fused into the stencil load (K2, stage-wise formulation), dense output + velocity epilogue (K3) and
+// the host-side replica of scipy's RK45 controller.
+//
+// Reference: optimals.py:124-206 (compute_optimal_velocity) + scipy 1.18.1 solve_ivp/RK45
+// (rk.py:14-71,85-180,538-565,715-737; common.py:63-134; ivp.py:604-621,659-728; base.py:179-210).
+//
+// Data layout in HBM: every field is a dense C-order (Ny,Nx) FP64 array.  Workspace = y, y_new, K[0..6],
+// coef (10 arrays).  coef = (V + g*m)/(mu*sigma^2), with NaN marking wall cells (V<0 -> k = 0, optimals.py:162).
+//
+// Error norm: per-tile partial sums -> per-tile-row sums (fixed order) -> sequential sum over tile rows on
+// the host.  The order depends only on global tile indices, so a row-band decomposition whose bands are
+// multiples of TY rows reproduces the single-GPU sum bit for bit.
+#include <cmath>
+#include <algorithm>
+
+#include "oc_common.h"
+
+namespace {
+
+// scipy/rk.py:541-565
+const double RK_A[6][5] = {{0, 0, 0, 0, 0},
+                           {1.0 / 5, 0, 0, 0, 0},
+                           {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                           {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                           {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                           {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+const double RK_B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+const double RK_P[7][4] = {
+    {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
+    {0, 0, 0, 0},
+    {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
+    {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
+    {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
+    {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
+    {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+
+constexpr int TX = 128, TY = 16, NTHREADS = 256;  // stage tile
+constexpr int SW = TX + 2;                        // smem row pitch (doubles)
+
+// y + h * sum_j a[j]*k[j]  (rk.py:63-64: dy = np.dot(K[:s].T, a[:s]) * h ; y + dy)
+struct Comb {
+    const double *y;
+    const double *k[6];
+    double a[6];
+    double h;
+};
+
+template <int N>
+__device__ __forceinline__ double comb_eval(const Comb &c, size_t idx) {
+    if (N == 0) return c.y[idx];
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) acc += __ldg(c.k[j] + idx) * c.a[j];
+    return c.y[idx] + acc * c.h;
+}
+
+struct ErrArgs {        // MODE 1 only
+    const double *k[6];  // K[0..5] (K[6] is the kernel's own output)
+    double e[7];
+    double h, rtol, atol;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    // fixed-order tree: warp shuffle, then warp 0 over the 8 warp sums
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NTHREADS / 32; i++) s += red[i];
+    }
+    return s;  // valid on thread 0
+}
+
+// MODE 0: kout = f(comb)                         (one RK stage, rk.py:62-64)
+// MODE 1: ynew = comb; kout = f(ynew); partial[tile] = sum((h*K.E/scale)^2)   (rk.py:66-69,146-147)
+template <int N, int MODE>
+__global__ void __launch_bounds__(NTHREADS)
+hjb_stage_kernel(Comb c, const double *__restrict__ coef, double *__restrict__ kout, double *__restrict__ ynew,
+                 ErrArgs ea, double *__restrict__ partial, int Ny, int Nx, double diff_over_dxdy) {
+    __shared__ double tile[(TY + 2) * SW];
+    __shared__ double red[NTHREADS / 32];
+    const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
+    for (int idx = threadIdx.x; idx < (TY + 2) * SW; idx += NTHREADS) {
+        int ly = idx / SW, lx = idx - ly * SW;
+        int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
+        // mirror ghosts (optimals.py:149-152): row -1 := row 1, row Ny := row Ny-2; same for columns
+        if (gy < 0) gy = 1;
+        if (gy == Ny) gy = Ny - 2;
+        if (gx < 0) gx = 1;
+        if (gx == Nx) gx = Nx - 2;
+        double v = 0.0;
+        if (gy < Ny && gx < Nx) v = comb_eval<N>(c, (size_t)gy * Nx + gx);
+        tile[idx] = v;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    const int lx = threadIdx.x & (TX - 1);
+    const int gx = tx0 + lx;
+#pragma unroll 2
+    for (int ly = threadIdx.x / TX; ly < TY; ly += NTHREADS / TX) {
+        int gy = ty0 + ly;
+        if (gy >= Ny || gx >= Nx) continue;
+        size_t g = (size_t)gy * Nx + gx;
+        const double *t = tile + (ly + 1) * SW + (lx + 1);
+        double C = t[0];
+        // optimals.py:154-160 (same summation order: up + down + left + right - 4C)
+        double lap = t[-SW] + t[SW] + t[-1] + t[1] - 4.0 * C;
+        double cf = coef[g];
+        double r = diff_over_dxdy * lap - cf * C;
+        if (cf != cf) r = 0.0;  // wall: optimals.py:162
+        kout[g] = r;
+        if (MODE == 1) {
+            ynew[g] = C;
+            double e = r * ea.e[6];
+#pragma unroll
+            for (int j = 5; j >= 0; j--)
+                if (j != 1) e += __ldg(ea.k[j] + g) * ea.e[j];
+            double sc = ea.atol + fmax(fabs(c.y[g]), fabs(C)) * ea.rtol;
+            double q = (e * ea.h) / sc;
+            acc += q * q;
+        }
+    }
+    if (MODE == 1) {
+        double s = block_sum(acc, red);
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// sum of the tile partials of one tile row, in fixed order -> rowsum[tile_row]
+__global__ void __launch_bounds__(NTHREADS) rowgroup_sum_kernel(const double *__restrict__ partial, int nbx,
+                                                                double *__restrict__ rowsum) {
+    __shared__ double red[NTHREADS / 32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nbx; i += NTHREADS) v += partial[(size_t)blockIdx.x * nbx + i];
+    double s = block_sum(v, red);
+    if (threadIdx.x == 0) rowsum[blockIdx.x] = s;
+}
+
+// select_initial_step norms (common.py:109-127): mode 0: (y/sc)^2 and (f/sc)^2 ; mode 1: ((f1-f0)/sc)^2
+__global__ void __launch_bounds__(NTHREADS)
+init_norm_kernel(const double *__restrict__ y, const double *__restrict__ f0, const double *__restrict__ f1,
+                 double rtol, double atol, int Ny, int Nx, double *__restrict__ partial, int mode) {
+    __shared__ double red[NTHREADS / 32];
+    const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
+    const int gx = tx0 + (threadIdx.x & (TX - 1));
+    double a0 = 0.0, a1 = 0.0;
+    for (int ly = threadIdx.x / TX; ly < TY; ly += NTHREADS / TX) {
+        int gy = ty0 + ly;
+        if (gy >= Ny || gx >= Nx) continue;
+        size_t g = (size_t)gy * Nx + gx;
+        double sc = atol + fabs(y[g]) * rtol;
+        if (mode == 0) {
+            double q0 = y[g] / sc, q1 = f0[g] / sc;
+            a0 += q0 * q0;
+            a1 += q1 * q1;
+        } else {
+            double q = (f1[g] - f0[g]) / sc;
+            a0 += q * q;
+        }
+    }
+    size_t nb = (size_t)gridDim.x * gridDim.y, b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    double s0 = block_sum(a0, red);
+    if (threadIdx.x == 0) partial[b] = s0;
+    __syncthreads();
+    if (mode == 0) {
+        double s1 = block_sum(a1, red);
+        if (threadIdx.x == 0) partial[nb + b] = s1;
+    }
+}
+
+// coef = (V<0) ? NaN : (V + g*m)/(mu*sigma^2); y = 1 (optimals.py:83)
+__global__ void prep_kernel(const double *__restrict__ V, const double *__restrict__ m, double g, double inv_den,
+                            size_t n, double *__restrict__ coef, double *__restrict__ y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = V[i];
+    double mm = m ? m[i] : 0.0;
+    coef[i] = (v < 0) ? __longlong_as_double(0x7ff8000000000000LL) : (v + g * mm) * inv_den;
+    if (y) y[i] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: dense output (rk.py:178-180,723-737) + vels (optimals.py:168-186), up to DMAX t_eval points per launch.
+constexpr int DTX = 64, DTY = 8, DSW = DTX + 2, DMAX = 6;
+constexpr int DCELLS = (DTY + 2) * DSW;                      // 660
+constexpr int DPER = (DCELLS + NTHREADS - 1) / NTHREADS;     // 3
+
+struct DenseArgs {
+    const double *yold;
+    const double *k[7];
+    double P[7][4];
+    double h;  // t - t_old (RkDenseOutput.h)
+    int n_emit;
+    double x[DMAX];       // (t_eval - t_old)/h
+    double *phi[DMAX];    // (Ny,Nx) slice or NULL
+    double *vx[DMAX];     // (Ny-2,Nx-2) slice or NULL
+    double *vy[DMAX];
+    double mu, lim, two_dx, two_dy;
+};
+
+__device__ __forceinline__ double clamp_lim(double p, double lim) {
+    // optimals.py:172: phi*(phi > lim) + lim*(phi < lim)
+    return p * (p > lim ? 1.0 : 0.0) + lim * (p < lim ? 1.0 : 0.0);
+}
+
+__device__ __forceinline__ void vels_point(double pc0, double pW, double pE, double pS, double pN, double mu,
+                                           double lim, double two_dx, double two_dy, double &ox, double &oy) {
+    // inputs already clamped once (:172); :174-186
+    double gx = (pE - pW) / two_dx;
+    double gy = (pN - pS) / two_dy;
+    double pc = clamp_lim(pc0, lim);  // :177 second clamp
+    double ux = gx / (mu * pc), uy = gy / (mu * pc);
+    double nr = sqrt(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));  // no FMA: bit-equal to numpy (:182)
+    double gt = nr > lim ? 1.0 : 0.0, lt = nr < lim ? 1.0 : 0.0;
+    double den = nr * gt + lt;
+    ox = (ux * gt) / den;
+    oy = (uy * gt) / den;
+}
+
+__global__ void __launch_bounds__(NTHREADS) hjb_dense_kernel(DenseArgs a, int Ny, int Nx) {
+    __shared__ double tile[DCELLS];
+    const int tx0 = blockIdx.x * DTX, ty0 = blockIdx.y * DTY;
+    double q[DPER][4], y0[DPER];
+#pragma unroll
+    for (int s = 0; s < DPER; s++) {
+        int idx = threadIdx.x + s * NTHREADS;
+        q[s][0] = q[s][1] = q[s][2] = q[s][3] = 0.0;
+        y0[s] = 0.0;
+        if (idx < DCELLS) {
+            int ly = idx / DSW, lx = idx - ly * DSW;
+            int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
+            if (gy >= 0 && gy < Ny && gx >= 0 && gx < Nx) {
+                size_t g = (size_t)gy * Nx + gx;
+                y0[s] = a.yold[g];
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    if (j == 1) continue;  // P[1,:] == 0
+                    double kj = __ldg(a.k[j] + g);
+#pragma unroll
+                    for (int p = 0; p < 4; p++) q[s][p] += kj * a.P[j][p];
+                }
+            }
+        }
+    }
+    for (int e = 0; e < a.n_emit; e++) {
+        double x = a.x[e];
+        double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;  // np.cumprod
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < DPER; s++) {
+            int idx = threadIdx.x + s * NTHREADS;
+            if (idx < DCELLS) {
+                double d = q[s][0] * p1 + q[s][1] * p2 + q[s][2] * p3 + q[s][3] * p4;
+                double ph = a.h * d + y0[s];
+                int ly = idx / DSW, lx = idx - ly * DSW;
+                int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
+                if (a.phi[e] && ly >= 1 && ly <= DTY && lx >= 1 && lx <= DTX && gy < Ny && gx < Nx)
+                    a.phi[e][(size_t)gy * Nx + gx] = ph;
+                tile[idx] = clamp_lim(ph, a.lim);
+            }
+        }
+        __syncthreads();
+        if (a.vx[e]) {
+#pragma unroll
+            for (int r = 0; r < (DTX * DTY) / NTHREADS; r++) {
+                int cell = threadIdx.x + r * NTHREADS;
+                int ly = cell / DTX, lx = cell - ly * DTX;
+                int gy = ty0 + ly, gx = tx0 + lx;
+                if (gy >= 1 && gy < Ny - 1 && gx >= 1 && gx < Nx - 1) {
+                    const double *t = tile + (ly + 1) * DSW + (lx + 1);
+                    double ox, oy;
+                    vels_point(t[0], t[-1], t[1], t[-DSW], t[DSW], a.mu, a.lim, a.two_dx, a.two_dy, ox, oy);
+                    size_t o = (size_t)(gy - 1) * (Nx - 2) + (gx - 1);
+                    a.vx[e][o] = ox;
+                    a.vy[e][o] = oy;
+                }
+            }
+        }
+    }
+}
+
+// standalone vels (optimals.py:168-186) for unit parity
+__global__ void __launch_bounds__(NTHREADS)
+vels_kernel(const double *__restrict__ phi, int Ny, int Nx, double mu, double lim, double two_dx, double two_dy,
+            double *__restrict__ vx, double *__restrict__ vy) {
+    int gx = blockIdx.x * 64 + (threadIdx.x & 63) + 1, gy = blockIdx.y * 4 + (threadIdx.x >> 6) + 1;
+    if (gy >= Ny - 1 || gx >= Nx - 1) return;
+    size_t g = (size_t)gy * Nx + gx;
+    double ox, oy;
+    vels_point(clamp_lim(phi[g], lim), clamp_lim(phi[g - 1], lim), clamp_lim(phi[g + 1], lim),
+               clamp_lim(phi[g - Nx], lim), clamp_lim(phi[g + Nx], lim), mu, lim, two_dx, two_dy, ox, oy);
+    size_t o = (size_t)(gy - 1) * (Nx - 2) + (gx - 1);
+    vx[o] = ox;
+    vy[o] = oy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct Solver {
+    oc_ctx *ctx;
+    cudaStream_t st;
+    int Ny, Nx, nbx, nby;
+    size_t n;
+    double *y, *ynew, *K[7], *coef;
+    double *partial, *rowsum_d, *rowsum_h;
+    double diff_over_dxdy;
+    int launches = 0;
+
+    template <int N, int MODE>
+    void launch_stage(const Comb &c, double *kout, double *yn, const ErrArgs &ea) {
+        dim3 grid(nbx, nby);
+        hjb_stage_kernel<N, MODE><<<grid, NTHREADS, 0, st>>>(c, coef, kout, yn, ea, partial, Ny, Nx, diff_over_dxdy);
+        launches++;
+    }
+    void stage(int N, const Comb &c, double *kout) {
+        ErrArgs ea{};
+        switch (N) {
+            case 0: launch_stage<0, 0>(c, kout, nullptr, ea); break;
+            case 1: launch_stage<1, 0>(c, kout, nullptr, ea); break;
+            case 2: launch_stage<2, 0>(c, kout, nullptr, ea); break;
+            case 3: launch_stage<3, 0>(c, kout, nullptr, ea); break;
+            case 4: launch_stage<4, 0>(c, kout, nullptr, ea); break;
+            case 5: launch_stage<5, 0>(c, kout, nullptr, ea); break;
+        }
+    }
+    // sum over tile rows of per-tile partials located at partial+off; host-visible after sync
+    int reduce_to_host(size_t off, double *out) {
+        rowgroup_sum_kernel<<<nby, NTHREADS, 0, st>>>(partial + off, nbx, rowsum_d);
+        launches++;
+        OC_CUDA(cudaMemcpyAsync(rowsum_h, rowsum_d, sizeof(double) * nby, cudaMemcpyDeviceToHost, st));
+        OC_CUDA(cudaStreamSynchronize(st));
+        double s = 0.0;
+        for (int i = 0; i < nby; i++) s += rowsum_h[i];  // fixed global order
+        *out = s;
+        return OC_OK;
+    }
+};
+
+int ensure_ws(oc_ctx *ctx, size_t n, int nbx, int nby) {
+    size_t need = 10 * n * sizeof(double);
+    if (ctx->hjb_ws_bytes < need) {
+        if (ctx->hjb_ws) cudaFree(ctx->hjb_ws);
+        ctx->hjb_ws = nullptr;
+        ctx->hjb_ws_bytes = 0;
+        if (cudaMalloc(&ctx->hjb_ws, need) != cudaSuccess) {
+            cudaGetLastError();
+            oc::set_error("cannot allocate %zu bytes of HJB workspace", need);
+            return OC_ERR_NOMEM;
+        }
+        ctx->hjb_ws_bytes = need;
+    }
+    size_t np = (size_t)2 * nbx * nby + nby;
+    if (ctx->hjb_partial_n < np) {
+        if (ctx->hjb_partial) cudaFree(ctx->hjb_partial);
+        OC_CUDA(cudaMalloc(&ctx->hjb_partial, np * sizeof(double)));
+        ctx->hjb_partial_n = np;
+    }
+    if (ctx->h_pinned_n < (size_t)nby + 16) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        OC_CUDA(cudaMallocHost(&ctx->h_pinned, ((size_t)nby + 16) * sizeof(double)));
+        ctx->h_pinned_n = (size_t)nby + 16;
+    }
+    return OC_OK;
+}
+
+}  // namespace
+
+extern "C" int oc_hjb_rhs(oc_ctx *ctx, const double *d_phi, const double *d_V, const double *d_m,
+                          const oc_hjb_params *prm, double *d_out, void *stream) {
+    OC_ARG(ctx && d_phi && d_V && prm && d_out, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    Solver s{};
+    s.ctx = ctx; s.st = (cudaStream_t)stream; s.Ny = ctx->Ny; s.Nx = ctx->Nx;
+    s.n = (size_t)s.Ny * s.Nx;
+    s.nbx = (s.Nx + TX - 1) / TX; s.nby = (s.Ny + TY - 1) / TY;
+    int rc = ensure_ws(ctx, s.n, s.nbx, s.nby);
+    if (rc) return rc;
+    s.coef = ctx->hjb_ws;
+    s.partial = ctx->hjb_partial;
+    double s2 = prm->sigma * prm->sigma;
+    s.diff_over_dxdy = (-0.5 * s2) / (ctx->dx * ctx->dy);
+    prep_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, s.st>>>(d_V, d_m, prm->g, 1.0 / (prm->mu * s2), s.n, s.coef, nullptr);
+    Comb c{};
+    c.y = d_phi;
+    s.stage(0, c, d_out);
+    oc::count_launch(2);
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+
+extern "C" int oc_hjb_vels(oc_ctx *ctx, const double *d_phi, const oc_hjb_params *prm, double *d_vx, double *d_vy,
+                           void *stream) {
+    OC_ARG(ctx && d_phi && prm && d_vx && d_vy, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    dim3 grid((ctx->Nx - 2 + 63) / 64, (ctx->Ny - 2 + 3) / 4);
+    vels_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(d_phi, ctx->Ny, ctx->Nx, prm->mu, prm->lim, 2 * ctx->dx,
+                                                             2 * ctx->dy, d_vx, d_vy);
+    oc::count_launch();
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+
+extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, const oc_hjb_params *prm, double T,
+                            const double *t_eval, int nt, double *d_phi, double *d_vx, double *d_vy,
+                            oc_hjb_stats *stats, double *trace_h, double *trace_err, int trace_cap, int *trace_n,
+                            void *stream) {
+    OC_ARG(ctx && d_V && prm && stats, "NULL argument");
+    OC_ARG(nt >= 1 && t_eval, "t_eval required");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    Solver s{};
+    s.ctx = ctx; s.st = (cudaStream_t)stream; s.Ny = ctx->Ny; s.Nx = ctx->Nx;
+    const size_t n = s.n = (size_t)s.Ny * s.Nx;
+    s.nbx = (s.Nx + TX - 1) / TX; s.nby = (s.Ny + TY - 1) / TY;
+    int rc = ensure_ws(ctx, n, s.nbx, s.nby);
+    if (rc) return rc;
+    double *ws = ctx->hjb_ws;
+    s.coef = ws; s.y = ws + n; s.ynew = ws + 2 * n;
+    for (int j = 0; j < 7; j++) s.K[j] = ws + (3 + j) * n;
+    s.partial = ctx->hjb_partial;
+    s.rowsum_d = ctx->hjb_partial + (size_t)2 * s.nbx * s.nby;
+    s.rowsum_h = ctx->h_pinned;
+    const double s2 = prm->sigma * prm->sigma;
+    s.diff_over_dxdy = (-0.5 * s2) / (ctx->dx * ctx->dy);
+    const double rtol = prm->rtol, atol = prm->atol;
+    const double sqrt_n = std::sqrt((double)n);
+    memset(stats, 0, sizeof(*stats));
+    int ntr = 0;
+    OC_CUDA(cudaEventRecord(ctx->ev0, s.st));
+
+    prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(d_V, d_m, prm->g, 1.0 / (prm->mu * s2), n, s.coef, s.y);
+    s.launches++;
+    const double t_bound = 0.0;
+    const double direction = (t_bound != T) ? (t_bound > T ? 1.0 : -1.0) : 1.0;
+    double t = T;
+    // rk.py:94: f = fun(t0, y0)
+    {
+        Comb c{};
+        c.y = s.y;
+        s.stage(0, c, s.K[0]);
+        stats->nfev++;
+    }
+    // common.py:109-134 select_initial_step
+    double h_abs;
+    {
+        double interval = std::fabs(t_bound - T);
+        if (interval == 0.0) h_abs = 0.0;
+        else {
+            dim3 grid(s.nbx, s.nby);
+            init_norm_kernel<<<grid, NTHREADS, 0, s.st>>>(s.y, s.K[0], nullptr, rtol, atol, s.Ny, s.Nx, s.partial, 0);
+            s.launches++;
+            double s0, s1, sq2;
+            if ((rc = s.reduce_to_host(0, &s0))) return rc;
+            if ((rc = s.reduce_to_host((size_t)s.nbx * s.nby, &s1))) return rc;
+            double d0 = std::sqrt(s0) / sqrt_n, d1 = std::sqrt(s1) / sqrt_n;
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = std::min(h0, interval);
+            Comb c{};
+            c.y = s.y; c.k[0] = s.K[0]; c.a[0] = 1.0; c.h = h0 * direction;  // y1 = y0 + h0*direction*f0
+            s.stage(1, c, s.K[1]);
+            stats->nfev++;
+            init_norm_kernel<<<grid, NTHREADS, 0, s.st>>>(s.y, s.K[0], s.K[1], rtol, atol, s.Ny, s.Nx, s.partial, 1);
+            s.launches++;
+            if ((rc = s.reduce_to_host(0, &sq2))) return rc;
+            double d2 = std::sqrt(sq2) / sqrt_n / h0;
+            double h1;
+            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = std::max(1e-6, h0 * 1e-3);
+            else h1 = std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
+            h_abs = std::min(std::min(100 * h0, h1), interval);
+        }
+    }
+    stats->h0 = h_abs;
+
+    int t_eval_i = nt;  // ivp.py:617-621
+    int n_out = 0, status = 1;
+    const double error_exponent = -1.0 / 5.0;
+    const size_t n_int = (size_t)(s.Ny - 2) * (s.Nx - 2);
+
+    while (status == 1) {
+        if (t == t_bound) { status = 0; break; }  // base.py:193-198
+        double min_step = 10 * std::fabs(std::nextafter(t, direction * INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool accepted = false, rejected = false;
+        double h = 0, t_new = 0;
+        while (!accepted) {
+            if (h_abs < min_step) { status = -1; break; }
+            h = h_abs * direction;
+            t_new = t + h;
+            if (direction * (t_new - t_bound) > 0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = std::fabs(h);
+            // rk_step (rk.py:61-69): K[0] = f already in place
+            for (int sgi = 1; sgi < 6; sgi++) {
+                Comb c{};
+                c.y = s.y; c.h = h;
+                for (int j = 0; j < sgi; j++) { c.k[j] = s.K[j]; c.a[j] = RK_A[sgi][j]; }
+                s.stage(sgi, c, s.K[sgi]);
+            }
+            {
+                // y_new = y + h*dot(K[:-1].T,B) with B[1]=0 dropped; K[6] = f(y_new); error partials
+                Comb c{};
+                c.y = s.y; c.h = h;
+                int m = 0;
+                for (int j = 0; j < 6; j++)
+                    if (j != 1) { c.k[m] = s.K[j]; c.a[m] = RK_B[j]; m++; }
+                ErrArgs ea{};
+                for (int j = 0; j < 6; j++) ea.k[j] = s.K[j];
+                for (int j = 0; j < 7; j++) ea.e[j] = RK_E[j];
+                ea.h = h; ea.rtol = rtol; ea.atol = atol;
+                s.launch_stage<5, 1>(c, s.K[6], s.ynew, ea);
+            }
+            stats->nfev += 6;
+            double se;
+            if ((rc = s.reduce_to_host(0, &se))) return rc;
+            double error_norm = std::sqrt(se) / sqrt_n;  // rk.py:147, common.py:63-65
+            if (trace_h && ntr < trace_cap) { trace_h[ntr] = h; trace_err[ntr] = error_norm; }
+            ntr++;
+            if (error_norm < 1) {  // rk.py:149-161
+                double factor = (error_norm == 0) ? 10.0 : std::min(10.0, 0.9 * std::pow(error_norm, error_exponent));
+                if (rejected) factor = std::min(1.0, factor);
+                h_abs *= factor;
+                accepted = true;
+                stats->n_accepted++;
+            } else {  // rk.py:162-165
+                h_abs *= std::max(0.2, 0.9 * std::pow(error_norm, error_exponent));
+                rejected = true;
+                stats->n_rejected++;
+            }
+        }
+        if (status == -1) break;
+        const double t_old = t;
+        if (direction * (t_new - t_bound) >= 0) status = 0;  // base.py:205-208
+
+        // ivp.py:715-728, direction < 0: first ascending index with t_eval_asc >= t_new
+        int lo = 0, hi = nt;
+        while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if (t_eval[nt - 1 - mid] < t_new) lo = mid + 1; else hi = mid;
+        }
+        const int t_eval_i_new = lo;
+        if (t_eval_i_new < t_eval_i) {
+            const double hh = t_new - t_old;
+            int ia = t_eval_i - 1;
+            while (ia >= t_eval_i_new) {
+                DenseArgs a{};
+                a.yold = s.y;
+                for (int j = 0; j < 7; j++) { a.k[j] = s.K[j]; for (int p = 0; p < 4; p++) a.P[j][p] = RK_P[j][p]; }
+                a.h = hh; a.mu = prm->mu; a.lim = prm->lim; a.two_dx = 2 * ctx->dx; a.two_dy = 2 * ctx->dy;
+                int e = 0;
+                bool any = false;
+                for (; e < DMAX && ia >= t_eval_i_new; ia--) {
+                    int kd = nt - 1 - ia;  // column of sol.y
+                    a.x[e] = (t_eval[kd] - t_old) / hh;
+                    a.phi[e] = d_phi ? d_phi + (size_t)kd * n : nullptr;
+                    int sl = nt - 1 - kd;  // vx_opt slice (optimals.py:200-204); column 0 (phi_T) has none
+                    bool has_v = d_vx && d_vy && kd >= 1;
+                    a.vx[e] = has_v ? d_vx + (size_t)sl * n_int : nullptr;
+                    a.vy[e] = has_v ? d_vy + (size_t)sl * n_int : nullptr;
+                    if (a.phi[e] || a.vx[e]) { any = true; e++; }
+                    n_out++;
+                }
+                a.n_emit = e;
+                if (any) {
+                    dim3 grid((s.Nx + DTX - 1) / DTX, (s.Ny + DTY - 1) / DTY);
+                    hjb_dense_kernel<<<grid, NTHREADS, 0, s.st>>>(a, s.Ny, s.Nx);
+                    s.launches++;
+                }
+            }
+            t_eval_i = t_eval_i_new;
+        }
+        // accept (rk.py:167-174): y <- y_new, f <- f_new (FSAL: pointer swaps)
+        t = t_new;
+        std::swap(s.y, s.ynew);
+        std::swap(s.K[0], s.K[6]);
+    }
+    OC_CUDA(cudaEventRecord(ctx->ev1, s.st));
+    OC_CUDA(cudaStreamSynchronize(s.st));
+    OC_CUDA(cudaGetLastError());
+    float ms = 0;
+    OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    stats->gpu_ms = ms;
+    stats->status = status;
+    stats->n_out = n_out;
+    stats->launches = s.launches;
+    oc::count_launch(s.launches);
+    if (trace_n) *trace_n = ntr;
+    if (status == -1) {
+        oc::set_error("RK45: required step size is less than spacing between numbers (t=%g)", t);
+        return OC_ERR_STEP_TOO_SMALL;
+    }
+    return OC_OK;
+}

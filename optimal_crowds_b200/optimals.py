@@ -1,0 +1,175 @@
+"""HJB optimal-velocity field -- mirror of the reference's ``optimals.optimals`` (optimals.py:11-250) whose
+solve runs on the GPU through liboc_b200.so (oc_hjb_solve).
+
+Same constructor, methods and attributes as the reference:
+``optimals(room, V, T, target)``, ``compute_optimal_velocity(t, m)``, ``choose_optimal_velocity(pos, t)``,
+``draw_optimal_velocity()``, ``vx_opt, vy_opt, nt_opt, V, phi_T, lim, ...``.
+
+Differences that do not change results:
+  * the field lives on the device (``d_vx``, ``d_vy``: torch CUDA tensors of shape (nt-1, Ny-2, Nx-2));
+    ``vx_opt`` / ``vy_opt`` are numpy views materialised on first access after a solve;
+  * ``V`` may be handed over as a numpy array (mutated in place like optimals.py:89-91) or a CUDA tensor.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def _load_config():
+    """optimals.py:36: 'optimal_crowds/config.json' relative to the CWD; falls back to the packaged copy."""
+    for p in ("optimal_crowds/config.json", os.path.join(os.path.dirname(__file__), "config.json")):
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.loads(f.read())
+    raise FileNotFoundError("config.json")
+
+
+def _load_room(room):
+    if isinstance(room, dict):
+        return room
+    with open(os.path.join(os.environ.get("OC_ROOMS_DIR", "rooms"), room + ".json")) as f:  # optimals.py:41
+        return json.loads(f.read())
+
+
+class optimals:
+    def __init__(self, room, V, T, target, _ctx=None, _config=None):
+        var_config = _config if _config is not None else _load_config()
+        var_room = _load_room(room)
+        self.room_length = var_room['room_length']
+        self.room_height = var_room['room_height']
+        self.grid_step = var_config['grid_step']
+        self.Ny, self.Nx = _lib.grid_shape(self.room_length, self.room_height, self.grid_step)  # optimals.py:55-56
+        self.dx = self.dy = self.grid_step
+        hp = var_config['hjb_params']
+        self.sigma, self.mu, self.g = hp['sigma'], hp['mu'], hp['g']
+        self.pot, self.pot_target = hp['wall_potential'], hp['target_potential']
+        self.dt = var_config['dt']
+        self.T = T
+        self.nt_opt = round(self.T / self.dt)  # optimals.py:76
+        self.target = target
+        self.lim = 10e-3                       # optimals.py:95
+        self._config = var_config
+        self._ctx = _ctx if _ctx is not None else _lib.Context(self.room_length, self.room_height, self.grid_step)
+        self._prm = _lib.hjb_params(var_config)
+        # potential: remap in place (optimals.py:89-91) and keep a device copy
+        import torch
+        if isinstance(V, np.ndarray):
+            V[V < 0] = self.pot
+            V[V > 0] = self.pot_target
+            self.V = V
+            self.d_V = self._ctx.to_device(V)
+        else:
+            V[V < 0] = self.pot
+            V[V > 0] = self.pot_target
+            self.d_V = V
+            self.V = None  # materialised on demand by V_host()
+        self.d_tiles, self.v_min = self._ctx.wall_tiles(self.d_V)
+        n_slices = max(self.nt_opt - 1, 0)
+        self.d_vx = torch.empty((n_slices, self.Ny - 2, self.Nx - 2), dtype=torch.float64, device=self.d_V.device)
+        self.d_vy = torch.empty_like(self.d_vx)
+        self._h_vx = self._h_vy = None
+        self.phi_T = np.zeros((self.Ny, self.Nx), dtype=float).reshape(self.Nx * self.Ny) + 1  # optimals.py:83,93
+        self.last_stats = None
+
+    # ---- lazily materialised host views -------------------------------------------------------------
+    @property
+    def X_opt(self):
+        return np.meshgrid(self._ctx.X, self._ctx.Y)[0]
+
+    @property
+    def Y_opt(self):
+        return np.meshgrid(self._ctx.X, self._ctx.Y)[1]
+
+    @property
+    def vx_opt(self):
+        if self._h_vx is None:
+            self._h_vx = self.d_vx.cpu().numpy()
+        return self._h_vx
+
+    @property
+    def vy_opt(self):
+        if self._h_vy is None:
+            self._h_vy = self.d_vy.cpu().numpy()
+        return self._h_vy
+
+    def V_host(self):
+        return self.V if self.V is not None else self.d_V.cpu().numpy()
+
+    # ---- optimals.py:124-206 --------------------------------------------------------------------------
+    def compute_optimal_velocity(self, t, m):
+        """Solve the HJB equation backward from T to 0 and fill the first nt-1 slices of the field.
+
+        ``m``: density as a numpy array (Ny,Nx), a CUDA tensor, or None / scalar 0 for no density."""
+        import torch
+        self.t = t
+        self.nt_opt = round((self.T - self.t) / self.dt)  # optimals.py:140
+        nt = self.nt_opt
+        if nt < 1:
+            # reference: np.linspace(T,0,0) -> solve_ivp raises on an empty t_eval
+            raise ValueError("Values in `t_eval` are not within `t_span`.")
+        if m is None or (np.isscalar(m) and m == 0):
+            d_m = None
+        elif isinstance(m, np.ndarray):
+            d_m = self._ctx.to_device(np.asarray(m, dtype=np.float64).reshape(self.Ny, self.Nx))
+        else:
+            d_m = m.reshape(self.Ny, self.Nx)
+        if nt - 1 > self.d_vx.shape[0]:
+            raise IndexError("re-solve asks for more slices than the field was allocated for")  # as numpy would
+        res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_phi=False, want_vel=nt > 1,
+                                  out_vx=self.d_vx, out_vy=self.d_vy)
+        self._h_vx = self._h_vy = None
+        self.last_stats = res["stats"]
+        if res["rc"] == _lib.OC_ERR_STEP_TOO_SMALL:
+            # the reference ignores sol.status and then fails in its fill loop on the short sol.y (App. C #15)
+            raise IndexError("RK45 stopped early (required step size is less than spacing between numbers)")
+        print('Optimal trajectories have been learnt for ' + self.target)  # optimals.py:206
+
+    # ---- optimals.py:212-250 --------------------------------------------------------------------------
+    def choose_optimal_velocity(self, pos, t):
+        """Host-side sampler with the reference's exact index semantics (diagonal pair, one-node shift).
+        The GCFM step uses the device version of this function inside liboc_b200.so."""
+        x, y = pos
+        if t >= self.nt_opt - 1:
+            return np.array((0., 0.), dtype=float)
+        cols = self._axis_nodes(x, self.room_length, self.dx, self.Nx)
+        rows = self._axis_nodes(y, self.room_height, self.dy, self.Ny)
+        # numpy pairs two index lists element-wise; a scalar broadcasts against a list
+        n = max(len(rows), len(cols))
+        rows = rows * (n // len(rows))
+        cols = cols * (n // len(cols))
+        sx, sy = self.d_vx[t], self.d_vy[t]  # IndexError for t beyond the allocation, like numpy
+        H, W = sx.shape
+        for i, j in zip(rows, cols):
+            if not (-H <= i < H and -W <= j < W):
+                raise IndexError(f"index ({i},{j}) is out of bounds for the field of shape ({H},{W})")
+        import torch
+        ii = torch.tensor(rows, device=sx.device); jj = torch.tensor(cols, device=sx.device)
+        vals = torch.stack([sx[ii, jj], sy[ii, jj]]).cpu().numpy()
+        return np.array((np.mean(vals[0]), np.mean(vals[1])), dtype=float)
+
+    @staticmethod
+    def _axis_nodes(c, extent, step, n_nodes):
+        if c < extent - step:
+            k = int(c // step)
+            return [k, k + 1] if c > step else [k]
+        return [n_nodes - 3]
+
+    # ---- optimals.py:97-118 ---------------------------------------------------------------------------
+    def draw_optimal_velocity(self):
+        """Quiver plot of the field per time slice (needs matplotlib; visualisation only)."""
+        import matplotlib.pyplot as plt
+        X, Y = self.X_opt[1:-1, 1:-1], self.Y_opt[1:-1, 1:-1]
+        for i in range(self.nt_opt - 1):
+            if i < self.nt_opt - 2:
+                plt.quiver(X, Y, self.vx_opt[i], self.vy_opt[i])
+            else:
+                plt.plot()
+            plt.xlim([0, self.room_length])
+            plt.ylim([0, self.room_height])
+            plt.title('t = {:.2f}s'.format(i * self.dt))
+            plt.show()

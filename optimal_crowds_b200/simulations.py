@@ -1,0 +1,373 @@
+"""Simulation driver -- mirror of the reference's ``simulations.simulation`` (simulations.py:18-703).
+
+Same public surface: ``simulation(room, T, recompute=False)``, ``run(verbose, draw, mode)``,
+``step(dt, verbose)``, ``draw_history(mode)``, ``draw(mode)``, ``draw_final_trajectories()``,
+``evac_times(draw)``, ``initial_positions()``, ``gaussian_density(sigma)``, ``create_potential(var_room,
+targets)``, ``write_history(time)`` and the attributes the reference's users read (``agents, targets, Vs, V,
+N, inside, time, simu_step, history, ...``).  File formats (rooms/*.json, config.json), CWD-relative paths,
+printed messages and the numpy legacy global RNG stream are the reference's.
+
+What runs where: JSON parsing, the RNG, the run loop, history bookkeeping and plotting stay on the host;
+rasterisation, the HJB solve, the density splat and the whole GCFM step run in liboc_b200.so on the GPU.
+The crowd lives on the device as struct-of-arrays; ``self.agents`` are ``pedestrians.ped`` views.
+"""
+from __future__ import annotations
+
+import json
+import warnings
+
+import numpy as np
+
+from . import _lib, optimals, pedestrians
+from .optimals import _load_config, _load_room
+
+warnings.filterwarnings("ignore")  # simulations.py:15
+
+
+class simulation:
+
+    def __init__(self, room, T, recompute=False, record=True):
+        import torch
+        self.recompute = recompute
+        var_config = _load_config()       # simulations.py:42
+        var_room = _load_room(room)       # simulations.py:47
+        self._config, self._room = var_config, var_room
+        self.room_length = var_room['room_length']
+        self.room_height = var_room['room_height']
+        self.grid_step = var_config['grid_step']
+        self._ctx = _lib.Context(self.room_length, self.room_height, self.grid_step)
+        self.Ny, self.Nx = self._ctx.Ny, self._ctx.Nx       # simulations.py:63-64
+        self.dx = self.dy = self.grid_step
+        self.sigma_convolution = var_config['sigma_convolution']
+        self.pot = var_config['hjb_params']['wall_potential']
+        self.lim = 10e-3
+        self.T = T
+        self.time = 0.
+        self.simu_step = 0
+        self.dt = var_config['dt']
+        self.relaxation = var_config['relaxation']
+        self.noise_intensity = var_config['hjb_params']['sigma']
+        self.a_min = var_config['b_min']                    # simulations.py:88
+        self.tau_a, self.b_min, self.b_max = var_config['tau_a'], var_config['b_min'], var_config['b_max']
+        self.eta, self.eta_walls = var_config['eta'], var_config['eta_walls']
+        self.repulsion_cutoff = var_config['repulsion_cutoff']
+        self.v_max = var_config['v_max']
+        self.recompute_step = var_config['recompute_frequency']
+        self.history = {}
+        self._record = record
+        self._gcfm_prm = _lib.gcfm_params(var_config, self.room_length, self.room_height, self.Ny, self.Nx)
+        diag = float(np.hypot(self.room_length, self.room_height))
+        if abs(self.pot) * 10e3 <= diag:
+            raise NotImplementedError("wall search assumes |wall_potential|*10e3 exceeds the room diagonal")
+
+        # crowd initialisation (simulations.py:104-160), same RNG consumption
+        N = 0
+        self.targets = {}
+        self.Vs = {}
+        self.V = np.zeros((self.Ny, self.Nx)) + 1
+        self.place_ped = np.zeros((self.Ny, self.Nx))
+        r_in = 0.2
+        xs_all, ys_all, vdes_all, key_all, agents = [], [], [], [], []
+        X1, Y1 = self._ctx.X, self._ctx.Y
+        for box_name in var_room['initial_boxes']:
+            box = var_room['initial_boxes'][box_name]
+            targets = box[5:]
+            key = ' or '.join(targets)
+            V = self.create_potential(var_room, targets)
+            self.Vs[key] = V
+            self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config)
+            self.V += V
+            loc_N = int(box[4] * box[2] * box[3])
+            N += loc_N
+            xs = np.empty(loc_N)
+            ys = np.empty(loc_N)
+            placed = 0
+            while placed < loc_N:
+                x_in = np.random.uniform(box[0] - box[2] / 2, box[0] + box[2] / 2, 1)
+                y_in = np.random.uniform(box[1] - box[3] / 2, box[1] + box[3] / 2, 1)
+                # nodes within r_in of the trial point: only a small window of the grid can qualify, and on
+                # that window the test below is the reference's expression (simulations.py:132-135) verbatim
+                j0, j1 = self._window(X1, x_in[0], r_in)
+                i0, i1 = self._window(Y1, y_in[0], r_in)
+                near = np.sqrt((X1[None, j0:j1] - x_in) ** 2 + (Y1[i0:i1, None] - y_in) ** 2) < r_in
+                sub = self.place_ped[i0:i1, j0:j1]
+                if 1 in sub[near]:
+                    continue
+                sub[near] = 1
+                xs[placed] = x_in[0]
+                ys[placed] = y_in[0]
+                placed += 1
+            v_des_all = np.random.normal(1.34, 0.26, size=loc_N)
+            kid = list(self.targets).index(key)
+            for i in range(loc_N):
+                a = pedestrians.ped(None, None, self.grid_step, self.Vs[key], key, var_room['targets'], targets,
+                                    xs[i], ys[i], 0, 0, self.room_length, self.room_height, v_des_all[i],
+                                    self.a_min, self.tau_a, self.b_min, self.b_max, self.eta, self.eta_walls)
+                a._bind(self, len(agents))
+                agents.append(a)
+            xs_all.append(xs); ys_all.append(ys); vdes_all.append(v_des_all)
+            key_all.append(np.full(loc_N, kid, dtype=np.int32))
+        self.V[self.V > np.min(self.V)] = 0                 # simulations.py:157
+        self.N = N
+        self.inside = self.N
+        self.agents = np.array(agents, dtype=object)
+
+        cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt)
+        x0, y0 = cat(xs_all, np.float64), cat(ys_all, np.float64)
+        self._h_vdes = cat(vdes_all, np.float64)
+        self._h_key = cat(key_all, np.int32)
+        self._h_status = np.ones(N, dtype=np.uint8)
+        self._h_time0 = np.zeros(N)
+        ctx = self._ctx
+        self._state = dict(x=ctx.to_device(x0), y=ctx.to_device(y0), vx=ctx.to_device(np.zeros(N)),
+                           vy=ctx.to_device(np.zeros(N)), time=ctx.to_device(np.zeros(N)),
+                           status=ctx.to_device(self._h_status.copy()))
+        self._d_vdes = ctx.to_device(self._h_vdes)
+        self._d_key = ctx.to_device(self._h_key)
+        self._d_Vglobal = ctx.to_device(self.V)
+        # per-step host record of (x, y, vx, vy); row k = state after k steps (ped.traj / ped.vels views)
+        self._track = [np.column_stack([x0, y0, np.zeros(N), np.zeros(N)])]
+        self._exit_step = np.full(N, -1, dtype=np.int64)   # step index at which the agent left
+        self._exit_order = []                               # agent ids in exit order over the whole run
+        self._h_now = self._track[0]
+        self._h_timev = np.zeros(N)
+        print('ABM simulation room created!')               # simulations.py:162
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    @staticmethod
+    def _window(coords, c, r):
+        step = coords[1] - coords[0]
+        lo = int(np.floor((c - r) / step)) - 2
+        hi = int(np.ceil((c + r) / step)) + 3
+        return max(lo, 0), min(hi, len(coords))
+
+    @property
+    def X_opt(self):
+        return np.meshgrid(self._ctx.X, self._ctx.Y)[0]
+
+    @property
+    def Y_opt(self):
+        return np.meshgrid(self._ctx.X, self._ctx.Y)[1]
+
+    def _sync_host(self):
+        st = self._state
+        import torch
+        packed = torch.stack([st["x"], st["y"], st["vx"], st["vy"], st["time"]], dim=1).cpu().numpy()
+        self._h_now = packed[:, :4]
+        self._h_timev = packed[:, 4].copy()
+
+    def _agent_now(self, i):
+        r = self._h_now[i]
+        return np.array(r[:2], dtype=float), np.array(r[2:], dtype=float)
+
+    def _agent_time(self, i):
+        t = self._h_timev[i]
+        return 0 if t == 0 and self.simu_step == 0 else float(t)
+
+    def _agent_track(self, i, which):
+        """list of per-step positions (which=0) or velocities (which=1) up to the agent's exit (ped.traj/vels)."""
+        last = self._exit_step[i] + 1 if self._exit_step[i] >= 0 else len(self._track) - 1
+        sl = slice(0, 2) if which == 0 else slice(2, 4)
+        return [np.array(self._track[k][i, sl], dtype=float) for k in range(min(last, len(self._track) - 1) + 1)]
+
+    def _set_status(self, i, v):
+        self._h_status[i] = 1 if v else 0
+        self._state["status"][i] = int(self._h_status[i])
+
+    def _keys(self):
+        out = []
+        for key, opt in self.targets.items():
+            doors = np.array([self._room['targets'][t] for t in key.split(' or ')], dtype=np.float64) \
+                if key else np.zeros((0, 4))
+            out.append(dict(V=opt.d_V, tiles=opt.d_tiles, v_min=opt.v_min, vx=opt.d_vx, vy=opt.d_vy,
+                            nt_opt=opt.nt_opt, doors=self._doors[key]))
+        return out
+
+    @property
+    def _doors(self):
+        if not hasattr(self, "_doors_cache"):
+            self._doors_cache = {}
+            for box in self._room['initial_boxes'].values():
+                tg = box[5:]
+                self._doors_cache[' or '.join(tg)] = np.array([self._room['targets'][t] for t in tg],
+                                                              dtype=np.float64).reshape(-1, 4)
+        return self._doors_cache
+
+    # ---- simulations.py:252-342 ----------------------------------------------------------------------
+    def step(self, dt, verbose=False):
+        """One GCFM step for every agent still inside, with the reference's sequential sweep semantics."""
+        if dt != self.dt:
+            prm = _lib.gcfm_params(dict(self._config, dt=dt), self.room_length, self.room_height, self.Ny, self.Nx)
+        else:
+            prm = self._gcfm_prm
+        if self.N > 0:
+            perm = np.random.choice(np.arange(self.N), self.N, replace=False)      # simulations.py:271
+            n_active = int(self._h_status.sum())
+            # one pair per active agent in sweep order == N calls of normal(size=2)   simulations.py:303
+            noise = np.random.normal(size=(n_active, 2)) if n_active else np.zeros((0, 2))
+            exits, rc = self._ctx.gcfm_step(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm, noise,
+                                            self.simu_step)
+            if rc == _lib.OC_ERR_SAMPLER_RANGE:
+                raise IndexError("agent position outside the velocity field's index range "
+                                 "(the reference raises here too: optimals.py:247)")
+            for a in exits:
+                self._h_status[a] = 0
+                self._exit_step[a] = self.simu_step
+                self._exit_order.append(int(a))
+            self.inside += -len(exits)
+            if self._record:
+                self._sync_host()
+                self._track.append(np.array(self._h_now))
+        self.time += dt
+        self.simu_step += 1
+        if verbose:
+            print('t = {:.2f}s exit = {}/{}'.format(self.time, self.N - self.inside, self.N) + 10 * ' ', end='\n')
+
+    # ---- simulations.py:344-399 ----------------------------------------------------------------------
+    def evac_times(self, draw=False):
+        if self.inside > 0:
+            raise ValueError('There are still people inside!')
+        if not self._record:
+            self._sync_host()
+        times = np.array(self._h_timev, dtype=float)
+        if draw:
+            import matplotlib.pyplot as plt
+            plt.figure(figsize=(self.room_length, self.room_height))
+            xs, ys = self.initial_positions()
+            plt.scatter(xs, ys, c=times)
+            plt.xlim(0, self.room_length)
+            plt.ylim(0, self.room_height)
+            plt.title('Evacuation time')
+            plt.colorbar()
+        else:
+            return times
+
+    def initial_positions(self):
+        return np.array(self._track[0][:, 0], dtype=float), np.array(self._track[0][:, 1], dtype=float)
+
+    # ---- simulations.py:401-451 ----------------------------------------------------------------------
+    def run(self, verbose=False, draw=False, mode='scatter'):
+        print(f"Computing trajectories at time {self.time}")
+        self._solve_all()
+        while (self.inside > 0) & (self.time < self.T):
+            if self.recompute and (self.simu_step % self.recompute_step == 0) and self.simu_step > 0:
+                print(f"Computing trajectories at time {self.time}")
+                self._solve_all()
+            self.write_history(self.time)
+            self.step(self.dt, verbose=verbose)
+            if draw and (self.simu_step % 10) == 0:
+                import matplotlib.pyplot as plt
+                self.draw(mode)
+                plt.show()
+        if self.inside == 0:
+            print('Evacuation complete in {:.2f}s!'.format(self.time))
+        else:
+            print('Evacuation failed!' + 10 * ' ')
+
+    def _solve_all(self):
+        # simulations.py:424-425 / :434-435: density * (simu_step > 0); the product with False is all zeros,
+        # so at step 0 the splat is skipped and no density is passed (identical input to the solver)
+        d_m = self._density_device(self.sigma_convolution) if self.simu_step > 0 else None
+        for target in self.targets:
+            self.targets[target].compute_optimal_velocity(self.time, d_m)
+
+    # ---- simulations.py:453-487 ----------------------------------------------------------------------
+    def _density_device(self, sigma):
+        st = self._state
+        return self._ctx.density(st["x"], st["y"], st["status"], sigma, self._d_Vglobal)
+
+    def gaussian_density(self, sigma):
+        return self._density_device(sigma).cpu().numpy()
+
+    # ---- simulations.py:516-576 ----------------------------------------------------------------------
+    def create_potential(self, var_room, targets):
+        tg = [var_room['targets'][t] for t in targets]
+        V = self._ctx.rasterise(list(var_room['walls'].values()), list(var_room['holes'].values()),
+                                list(var_room['cylinders'].values()), tg, remap=False)
+        return V.cpu().numpy()
+
+    # ---- simulations.py:579-589 ----------------------------------------------------------------------
+    def write_history(self, time):
+        frame = []
+        now = self._h_now
+        keys = list(self.targets)
+        for i in np.nonzero(self._h_status)[0]:
+            frame.append([np.array(now[i, :2], dtype=float), np.array(now[i, 2:], dtype=float),
+                          keys[self._h_key[i]], self._h_vdes[i]])
+        frame.append(self.gaussian_density(self.sigma_convolution))
+        self.history[time] = frame
+
+    # ---- plotting (visualisation only; needs matplotlib / seaborn) ---------------------------------------
+    def _ellipse_axes(self, vel, v_des):
+        speed = np.linalg.norm(vel)
+        a = self.a_min + self.tau_a * speed
+        b = self.b_max - (self.b_max - self.b_min) * np.minimum(speed / v_des, 1)
+        return a, b
+
+    def _draw_frame(self, frame, mode, title):
+        import matplotlib.pyplot as plt
+        from matplotlib.patches import Ellipse
+        import seaborn as sns
+        keys = list(self.targets)
+        colors = sns.color_palette(n_colors=len(keys))
+        fig = plt.figure(figsize=(self.room_length, self.room_height))
+        ax = plt.gca()
+        if mode == 'density':
+            plt.imshow(np.flip(frame[-1], axis=0), extent=[0, self.room_length, 0, self.room_height])
+        else:
+            plt.imshow(np.flip(self.V, axis=0), extent=[0, self.room_length, 0, self.room_height])
+            for pos, vel, target, v_des in frame[:-1]:
+                c = colors[keys.index(target)]
+                if mode == 'arrows':
+                    plt.quiver(pos[0], pos[1], vel[0], vel[1], color=c)
+                else:
+                    a, b = self._ellipse_axes(vel, v_des)
+                    ang = np.degrees(np.arctan2(vel[1], vel[0]))
+                    ax.add_patch(Ellipse((pos[0], pos[1]), 2 * a, 2 * b, angle=ang, color=c))
+        plt.xlim([0, self.room_length])
+        plt.ylim([0, self.room_height])
+        plt.title(title)
+        return fig
+
+    def _current_frame(self):
+        now, keys = self._h_now, list(self.targets)
+        frame = [[np.array(now[i, :2]), np.array(now[i, 2:]), keys[self._h_key[i]], self._h_vdes[i]]
+                 for i in np.nonzero(self._h_status)[0]]
+        frame.append(self.gaussian_density(self.sigma_convolution))
+        return frame
+
+    def draw(self, mode='scatter'):
+        """simulations.py:164-250"""
+        import matplotlib.pyplot as plt
+        self._draw_frame(self._current_frame(), mode,
+                         't = {:.2f}s exit = {}/{}'.format(self.time, self.N - self.inside, self.N))
+        plt.show()
+
+    def draw_history(self, mode='scatter'):
+        """simulations.py:591-703: every 10th recorded frame, then the current state."""
+        import matplotlib.pyplot as plt
+        times = list(self.history.keys())
+        for j, t in enumerate(times):
+            if j % 10 == 0 or j == len(times) - 1:
+                self._draw_frame(self.history[t], mode, 't = {:.2f}s'.format(t))
+                plt.show()
+        self.draw(mode)
+
+    def draw_final_trajectories(self):
+        """simulations.py:489-514"""
+        import matplotlib.pyplot as plt
+        from matplotlib.patches import Patch
+        import seaborn as sns
+        keys = list(self.targets)
+        colors = sns.color_palette(n_colors=len(keys))
+        plt.figure(figsize=(self.room_length, self.room_height))
+        for i in range(self.N):
+            traj = np.array(self.agents[i].traj, dtype=float)
+            plt.plot(traj[:, 0], traj[:, 1], color=colors[self._h_key[i]])
+        plt.imshow(np.flip(self.V, axis=0), extent=[0, self.room_length, 0, self.room_height])
+        plt.xlim([0, self.room_length])
+        plt.ylim([0, self.room_height])
+        plt.title('{}/{} pedestrians evacuated in {:.2f}s'.format(self.N - self.inside, self.N, self.time))
+        plt.legend(handles=[Patch(color=colors[i], label=keys[i]) for i in range(len(keys))], loc='upper right',
+                   frameon=False)
+        plt.show()

@@ -1,0 +1,260 @@
+"""GPU parity: GCFM path (K4 wall search, K5 prepare, K6 sweep), density (K7) and rasteriser (K8)
+through the C ABI.
+
+Bars: bit-exact against the CPU oracle O2 (oracle/oc_oracle_gcfm.c) -- positions, velocities, exit sets and
+exit ORDER over whole runs; bit-exact argmin indices and masks against the reference goldens; <= 1e-12
+against the reference goldens (O1) for forces and teacher-forced steps.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden, room_grid
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(room, cfg):
+    from optimal_crowds_b200 import _lib
+    ctx = _lib.Context(room["room_length"], room["room_height"], cfg["grid_step"])
+    prm = _lib.gcfm_params(cfg, room["room_length"], room["room_height"], ctx.Ny, ctx.Nx)
+    return ctx, prm
+
+
+def test_pair_force_bitexact_vs_oracle_and_close_to_reference(cfg):
+    from oracle import cpu_oracle as co
+    u = golden("units")
+    room = json.loads(str(u["room"]))
+    ctx, prm = _setup(room, cfg)
+    P = co.gcfm_params(cfg, room["room_length"], room["room_height"], ctx.Ny, ctx.Nx)
+    f = ctx.pair_force(prm, ctx.to_device(u["pair_pi"]), ctx.to_device(u["pair_vi"]), ctx.to_device(u["pair_vdes"]),
+                       ctx.to_device(u["pair_pj"]), ctx.to_device(u["pair_vj"])).cpu().numpy()
+    o2 = np.array([co.pair_force(P, u["pair_pi"][q], u["pair_vi"][q], u["pair_vdes"][q], u["pair_pj"][q],
+                                 u["pair_vj"][q]) for q in range(len(f))])
+    assert np.array_equal(f, o2)
+    assert np.abs(f - u["pair_out"]).max() < 1e-12
+    ctx.close()
+
+
+def test_wall_force_and_argmin(cfg):
+    from oracle import cpu_oracle as co
+    u = golden("units")
+    room = json.loads(str(u["room"]))
+    ctx, prm = _setup(room, cfg)
+    P = co.gcfm_params(cfg, room["room_length"], room["room_height"], ctx.Ny, ctx.Nx)
+    V = ctx.to_device(u["wall_V"])
+    p, v = u["wall_p"], u["wall_v"]
+    fx, fy, ind = ctx.wall_force(prm, V, ctx.to_device(p[:, 0].copy()), ctx.to_device(p[:, 1].copy()),
+                                 ctx.to_device(v[:, 0].copy()), ctx.to_device(v[:, 1].copy()),
+                                 ctx.to_device(u["wall_vdes"]))
+    assert np.array_equal(ind.cpu().numpy(), u["wall_ind"])  # bit-exact np.argmin incl. ties
+    f = np.column_stack([fx.cpu().numpy(), fy.cpu().numpy()])
+    assert np.abs(f - u["wall_out"]).max() < 1e-12
+    o2 = np.array([co.wall_force(P, ctx.X, ctx.Y, u["wall_V"], p[q], v[q], u["wall_vdes"][q])[:2] for q in range(len(p))])
+    assert np.array_equal(f, o2)
+    ctx.close()
+
+
+def test_wall_argmin_far_from_walls(cfg):
+    """big empty room: the search must expand many rings and still return np.argmin's first index."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    Nx, Ny = 700, 500
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    ctx = _lib.Context(L, H, 0.05)
+    prm = _lib.gcfm_params(cfg, L, H, Ny, Nx)
+    V = np.zeros((Ny, Nx)); V[0, :] = V[-1, :] = V[:, 0] = V[:, -1] = -100
+    V[250, 350] = -100  # a single interior wall node
+    V[100:104, -1] = 1
+    rng = np.random.RandomState(0)
+    n = 300
+    p = np.column_stack([rng.uniform(0.1, L - 0.1, n), rng.uniform(0.1, H - 0.1, n)])
+    p[:40] = np.column_stack([ctx.X[rng.randint(1, Nx - 1, 40)] + 0.025, ctx.Y[rng.randint(1, Ny - 1, 40)] + 0.025])
+    p[40:50] = [L / 2, H / 2]  # equidistant-ish from several frame nodes
+    z = np.zeros(n)
+    _, _, ind = ctx.wall_force(prm, ctx.to_device(V), ctx.to_device(p[:, 0].copy()), ctx.to_device(p[:, 1].copy()),
+                               ctx.to_device(z), ctx.to_device(z), ctx.to_device(z + 1.3))
+    ref = np.array([co.lib().oco_wall_argmin(co._p(ctx.X), co._p(ctx.Y), co._p(V), Ny, Nx,
+                                             co.C.c_double(p[q, 0]), co.C.c_double(p[q, 1])) for q in range(n)])
+    assert np.array_equal(ind.cpu().numpy(), ref)
+    ctx.close()
+
+
+def _load_keys(g, room, ctx, Ny, Nx, step_fields=None):
+    keys_dev, keys_cpu = [], []
+    from oracle import cpu_oracle as co
+    for kid in range(int(g["n_keys"])):
+        key = str(g[f"k{kid}_key"])
+        doors = np.array([room["targets"][t] for t in key.split(" or ")], dtype=np.float64)
+        V = g[f"k{kid}_V"]
+        nt = int(g[f"k{kid}_nt"])
+        if step_fields is not None:
+            s = step_fields
+            vx = np.zeros((s + 1, Ny - 2, Nx - 2)); vy = np.zeros_like(vx)
+            vx[s] = g[f"k{kid}_vx_step{s}"]; vy[s] = g[f"k{kid}_vy_step{s}"]
+        else:
+            vx = vy = None
+        Vd = ctx.to_device(V)
+        tiles, vmin = ctx.wall_tiles(Vd)
+        keys_dev.append(dict(V=Vd, tiles=tiles, v_min=vmin, vx=None if vx is None else ctx.to_device(vx),
+                             vy=None if vy is None else ctx.to_device(vy), nt_opt=nt, doors=doors))
+        keys_cpu.append(co.KeyData(V, vx if vx is not None else np.zeros((1, Ny - 2, Nx - 2)),
+                                   vy if vy is not None else np.zeros((1, Ny - 2, Nx - 2)), nt, doors))
+    return keys_dev, keys_cpu
+
+
+@pytest.mark.parametrize("name", ["gcfm_dense", "gcfm_small"])
+def test_teacher_forced_steps_vs_reference_and_oracle(name, cfg):
+    """one step from the reference's recorded state with the reference's perm/noise/field."""
+    import torch
+    from oracle import cpu_oracle as co
+    g = golden(name)
+    room = json.loads(str(g["room"]))
+    ctx, prm = _setup(room, cfg)
+    Ny, Nx = ctx.Ny, ctx.Nx
+    P = co.gcfm_params(cfg, room["room_length"], room["room_height"], Ny, Nx)
+    n_exit_total = 0
+    for s in [int(q) for q in g["field_steps"]]:
+        keys_dev, keys_cpu = _load_keys(g, room, ctx, Ny, Nx, step_fields=s)
+        b, a = g["before"][s], g["after"][s]
+        noise = g["noise"][s]; noise = noise[~np.isnan(noise[:, 0])]
+        st = {k: ctx.to_device(b[:, i].copy()) for i, k in enumerate(("x", "y", "vx", "vy"))}
+        st["time"] = ctx.to_device(b[:, 5].copy())
+        st["status"] = ctx.to_device(b[:, 4].astype(np.uint8))
+        ex, rc = ctx.gcfm_step(prm, st, ctx.to_device(g["v_des"]), ctx.to_device(g["agent_key"].astype(np.int32)),
+                               keys_dev, g["perm"][s], noise, s)
+        assert rc == 0
+        out = np.column_stack([st[k].cpu().numpy() for k in ("x", "y", "vx", "vy")] +
+                              [st["status"].cpu().numpy().astype(float), st["time"].cpu().numpy()])
+        # O1: the unmodified reference
+        assert np.abs(out - a).max() < 1e-12
+        assert np.array_equal(out[:, 4], a[:, 4])
+        # O2: bit-exact
+        so = {k: np.ascontiguousarray(b[:, i]) for i, k in enumerate(("x", "y", "vx", "vy"))}
+        so["time"] = np.ascontiguousarray(b[:, 5]); so["status"] = b[:, 4].astype(np.uint8)
+        ex2, bad, _ = co.gcfm_step(P, so, g["v_des"], g["agent_key"], keys_cpu, ctx.X, ctx.Y, g["perm"][s], noise, s)
+        o2 = np.column_stack([so[k] for k in ("x", "y", "vx", "vy")] + [so["status"].astype(float), so["time"]])
+        assert np.array_equal(out, o2)
+        assert np.array_equal(ex, ex2)
+        n_exit_total += len(ex)
+    if name == "gcfm_small":
+        assert n_exit_total == 2
+    ctx.close()
+
+
+def _random_crowd(rng, N, L, H, margin=1.0, min_dist=0.25):
+    pts = []
+    cell = {}
+    while len(pts) < N:
+        p = (rng.uniform(margin, L - margin), rng.uniform(margin, H - margin))
+        c = (int(p[0] / min_dist), int(p[1] / min_dist))
+        ok = True
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for q in cell.get((c[0] + dx, c[1] + dy), []):
+                    if (q[0] - p[0]) ** 2 + (q[1] - p[1]) ** 2 < min_dist ** 2:
+                        ok = False
+        if ok:
+            pts.append(p); cell.setdefault(c, []).append(p)
+    return np.array(pts)
+
+
+@pytest.mark.parametrize("N,L,H,steps", [(40, 8.0, 5.0, 60), (1500, 40.0, 30.0, 12)])
+def test_free_running_bitexact_vs_oracle(N, L, H, steps, cfg):
+    """whole runs: GPU sweep == sequential CPU sweep bit for bit (positions, velocities, exit order)."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    rng = np.random.RandomState(N)
+    ctx = _lib.Context(L, H, 0.05)
+    Ny, Nx = ctx.Ny, ctx.Nx
+    prm = _lib.gcfm_params(cfg, L, H, Ny, Nx)
+    P = co.gcfm_params(cfg, L, H, Ny, Nx)
+    # two keys with different doors; a synthetic smooth velocity field pointing to the door
+    doors = [np.array([[L, H / 2, 0.6, 2.0]]), np.array([[L / 2, H, 3.0, 0.6], [0.0, H / 2, 0.6, 2.0]])]
+    keys_dev, keys_cpu = [], []
+    nsl = steps + 2
+    Xi, Yi = np.meshgrid(ctx.X[1:-1], ctx.Y[1:-1])
+    for kd in doors:
+        V = co.create_potential(ctx.X, ctx.Y, [[L / 3, H / 2, 0.4, H / 2]], [], [[2 * L / 3, H / 3, 0.5]], kd)
+        V[V < 0] = -100; V[V > 0] = 1
+        ux, uy = kd[0, 0] - Xi, kd[0, 1] - Yi
+        nrm = np.sqrt(ux ** 2 + uy ** 2) + 1e-9
+        vx = np.repeat((ux / nrm)[None], nsl, 0) * np.linspace(1, 0.9, nsl)[:, None, None]
+        vy = np.repeat((uy / nrm)[None], nsl, 0)
+        Vd = ctx.to_device(V)
+        tiles, vmin = ctx.wall_tiles(Vd)
+        keys_dev.append(dict(V=Vd, tiles=tiles, v_min=vmin, vx=ctx.to_device(vx), vy=ctx.to_device(vy), nt_opt=nsl + 1, doors=kd))
+        keys_cpu.append(co.KeyData(V, vx, vy, nsl + 1, kd))
+    pos = _random_crowd(rng, N, L, H)
+    # keep agents off wall nodes
+    vdes = rng.normal(1.34, 0.26, N)
+    key_id = rng.randint(0, 2, N).astype(np.int32)
+    # some agents start next to a door so that exits happen early
+    pos[:5] = np.column_stack([np.full(5, L - 0.35), H / 2 + np.linspace(-0.8, 0.8, 5)]); key_id[:5] = 0
+    cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=rng.normal(0, 0.5, N), vy=rng.normal(0, 0.5, N),
+               time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    dev = {k: ctx.to_device(v) for k, v in cpu.items()}
+    vd_dev, kid_dev = ctx.to_device(vdes), ctx.to_device(key_id)
+    order_gpu, order_cpu = [], []
+    for s in range(steps):
+        perm = rng.permutation(N)
+        n_act = int(cpu["status"].sum())
+        noise = rng.normal(size=(n_act, 2))
+        ex, rc = ctx.gcfm_step(prm, dev, vd_dev, kid_dev, keys_dev, perm, noise, s)
+        ex2, bad, _ = co.gcfm_step(P, cpu, vdes, key_id, keys_cpu, ctx.X, ctx.Y, perm, noise, s)
+        assert rc == 0 and bad == 0
+        assert np.array_equal(ex, ex2), f"exit order differs at step {s}"
+        order_gpu += list(ex); order_cpu += list(ex2)
+        for k in ("x", "y", "vx", "vy", "time", "status"):
+            assert np.array_equal(dev[k].cpu().numpy(), cpu[k]), f"{k} differs at step {s}"
+    assert len(order_cpu) >= 3
+    ctx.close()
+
+
+def test_sampler_range_error_is_reported(cfg):
+    """App. C #7: positions for which the reference raises IndexError -> OC_ERR_SAMPLER_RANGE."""
+    from optimal_crowds_b200 import _lib
+    u = golden("units")
+    room = json.loads(str(u["room"]))
+    ctx, prm = _setup(room, cfg)
+    Vd = ctx.to_device(u["wall_V"])
+    tiles, vmin = ctx.wall_tiles(Vd)
+    bad = np.where(u["samp_ok"] == 0)[0]
+    assert len(bad) > 0
+    for q in list(bad[:3]) + list(np.where(u["samp_ok"] == 1)[0][:3]):
+        p = u["samp_p"][q]; t = int(u["samp_t"][q])
+        key = dict(V=Vd, tiles=tiles, v_min=vmin, vx=ctx.to_device(u["samp_vx"]), vy=ctx.to_device(u["samp_vy"]),
+                   nt_opt=int(u["samp_nt_opt"]), doors=np.array([[100.0, 100.0, 0.1, 0.1]]))
+        st = dict(x=ctx.to_device(np.array([p[0]])), y=ctx.to_device(np.array([p[1]])), vx=ctx.to_device(np.zeros(1)),
+                  vy=ctx.to_device(np.zeros(1)), time=ctx.to_device(np.zeros(1)),
+                  status=ctx.to_device(np.ones(1, dtype=np.uint8)))
+        _, rc = ctx.gcfm_step(prm, st, ctx.to_device(np.array([1.3])), ctx.to_device(np.zeros(1, dtype=np.int32)),
+                              [key], np.array([0]), np.zeros((1, 2)), t)
+        assert (rc == _lib.OC_ERR_SAMPLER_RANGE) == (u["samp_ok"][q] == 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("rname", ["room_test", "exit_opposite", "dense", "small"])
+def test_rasteriser_and_density_vs_reference(rname, cfg):
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    u = golden("units")
+    room = json.loads(str(u[f"rast_{rname}_room"]))
+    ctx, _ = _setup(room, cfg)
+    kid = 0
+    while f"rast_{rname}_k{kid}" in u:
+        key = str(u[f"rast_{rname}_k{kid}_key"])
+        tg = [room["targets"][t] for t in key.split(" or ")]
+        V = ctx.rasterise(list(room["walls"].values()), list(room["holes"].values()), list(room["cylinders"].values()),
+                          tg, remap=True, wall_value=-100.0, target_value=1.0)
+        assert np.array_equal(V.cpu().numpy(), u[f"rast_{rname}_k{kid}"])  # bit-equal masks
+        kid += 1
+    xy = u[f"dens_{rname}_xy"]
+    st = u[f"dens_{rname}_status"]
+    d = ctx.density(ctx.to_device(xy[:, 0].copy()), ctx.to_device(xy[:, 1].copy()), ctx.to_device(st), 0.5,
+                    ctx.to_device(u[f"rast_{rname}_Vglobal"])).cpu().numpy()
+    assert np.abs(d - u[f"dens_{rname}"]).max() < 1e-13
+    d2 = co.density(ctx.X, ctx.Y, u[f"rast_{rname}_Vglobal"], xy[:, 0], xy[:, 1], st, 0.5)
+    assert np.array_equal(d, d2)
+    ctx.close()

@@ -1,0 +1,146 @@
+"""GPU parity: HJB path (K1 RHS, K2 RK45, K3 dense output + vels) through the C ABI vs the CPU oracle and
+the golden vectors produced by the unmodified reference.
+
+Tolerance (BASELINE.json north_star): FP64, 1e-10 relative on the value function and velocity field.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden, room_grid
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+def _ctx(room, cfg):
+    from optimal_crowds_b200 import _lib
+    return _lib.Context(room["room_length"], room["room_height"], cfg["grid_step"])
+
+
+def _field_close(a, b, lim_guard=None):
+    """max abs difference of unit-vector fields, ignoring cells within 1e-9 of the |v| == lim switch."""
+    d = np.abs(a - b)
+    if lim_guard is not None:
+        d = np.where(lim_guard, 0.0, d)
+    return d.max()
+
+
+@pytest.mark.parametrize("name", ["hjb_room_test_T3", "hjb_small_T2_density", "hjb_exit_opposite_T1"])
+def test_solve_matches_reference_golden(name, cfg, torch_mod):
+    from optimal_crowds_b200 import _lib
+    g = golden(name)
+    room = json.loads(str(g["room"]))
+    T = float(g["T"])
+    ctx = _ctx(room, cfg)
+    prm = _lib.hjb_params(cfg)
+    for kid in range(int(g["n_keys"])):
+        V = ctx.to_device(g[f"k{kid}_V"])
+        m = ctx.to_device(g[f"k{kid}_m"]) if f"k{kid}_m" in g else None
+        nt = int(g[f"k{kid}_nt"])
+        res = ctx.hjb_solve(V, m, prm, T, nt, want_phi=True, want_vel=True, trace=True)
+        st = res["stats"]
+        assert st["status"] == 0 and st["n_out"] == nt
+        # identical controller decisions: same number of attempts, same nfev, same h sequence
+        assert st["nfev"] == int(g[f"k{kid}_nfev"])
+        h_ref, e_ref = g[f"k{kid}_attempt_h"], g[f"k{kid}_attempt_err"]
+        assert len(res["trace_h"]) == len(h_ref)
+        np.testing.assert_allclose(res["trace_h"], h_ref, rtol=1e-11, atol=0)
+        np.testing.assert_allclose(res["trace_err"], e_ref, rtol=1e-9, atol=0)
+        assert np.array_equal(res["trace_err"] < 1, e_ref < 1)
+        np.testing.assert_allclose(st["h0"], float(g[f"k{kid}_h0"]), rtol=1e-12)
+        sl = g[f"k{kid}_slices"]
+        phi = res["phi"].cpu().numpy().reshape(nt, -1)
+        for q, s in enumerate(sl):
+            np.testing.assert_allclose(phi[nt - 1 - s], g[f"k{kid}_phi"][q], rtol=RTOL, atol=0)
+        vx = res["vx"].cpu().numpy(); vy = res["vy"].cpu().numpy()
+        assert np.abs(vx[sl] - g[f"k{kid}_vx"]).max() < RTOL
+        assert np.abs(vy[sl] - g[f"k{kid}_vy"]).max() < RTOL
+        # every slice is pinned through its checksum
+        np.testing.assert_allclose(vx.sum(axis=(1, 2)), g[f"k{kid}_vx_sum"], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(vy.sum(axis=(1, 2)), g[f"k{kid}_vy_sum"], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(np.abs(vx).sum(axis=(1, 2)), g[f"k{kid}_vx_abs"], rtol=0, atol=1e-8)
+    ctx.close()
+
+
+def test_rhs_and_vels_match_oracle(cfg, torch_mod):
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    rng = np.random.RandomState(3)
+    g = golden("hjb_small_T2_density")
+    room = json.loads(str(g["room"]))
+    ctx = _ctx(room, cfg)
+    prm = _lib.hjb_params(cfg)
+    V = g["k0_V"]; m = g["k0_m"]
+    Ny, Nx = V.shape
+    phi = np.exp(rng.normal(size=(Ny, Nx)))
+    ref = co.hjb_rhs(phi.ravel(), V, m, 0.05, 0.05, prm.sigma, prm.mu, prm.g).reshape(Ny, Nx)
+    out = ctx.hjb_rhs(ctx.to_device(phi), ctx.to_device(V), ctx.to_device(m), prm).cpu().numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() <= 1e-13 * scale
+    assert np.array_equal(out[V < 0], np.zeros((V < 0).sum()))
+    # vels: elementwise IEEE ops in the reference's order -> bit-exact
+    rvx, rvy = co.vels(phi.ravel(), Ny, Nx)
+    vx, vy = ctx.hjb_vels(ctx.to_device(phi), prm)
+    assert np.array_equal(vx.cpu().numpy(), rvx) and np.array_equal(vy.cpu().numpy(), rvy)
+    # phi below the clamp (optimals.py:172) and exactly flat regions (norm < lim -> 0)
+    phi2 = np.full((Ny, Nx), 3.0); phi2[10:20, 10:20] = 1e-3; phi2[30:, :] = np.linspace(1, 2, Nx)[None, :]
+    rvx, rvy = co.vels(phi2.ravel(), Ny, Nx)
+    vx, vy = ctx.hjb_vels(ctx.to_device(phi2), prm)
+    assert np.array_equal(vx.cpu().numpy(), rvx, equal_nan=True) and np.array_equal(vy.cpu().numpy(), rvy, equal_nan=True)
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape_T", [((37, 53), 0.7), ((130, 257), 0.5), ((16, 300), 0.3)])
+def test_solve_matches_oracle_ragged_grids(shape_T, cfg, torch_mod):
+    """grids that are not multiples of the tile sizes, with a target on the frame (mirror ghosts matter)."""
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    (Ny, Nx), T = shape_T
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    assert _lib.grid_shape(L, H, 0.05) == (Ny, Nx)
+    rng = np.random.RandomState(Ny)
+    V = np.zeros((Ny, Nx)); V[0, :] = V[-1, :] = V[:, 0] = V[:, -1] = -100
+    V[Ny // 3: Ny // 3 + 3, Nx // 4: Nx // 2] = -100
+    V[Ny // 2 - 2: Ny // 2 + 2, -1] = 1.0  # door on the right frame
+    V[0, 5:9] = 1.0                         # door on the bottom frame
+    m = rng.uniform(0, 1, (Ny, Nx))
+    nt = round(T / 0.02)
+    phi_ref, st_ref, h_ref, e_ref = co.hjb_solve(V, m, T, nt)
+    vx_ref, vy_ref = co.fill_field(phi_ref, Ny, Nx)
+    ctx = _lib.Context(L, H, 0.05)
+    res = ctx.hjb_solve(ctx.to_device(V), ctx.to_device(m), _lib.hjb_params(cfg), T, nt, want_phi=True, trace=True)
+    st = res["stats"]
+    assert (st["nfev"], st["n_accepted"], st["n_rejected"]) == (st_ref["nfev"], st_ref["n_accepted"], st_ref["n_rejected"])
+    np.testing.assert_allclose(res["trace_h"], h_ref, rtol=1e-11)
+    np.testing.assert_allclose(res["phi"].cpu().numpy().reshape(nt, -1), phi_ref, rtol=RTOL)
+    assert np.abs(res["vx"].cpu().numpy() - vx_ref).max() < RTOL
+    assert np.abs(res["vy"].cpu().numpy() - vy_ref).max() < RTOL
+    ctx.close()
+
+
+def test_solve_velocity_only_and_resolve_shorter(cfg, torch_mod):
+    """re-solve with fewer samples (optimals.py:140,193-194: span stays (T,0), nt shrinks)."""
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    g = golden("hjb_small_T2_density")
+    room = json.loads(str(g["room"]))
+    ctx = _ctx(room, cfg)
+    V = g["k0_V"]; Ny, Nx = V.shape
+    T = 2.0
+    nt = round((T - 1.0) / 0.02)  # re-solve at t = 1.0
+    phi_ref, st_ref, _, _ = co.hjb_solve(V, None, T, nt)
+    vx_ref, vy_ref = co.fill_field(phi_ref, Ny, Nx)
+    res = ctx.hjb_solve(ctx.to_device(V), None, _lib.hjb_params(cfg), T, nt)
+    assert res["phi"] is None and res["stats"]["nfev"] == st_ref["nfev"]
+    assert np.abs(res["vx"].cpu().numpy() - vx_ref).max() < RTOL
+    assert np.abs(res["vy"].cpu().numpy() - vy_ref).max() < RTOL
+    ctx.close()
