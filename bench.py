@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two hot paths (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA library)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm (C port of the reference's algorithm)
+
+Workload (config.workload): BASELINE.json configs[3], the slalom cylinder field.  The 16384 x 16384 grid with
+100k agents is row-decomposed into bands of 2048 rows; one band (16384 x 2048 nodes, 12.5k agents, T = 2 s
+-> nt = 100 field slices) is what one GPU holds, so the bench is WEAK scaling: N GPUs solve the
+16384 x (2048 N) room and N = 8 is exactly configs[3].  A "step" is one full HJB solve
+(optimals.compute_optimal_velocity: RK45 backward from T to 0 with dense output and the velocity epilogue).
+metric = HJB Gcell-updates/s (cell-update = one RHS evaluation at one node; a solve does nfev*Ny*Nx).
+The GCFM agent-steps/s figure is reported in the same JSON line under "gcfm".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BAND_NX, BAND_NY, BAND_AGENTS, T_DEFAULT = 16384, 2048, 12500, 2.0
+CPU_SAMPLE_NX, CPU_SAMPLE_NY, CPU_SAMPLE_T = 2048, 1024, 0.5
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_hjb_sample(threads=1):
+    """Bounded sample of the same workload on the host: the slalom room at 2048 x 1024 nodes, T = 0.5,
+    solved by the C port of the reference's algorithm (oracle/oc_oracle_hjb.c)."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import synthetic
+    room = synthetic.slalom_room(CPU_SAMPLE_NX, CPU_SAMPLE_NY, agents=200)
+    L, H = room["room_length"], room["room_height"]
+    X, Y = np.linspace(0, L, CPU_SAMPLE_NX), np.linspace(0, H, CPU_SAMPLE_NY)
+    V = co.create_potential(X, Y, [], [], list(room["cylinders"].values()), list(room["targets"].values()))
+    V[V < 0] = -100; V[V > 0] = 1
+    nt = round(CPU_SAMPLE_T / 0.02)
+    t0 = time.perf_counter()
+    _, st, _, _ = co.hjb_solve(V, None, CPU_SAMPLE_T, nt)
+    dt = time.perf_counter() - t0
+    cu = st["nfev"] * CPU_SAMPLE_NX * CPU_SAMPLE_NY
+    return cu / dt / 1e9, dt, st, f"slalom room at {CPU_SAMPLE_NX}x{CPU_SAMPLE_NY} nodes, T={CPU_SAMPLE_T} (nfev={st['nfev']}), {dt:.1f} s"
+
+
+def cpu_gcfm_sample(n_agents=150, steps=2):
+    """GCFM steps of the C port on the same sample room (full-grid wall argmin + O(N^2) pair loop, as the reference)."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import synthetic
+    with open(os.path.join(REPO, "optimal_crowds_b200", "config.json")) as f:
+        cfg = json.load(f)
+    nx, ny = 1024, 512
+    room = synthetic.slalom_room(nx, ny, agents=n_agents)
+    L, H = room["room_length"], room["room_height"]
+    X, Y = np.linspace(0, L, nx), np.linspace(0, H, ny)
+    doors = np.array(list(room["targets"].values()))
+    V = co.create_potential(X, Y, [], [], list(room["cylinders"].values()), doors)
+    V[V < 0] = -100; V[V > 0] = 1
+    P = co.gcfm_params(cfg, L, H, ny, nx)
+    rng = np.random.RandomState(0)
+    key = co.KeyData(V, rng.normal(size=(steps + 1, ny - 2, nx - 2)) * 0.1, rng.normal(size=(steps + 1, ny - 2, nx - 2)) * 0.1,
+                     steps + 2, doors)
+    st = dict(x=rng.uniform(2, L - 2, n_agents), y=rng.uniform(2, H - 2, n_agents), vx=rng.normal(0, .3, n_agents),
+              vy=rng.normal(0, .3, n_agents), time=np.zeros(n_agents), status=np.ones(n_agents, dtype=np.uint8))
+    vdes = rng.normal(1.34, 0.26, n_agents)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        co.gcfm_step(P, st, vdes, np.zeros(n_agents, dtype=np.int32), [key], X, Y, rng.permutation(n_agents),
+                     rng.normal(size=(n_agents, 2)), s)
+    dt = time.perf_counter() - t0
+    return n_agents * steps / dt, f"{n_agents} agents x {steps} steps on a {nx}x{ny} grid, {dt:.1f} s"
+
+
+def run_reference_arm(args):
+    """CPU arm: the reference is single-threaded per solve (numpy ufuncs), so all host cores are used the way a
+    user of the reference would use them -- one independent solve per core, aggregate throughput."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu_oracle as co
+    co.lib()
+    cores = max(1, min(os.cpu_count() or 1, 16))
+    vals, dts, last = [], [], None
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL inside the C solve
+            outs = list(ex.map(lambda _: cpu_hjb_sample(), range(cores)))
+        dt = time.perf_counter() - t0
+        cu = sum(o[2]["nfev"] for o in outs) * CPU_SAMPLE_NX * CPU_SAMPLE_NY
+        if it >= args.warmup:
+            vals.append(cu / dt / 1e9); dts.append(dt)
+        last = f"{cores} concurrent independent solves (one per core), each: " + outs[0][3]
+    v = float(np.mean(vals))
+    gc, gsample = cpu_gcfm_sample()
+    line = {"impl": "reference", "metric": "hjb_gcell_updates_per_s", "value": v, "unit": "Gcell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dts) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "slalom (configs[3]) cylinder field; CPU arm runs a bounded sample", "sample": last},
+            "cpu_baseline": {"value": v, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": last},
+            "e2e": {"value": v, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gcfm": {"value": gc, "unit": "agent-steps/s", "sample": gsample, "cores": 1, "kind": "port"}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--T", type=float, default=T_DEFAULT)
+    ap.add_argument("--band-ny", type=int, default=BAND_NY)
+    ap.add_argument("--nx", type=int, default=BAND_NX)
+    ap.add_argument("--agents", type=int, default=BAND_AGENTS)
+    ap.add_argument("--gcfm-steps", type=int, default=20)
+    ap.add_argument("--fused", type=int, default=int(os.environ.get("OC_FUSED", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from optimal_crowds_b200 import _lib, simulations, synthetic
+
+    W, K = max(args.warmup, 0), args.steps
+    nx, ny = args.nx, args.band_ny
+    t_start = time.perf_counter()
+
+    def note(msg):
+        if rank == 0:
+            print(f"[bench {time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    room = synthetic.slalom_room(nx, ny, agents=args.agents)
+    np.random.seed(1000 + rank)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        simu = simulations.simulation(room, args.T, recompute=False, record=False)
+    note(f"simulation built: N={simu.N} agents, grid {simu.Ny}x{simu.Nx}, keys={len(simu.targets)}")
+    key = list(simu.targets)[0]
+    opt = simu.targets[key]
+    opt._prm.fused = args.fused
+    opt._prm.profile = 1
+    cells = nx * ny
+    # density input m as a HOST buffer (the reference-facing signature takes a numpy array), pinned
+    m_host = torch.zeros((ny, nx), dtype=torch.float64).pin_memory()
+    m_dev = m_host.to("cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def solve(m):
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt.compute_optimal_velocity(0.0, m)
+        return opt.last_stats
+
+    # ---- device-resident timing: inputs already in HBM ------------------------------------------
+    for _ in range(W):
+        solve(m_dev)
+    barrier()
+    note(f"warm-up done: {opt.last_stats}")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cls_ms, cls_bytes, cls_n = np.zeros(3), np.zeros(3), np.zeros(3)
+    nfev_total = 0
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        st = solve(m_dev)
+        nfev_total += st["nfev"]
+        cls_ms += st["cls_ms"]; cls_bytes += st["cls_bytes"]; cls_n += st["cls_launches"]
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * nfev_total * cells / (ms_max * 1e-3) / 1e9
+
+    note(f"device-resident: {value:.2f} Gcu/s, {ms_max / K:.1f} ms/solve")
+    # ---- end to end: host m -> H2D, solve, D2H of a scalar checksum of the first field slice -----------
+    for _ in range(min(W, 2)):
+        solve(m_host.numpy())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nfev_e2e = 0
+    t_wall = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        st = solve(m_host.numpy())
+        nfev_e2e += st["nfev"]
+        chk = float(opt.d_vx[0].sum().item())  # D2H read of the step's result
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * nfev_e2e * cells / (float(t.item()) * 1e-3) / 1e9
+
+    note(f"e2e: {e2e_value:.2f} Gcu/s")
+    # ---- GCFM: agent-steps/s through simulation.step (host RNG + H2D + sweep + exit log D2H) -----------
+    for _ in range(3):
+        simu.step(simu.dt)
+    barrier()
+    g0 = time.perf_counter()
+    agent_steps, dev_ms = 0, 0.0
+    for _ in range(args.gcfm_steps):
+        agent_steps += int(simu._h_status.sum())
+        simu.step(simu.dt)
+        dev_ms += simu._ctx.gcfm_last_ms()
+    barrier()
+    g_wall = time.perf_counter() - g0
+    gt = torch.tensor([g_wall, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+    gcfm = {"metric": "gcfm_agent_steps_per_s", "value": world * agent_steps / float(gt[1].item()),
+            "unit": "agent-steps/s", "e2e_value": world * agent_steps / float(gt[0].item()),
+            "agents_per_gpu": simu.N, "steps": args.gcfm_steps, "ms_per_step": float(gt[1].item()) * 1e3 / args.gcfm_steps,
+            "note": "value = CUDA-event time of oc_gcfm_step (H2D perm/noise + kernels + exit log); e2e_value adds the "
+                    "host numpy RNG draw and Python; parity mode (sequential-sweep semantics, host RNG stream)"}
+
+    note(f"gcfm: {gcfm['value']:.0f} agent-steps/s device, {gcfm['e2e_value']:.0f} e2e")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = load_peaks()
+    dom = 0  # RK stage kernels
+    achieved = cls_bytes[dom] / (cls_ms[dom] * 1e-3) / 1e9 if cls_ms[dom] > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "hjb_stage_kernel<N,MODE> (RK45 stage: combination + stencil [+ y_new, error])"
+            if not args.fused else "hjb_fused_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
+            else "fallback (B200_PROFILING.md)", "traffic": None,
+            "launches": int(cls_n[dom]), "avg_launch_ms": float(cls_ms[dom] / max(cls_n[dom], 1)),
+            "algorithmic_bytes_per_launch": float(cls_bytes[dom] / max(cls_n[dom], 1)),
+            "share_of_step": float(cls_ms[dom] / (ms * 1.0)) if ms > 0 else None,
+            "other_classes": {"dense_output+velocity": {"ms": float(cls_ms[1]), "GBps": float(cls_bytes[1] / max(cls_ms[1], 1e-9) / 1e6),
+                                                       "launches": int(cls_n[1])},
+                              "reductions": {"ms": float(cls_ms[2]), "launches": int(cls_n[2])}}}
+    tr_file = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tr_file):
+        try:
+            with open(tr_file) as f:
+                roof["traffic"] = json.load(f).get("fused" if args.fused else "stage")
+        except Exception:
+            pass
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        g, dt, stc, sample = cpu_hjb_sample()
+        cpu = {"value": g, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample}
+        try:
+            gc, gsample = cpu_gcfm_sample()
+            gcfm["cpu_baseline"] = {"value": gc, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": gsample}
+        except Exception as e:  # pragma: no cover
+            gcfm["cpu_baseline"] = {"error": str(e)}
+    line = {"metric": "hjb_gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"slalom (BASELINE configs[3]) cylinder field, {nx}x{ny * world} grid "
+                                   f"({nx}x{ny} band per GPU; N=8 is the 16384^2 / 100k-agent config), T={args.T} "
+                                   f"(nt={round(args.T / 0.02)} slices), {args.agents * world} agents",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent row bands (no halo exchange)",
+                       "l2": "inputs larger than L2 (each field 268 MB > 126 MB)", "formulation":
+                       "stage-wise RK45 (52 B/cell-update)" if not args.fused else "stage-fused RK45 step",
+                       "nfev_per_solve": nfev_total // K},
+            "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m_host.numel() * 8),
+                    "d2h_bytes_per_step": 8, "checksum": chk,
+                    "api": "optimals.compute_optimal_velocity(t, m_host) + read of sum(vx_opt[0])"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gcfm": gcfm}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -69,6 +69,13 @@ typedef struct {
     double rtol, atol;    /* solve_ivp defaults 1e-3 / 1e-6    optimals.py:196 */
     double lim;           /* 10e-3                             optimals.py:95 */
     int fused;            /* 0: one kernel per RK stage; 1: stage-fused step kernel (temporal blocking) */
+    int profile;          /* != 0: bracket every kernel with CUDA events and fill the per-class times below */
+    /* Teacher-forced controller (parity tests): signed step h to use for attempt i < n_forced_h instead of the
+     * controller's own value; accept/reject is still decided by the computed error norm.  NULL/0 = free-running.
+     * (The adaptive controller operates at the explicit-stability limit and amplifies rounding-level
+     * differences of the error norm ~10x per 40 attempts, so long solves are compared step-for-step.) */
+    const double *forced_h;
+    int n_forced_h;
     int reserved;
 } oc_hjb_params;
 
@@ -81,6 +88,13 @@ typedef struct {
     int launches;    /* kernels launched by this solve */
     double h0;       /* select_initial_step result */
     double gpu_ms;   /* CUDA-event time of the whole solve on `stream` */
+    /* per kernel class (only when prm->profile): launches, summed CUDA-event ms, summed algorithmic bytes
+     * (compulsory unique reads + writes).  class 0: RK stage kernels (K2),
+     * class 1: dense output + velocity epilogue (K3), class 2: reductions / setup */
+    int cls_launches[3];
+    int pad_;
+    double cls_ms[3];
+    double cls_bytes[3];
 } oc_hjb_stats;
 
 /* d_V: remapped potential {wall_value,0,target_value}; d_m: density or NULL (== zeros).
@@ -141,6 +155,9 @@ int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, dou
                  double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
                  const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
                  int simu_step, int *exit_log, int *n_exit, void *stream);
+
+/* CUDA-event time (ms) of the last oc_gcfm_step on this context (H2D of perm/noise, all kernels, exit-log copy). */
+double oc_gcfm_last_ms(oc_ctx *ctx);
 
 /* Nearest-wall search + wall force only (pedestrians.py:282-334) for N independent probes (unit parity):
  * d_ind (nullable, N int64): the np.argmin flat index. */

@@ -30,15 +30,31 @@ OC_ERR_STEP_TOO_SMALL = -5
 
 class HjbParams(C.Structure):
     _fields_ = [("sigma", C.c_double), ("mu", C.c_double), ("g", C.c_double), ("rtol", C.c_double),
-                ("atol", C.c_double), ("lim", C.c_double), ("fused", C.c_int), ("reserved", C.c_int)]
+                ("atol", C.c_double), ("lim", C.c_double), ("fused", C.c_int), ("profile", C.c_int),
+                ("forced_h", dp), ("n_forced_h", C.c_int), ("reserved", C.c_int)]
+
+    def force_steps(self, h):
+        """teacher-forced controller: replay the signed step sequence `h` (parity tests; see optimal_crowds.h)"""
+        if h is None:
+            self._keep = None
+            self.forced_h, self.n_forced_h = None, 0
+        else:
+            self._keep = np.ascontiguousarray(h, dtype=np.float64)
+            self.forced_h, self.n_forced_h = self._keep.ctypes.data_as(dp), len(self._keep)
+        return self
 
 
 class HjbStats(C.Structure):
     _fields_ = [("nfev", C.c_int), ("n_accepted", C.c_int), ("n_rejected", C.c_int), ("status", C.c_int),
-                ("n_out", C.c_int), ("launches", C.c_int), ("h0", C.c_double), ("gpu_ms", C.c_double)]
+                ("n_out", C.c_int), ("launches", C.c_int), ("h0", C.c_double), ("gpu_ms", C.c_double),
+                ("cls_launches", C.c_int * 3), ("pad_", C.c_int), ("cls_ms", C.c_double * 3),
+                ("cls_bytes", C.c_double * 3)]
 
     def asdict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_}
+        d = {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith(("cls_", "pad_"))}
+        for f in ("cls_launches", "cls_ms", "cls_bytes"):
+            d[f] = list(getattr(self, f))
+        return d
 
 
 class GcfmParams(C.Structure):
@@ -57,7 +73,7 @@ _lib = None
 
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
-           "oc_wall_force", "oc_pair_force", "oc_density"]
+           "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms"]
 
 
 def load():
@@ -72,6 +88,8 @@ def load():
     lib.oc_last_error.restype = C.c_char_p
     lib.oc_launch_count.restype = C.c_longlong
     lib.oc_wall_tiles_bytes.restype = C.c_longlong
+    lib.oc_gcfm_last_ms.restype = C.c_double
+    lib.oc_gcfm_last_ms.argtypes = [C.c_void_p]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
     lib.oc_ctx_destroy.restype = None
     lib.oc_ctx_destroy.argtypes = [C.c_void_p]
@@ -245,6 +263,9 @@ class Context:
         check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
         return exit_log[: n_exit.value].copy(), rc
 
+    def gcfm_last_ms(self):
+        return float(load().oc_gcfm_last_ms(self.h))
+
     def wall_force(self, prm: GcfmParams, V, x, y, vx, vy, vdes):
         import torch
         N = x.numel()
@@ -287,9 +308,9 @@ def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: 
     return p
 
 
-def hjb_params(cfg: dict, fused: int = 0) -> HjbParams:
+def hjb_params(cfg: dict, fused: int = 0, profile: int = 0) -> HjbParams:
     h = cfg["hjb_params"]
-    return HjbParams(h["sigma"], h["mu"], h["g"], 1e-3, 1e-6, 10e-3, int(fused), 0)
+    return HjbParams(h["sigma"], h["mu"], h["g"], 1e-3, 1e-6, 10e-3, int(fused), int(profile), None, 0, 0)
 
 
 def launch_count(reset=False):

@@ -63,6 +63,7 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->d_Y);
     cudaFree(c->hjb_ws);
     cudaFree(c->hjb_partial);
+    cudaFree(c->hjb_scratch);
     cudaFree(c->gcfm_ws);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
@@ -77,7 +78,7 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
 // frame = -1 (:565-568), targets = 1 (:570-574); strict '<' on the linspace coordinates.
 // optimals.py:89-91 remap: V<0 -> pot, V>0 -> pot_target.
 namespace {
-constexpr int RAST_CHUNK = 512;
+constexpr int RAST_CHUNK = 256;
 
 struct RastArgs {
     const double *walls, *holes, *cyls, *targets;  // device copies
@@ -86,51 +87,67 @@ struct RastArgs {
     double wall_value, target_value;
 };
 
+// Stage into shared memory the shapes of one chunk whose bounding box touches the block's node rectangle
+// (conservative, non-strict test; the per-node test below is the reference's strict one).  Order inside a
+// class does not matter: walls/cylinders add -1 (exact integer sums), holes/targets assign a constant.
+template <int W>
+__device__ __forceinline__ int stage_shapes(const double *__restrict__ src, int base, int n_total, double x0,
+                                            double x1, double y0, double y1, double *sh, int *cnt) {
+    if (threadIdx.x == 0) *cnt = 0;
+    __syncthreads();
+    int k = base + threadIdx.x;
+    if (k < n_total) {
+        const double *s = src + (size_t)k * W;
+        double hx = (W == 4) ? s[2] / 2 : s[2], hy = (W == 4) ? s[3] / 2 : s[2];
+        if (s[0] - hx <= x1 && s[0] + hx >= x0 && s[1] - hy <= y1 && s[1] + hy >= y0) {
+            int pos = atomicAdd(cnt, 1);
+            for (int q = 0; q < W; q++) sh[pos * W + q] = s[q];
+        }
+    }
+    __syncthreads();
+    return *cnt;
+}
+
 __global__ void __launch_bounds__(256) rasterise_kernel(const double *__restrict__ X, const double *__restrict__ Y,
                                                         int Ny, int Nx, RastArgs a, double *__restrict__ V) {
     __shared__ double sh[RAST_CHUNK * 4];
+    __shared__ int cnt;
     const int j = blockIdx.x * 32 + (threadIdx.x & 31);
     const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
     const bool in = (i < Ny && j < Nx);
     const double x = in ? X[j] : 0.0, y = in ? Y[i] : 0.0;
+    const double bx0 = X[blockIdx.x * 32], bx1 = X[min(blockIdx.x * 32 + 31, Nx - 1)];
+    const double by0 = Y[blockIdx.y * 8], by1 = Y[min(blockIdx.y * 8 + 7, Ny - 1)];
     double v = 0.0;
-    for (int base = 0; base < a.n_walls; base += RAST_CHUNK) {
-        int n = min(RAST_CHUNK, a.n_walls - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.walls[base * 4 + k];
-        __syncthreads();
+    for (int base = 0; base < a.n_walls; base += RAST_CHUNK) {  // simulations.py:538-547
+        int n = stage_shapes<4>(a.walls, base, a.n_walls, bx0, bx1, by0, by1, sh, &cnt);
         for (int k = 0; k < n; k++)
             if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v += -1.0;
+        __syncthreads();
     }
-    for (int base = 0; base < a.n_holes; base += RAST_CHUNK) {
-        int n = min(RAST_CHUNK, a.n_holes - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.holes[base * 4 + k];
-        __syncthreads();
+    for (int base = 0; base < a.n_holes; base += RAST_CHUNK) {  // :549-555
+        int n = stage_shapes<4>(a.holes, base, a.n_holes, bx0, bx1, by0, by1, sh, &cnt);
         for (int k = 0; k < n; k++)
             if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v = 0.0;
+        __syncthreads();
     }
-    for (int base = 0; base < a.n_cyls; base += RAST_CHUNK) {
-        int n = min(RAST_CHUNK, a.n_cyls - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < n * 3; k += 256) sh[k] = a.cyls[base * 3 + k];
-        __syncthreads();
+    for (int base = 0; base < a.n_cyls; base += RAST_CHUNK) {  // :557-563
+        int n = stage_shapes<3>(a.cyls, base, a.n_cyls, bx0, bx1, by0, by1, sh, &cnt);
         for (int k = 0; k < n; k++) {
             double ddx = x - sh[3 * k], ddy = y - sh[3 * k + 1];
             if (sqrt(ddx * ddx + ddy * ddy) < sh[3 * k + 2]) v += -1.0;
         }
+        __syncthreads();
     }
-    if (in && (j == 0 || j == Nx - 1 || i == 0 || i == Ny - 1)) v = -1.0;
-    for (int base = 0; base < a.n_targets; base += RAST_CHUNK) {
-        int n = min(RAST_CHUNK, a.n_targets - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < n * 4; k += 256) sh[k] = a.targets[base * 4 + k];
-        __syncthreads();
+    if (in && (j == 0 || j == Nx - 1 || i == 0 || i == Ny - 1)) v = -1.0;  // :565-568
+    for (int base = 0; base < a.n_targets; base += RAST_CHUNK) {  // :570-574
+        int n = stage_shapes<4>(a.targets, base, a.n_targets, bx0, bx1, by0, by1, sh, &cnt);
         for (int k = 0; k < n; k++)
             if (fabs(x - sh[4 * k]) < sh[4 * k + 2] / 2 && fabs(y - sh[4 * k + 1]) < sh[4 * k + 3] / 2) v = 1.0;
+        __syncthreads();
     }
     if (!in) return;
-    if (a.remap) {
+    if (a.remap) {  // optimals.py:89-91
         if (v < 0) v = a.wall_value;
         else if (v > 0) v = a.target_value;
     }

@@ -19,6 +19,8 @@ struct oc_ctx {
     // HJB workspace (lazily allocated, reused across solves)
     double *hjb_ws = nullptr;
     size_t hjb_ws_bytes = 0;
+    double *hjb_scratch = nullptr;  // phi slices of the fused step when only velocities are stored
+    size_t hjb_scratch_bytes = 0;
     double *hjb_partial = nullptr;  // per-tile error partial sums
     size_t hjb_partial_n = 0;
     double *h_pinned = nullptr;  // pinned host scratch (row-group sums, flags)
@@ -30,6 +32,7 @@ struct oc_ctx {
     void *gcfm_pinned = nullptr;
     size_t gcfm_pinned_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double gcfm_last_ms = 0.0;
 };
 
 namespace oc {

@@ -701,6 +701,7 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
         for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
         off += keys[k].n_doors;
     }
+    OC_CUDA(cudaEventRecord(ctx->ev0, st));
     OC_CUDA(cudaMemcpyAsync(w.keys, hk.data(), sizeof(KeyDev) * n_keys, cudaMemcpyHostToDevice, st));
     OC_CUDA(cudaMemcpyAsync(w.doors, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
     OC_CUDA(cudaMemcpyAsync(w.perm, perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
@@ -727,7 +728,13 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     exit_compact_kernel<<<1, 1024, 0, st>>>(N, w, pinned);
     oc::count_launch(7);
     OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaEventRecord(ctx->ev1, st));
     OC_CUDA(cudaStreamSynchronize(st));  // hk/hd lifetimes + host-visible exit log
+    {
+        float ms = 0;
+        OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->gcfm_last_ms = ms;
+    }
     int ne = pinned[0], fl = pinned[1];
     if (n_exit) *n_exit = ne;
     if (exit_log)
@@ -747,6 +754,8 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     }
     return OC_OK;
 }
+
+extern "C" double oc_gcfm_last_ms(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_ms : 0.0; }
 
 extern "C" int oc_wall_force(oc_ctx *ctx, const oc_gcfm_params *prm, const double *d_V, int N, const double *d_x,
                              const double *d_y, const double *d_vx, const double *d_vy, const double *d_vdes,

@@ -13,8 +13,10 @@
 // multiples of TY rows reproduces the single-GPU sum bit for bit.
 #include <cmath>
 #include <algorithm>
+#include <vector>
 
 #include "oc_common.h"
+#include "oc_hjb_fused.cuh"
 
 namespace {
 
@@ -310,11 +312,44 @@ struct Solver {
     double *partial, *rowsum_d, *rowsum_h;
     double diff_over_dxdy;
     int launches = 0;
+    bool profile = false;
+    struct Rec { int cls; double bytes; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    cudaEvent_t get_event() {
+        if (pool_used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[pool_used++];
+    }
+    void begin(int cls, double bytes) {
+        if (!profile) return;
+        Rec r{cls, bytes, get_event(), get_event()};
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end() {
+        if (!profile) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void collect(oc_hjb_stats *out) {
+        for (auto &r : recs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            out->cls_launches[r.cls]++;
+            out->cls_ms[r.cls] += ms;
+            out->cls_bytes[r.cls] += r.bytes;
+        }
+        for (auto e : pool) cudaEventDestroy(e);
+        pool.clear(); recs.clear();
+    }
 
     template <int N, int MODE>
     void launch_stage(const Comb &c, double *kout, double *yn, const ErrArgs &ea) {
         dim3 grid(nbx, nby);
+        // algorithmic words per cell: y + N k's + coef in, k out (+ y_new out, K[0..5] re-used for the error)
+        begin(0, 8.0 * (double)n * (MODE == 1 ? 9 : N + 3));
         hjb_stage_kernel<N, MODE><<<grid, NTHREADS, 0, st>>>(c, coef, kout, yn, ea, partial, Ny, Nx, diff_over_dxdy);
+        end();
         launches++;
     }
     void stage(int N, const Comb &c, double *kout) {
@@ -328,14 +363,56 @@ struct Solver {
             case 5: launch_stage<5, 0>(c, kout, nullptr, ea); break;
         }
     }
-    // sum over tile rows of per-tile partials located at partial+off; host-visible after sync
-    int reduce_to_host(size_t off, double *out) {
-        rowgroup_sum_kernel<<<nby, NTHREADS, 0, st>>>(partial + off, nbx, rowsum_d);
+    // ---- stage-fused step (oc_hjb_fused.cuh)
+    int fused_rc = 0, fused_gx = 0, fused_gy = 0;
+    void fused_plan(int n_sm) {
+        fused_gx = (Nx + fused::VX - 1) / fused::VX;
+        static const int cand[] = {32, 48, 64, 96, 128, 192, 256, 384, 512};
+        double best = 1e300;
+        for (int rc : cand) {
+            int gy = (Ny + rc - 1) / rc;
+            long long blocks = (long long)fused_gx * gy;
+            double cost = (double)((blocks + n_sm - 1) / n_sm) * (std::min(rc, Ny) + 2 * fused::HY);
+            if (cost < best) { best = cost; fused_rc = rc; fused_gy = gy; }
+        }
+    }
+    template <int NE>
+    int launch_fused_ne(const fused::Args &a) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(fused::Smem)));
+            attr_done = true;
+        }
+        dim3 grid(fused_gx, fused_gy);
+        begin(0, 8.0 * (double)n * (5 + NE));  // y, f, coef in; y_new, f_new, NE phi slices out
+        fused::hjb_fused_kernel<NE><<<grid, fused::BX, sizeof(fused::Smem), st>>>(a);
+        end();
         launches++;
-        OC_CUDA(cudaMemcpyAsync(rowsum_h, rowsum_d, sizeof(double) * nby, cudaMemcpyDeviceToHost, st));
+        return OC_OK;
+    }
+    int launch_fused(int ne, const fused::Args &a) {
+        switch (ne) {
+            case 0: return launch_fused_ne<0>(a);
+            case 1: return launch_fused_ne<1>(a);
+            case 2: return launch_fused_ne<2>(a);
+            case 3: return launch_fused_ne<3>(a);
+            case 4: return launch_fused_ne<4>(a);
+            case 5: return launch_fused_ne<5>(a);
+            default: return launch_fused_ne<6>(a);
+        }
+    }
+    // sum over tile rows of per-tile partials located at partial+off; host-visible after sync
+    int reduce_to_host(size_t off, double *out, int gx = -1, int gy = -1) {
+        if (gx < 0) { gx = nbx; gy = nby; }
+        begin(2, 8.0 * ((double)gx * gy + gy));
+        rowgroup_sum_kernel<<<gy, NTHREADS, 0, st>>>(partial + off, gx, rowsum_d);
+        end();
+        launches++;
+        OC_CUDA(cudaMemcpyAsync(rowsum_h, rowsum_d, sizeof(double) * gy, cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaStreamSynchronize(st));
         double s = 0.0;
-        for (int i = 0; i < nby; i++) s += rowsum_h[i];  // fixed global order
+        for (int i = 0; i < gy; i++) s += rowsum_h[i];  // fixed global order
         *out = s;
         return OC_OK;
     }
@@ -354,16 +431,22 @@ int ensure_ws(oc_ctx *ctx, size_t n, int nbx, int nby) {
         }
         ctx->hjb_ws_bytes = need;
     }
-    size_t np = (size_t)2 * nbx * nby + nby;
+    // large enough for the stage tiles and for any fused-step plan (>= 32-row chunks, 240-column tiles)
+    size_t np = (size_t)2 * nbx * nby + nby + 64;
+    {
+        size_t fgx = (size_t)(nbx * TX + fused::VX - 1) / fused::VX + 1, fgy = (size_t)(nby * TY + 31) / 32 + 1;
+        np = std::max(np, 2 * fgx * fgy + fgy + 64);
+    }
     if (ctx->hjb_partial_n < np) {
         if (ctx->hjb_partial) cudaFree(ctx->hjb_partial);
         OC_CUDA(cudaMalloc(&ctx->hjb_partial, np * sizeof(double)));
         ctx->hjb_partial_n = np;
     }
-    if (ctx->h_pinned_n < (size_t)nby + 16) {
+    size_t hp = (size_t)std::max(nby, (nby * TY + 31) / 32 + 1) + 16;
+    if (ctx->h_pinned_n < hp) {
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-        OC_CUDA(cudaMallocHost(&ctx->h_pinned, ((size_t)nby + 16) * sizeof(double)));
-        ctx->h_pinned_n = (size_t)nby + 16;
+        OC_CUDA(cudaMallocHost(&ctx->h_pinned, hp * sizeof(double)));
+        ctx->h_pinned_n = hp;
     }
     return OC_OK;
 }
@@ -429,6 +512,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     const double rtol = prm->rtol, atol = prm->atol;
     const double sqrt_n = std::sqrt((double)n);
     memset(stats, 0, sizeof(*stats));
+    s.profile = prm->profile != 0;
     int ntr = 0;
     OC_CUDA(cudaEventRecord(ctx->ev0, s.st));
 
@@ -475,6 +559,33 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     }
     stats->h0 = h_abs;
 
+    // stage-fused path (prm->fused): needs room for NE_MAX phi slices when only velocities are requested
+    bool use_fused = prm->fused != 0, fused_attempt = false;
+    double *phi_scratch = nullptr;
+    if (use_fused) {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+        s.fused_plan(n_sm);
+        size_t np_need = (size_t)2 * s.fused_gx * s.fused_gy + s.fused_gy;
+        if (ctx->hjb_partial_n < np_need || ctx->h_pinned_n < (size_t)s.fused_gy + 16) {
+            oc::set_error("internal: fused partial buffers too small");
+            return OC_ERR_ARG;
+        }
+        if (!d_phi && d_vx && d_vy) {
+            size_t need = (size_t)fused::NE_MAX * n * sizeof(double);
+            if (ctx->hjb_scratch_bytes < need) {
+                if (ctx->hjb_scratch) cudaFree(ctx->hjb_scratch);
+                ctx->hjb_scratch = nullptr; ctx->hjb_scratch_bytes = 0;
+                if (cudaMalloc(&ctx->hjb_scratch, need) != cudaSuccess) {
+                    cudaGetLastError();
+                    oc::set_error("cannot allocate %zu bytes of phi scratch", need);
+                    return OC_ERR_NOMEM;
+                }
+                ctx->hjb_scratch_bytes = need;
+            }
+            phi_scratch = ctx->hjb_scratch;
+        }
+    }
     int t_eval_i = nt;  // ivp.py:617-621
     int n_out = 0, status = 1;
     const double error_exponent = -1.0 / 5.0;
@@ -489,10 +600,58 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
         while (!accepted) {
             if (h_abs < min_step) { status = -1; break; }
             h = h_abs * direction;
+            if (prm->forced_h && ntr < prm->n_forced_h) h = prm->forced_h[ntr];  // teacher-forced (tests)
             t_new = t + h;
             if (direction * (t_new - t_bound) > 0) t_new = t_bound;
             h = t_new - t;
             h_abs = std::fabs(h);
+            // t_eval samples this attempt would emit if accepted (ivp.py:715-728): ascending indices
+            // [ia_lo, t_eval_i) with t_eval >= t_new
+            int ia_lo;
+            {
+                int lo = 0, hi = nt;
+                while (lo < hi) {
+                    int mid = (lo + hi) / 2;
+                    if (t_eval[nt - 1 - mid] < t_new) lo = mid + 1; else hi = mid;
+                }
+                ia_lo = std::min(lo, t_eval_i);
+            }
+            const int n_emit = t_eval_i - ia_lo;
+            const bool want_out = d_phi || (d_vx && d_vy);
+            fused_attempt = use_fused && (!want_out || n_emit <= fused::NE_MAX);
+            double se;
+            if (fused_attempt) {
+                // one launch: 6 RHS evaluations, y_new, f_new, error partial sums and the (speculative) dense
+                // output samples; a rejected attempt's samples are overwritten by the step that finally covers them
+                fused::Args fa{};
+                fa.y = s.y; fa.k1 = s.K[0]; fa.coef = s.coef; fa.ynew = s.ynew; fa.k7 = s.K[6]; fa.partial = s.partial;
+                fa.ha21 = h * RK_A[1][0];
+                for (int j = 0; j < 2; j++) fa.ha3[j] = h * RK_A[2][j];
+                for (int j = 0; j < 3; j++) fa.ha4[j] = h * RK_A[3][j];
+                for (int j = 0; j < 4; j++) fa.ha5[j] = h * RK_A[4][j];
+                for (int j = 0; j < 5; j++) fa.ha6[j] = h * RK_A[5][j];
+                for (int j = 0; j < 6; j++) fa.hb[j] = h * RK_B[j];
+                for (int j = 0; j < 7; j++) fa.he[j] = h * RK_E[j];
+                fa.A = s.diff_over_dxdy; fa.rtol = rtol; fa.atol = atol;
+                fa.Ny = s.Ny; fa.Nx = s.Nx; fa.RC = s.fused_rc;
+                int ne = 0;
+                if (want_out) {
+                    for (int ia = t_eval_i - 1; ia >= ia_lo; ia--, ne++) {
+                        const int kd = nt - 1 - ia;
+                        const double x = (t_eval[kd] - t) / h;  // RkDenseOutput: (t - t_old)/h
+                        double pw[4] = {x, x * x, x * x * x, x * x * x * x};
+                        for (int j = 0; j < 7; j++) {
+                            double acc = 0.0;
+                            for (int q = 0; q < 4; q++) acc += RK_P[j][q] * pw[q];
+                            fa.w[ne][j] = h * acc;
+                        }
+                        fa.phi[ne] = d_phi ? d_phi + (size_t)kd * n : phi_scratch + (size_t)ne * n;
+                    }
+                }
+                if ((rc = s.launch_fused(ne, fa))) return rc;
+                stats->nfev += 6;
+                if ((rc = s.reduce_to_host(0, &se, s.fused_gx, s.fused_gy))) return rc;
+            } else {
             // rk_step (rk.py:61-69): K[0] = f already in place
             for (int sgi = 1; sgi < 6; sgi++) {
                 Comb c{};
@@ -514,8 +673,8 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                 s.launch_stage<5, 1>(c, s.K[6], s.ynew, ea);
             }
             stats->nfev += 6;
-            double se;
             if ((rc = s.reduce_to_host(0, &se))) return rc;
+            }
             double error_norm = std::sqrt(se) / sqrt_n;  // rk.py:147, common.py:63-65
             if (trace_h && ntr < trace_cap) { trace_h[ntr] = h; trace_err[ntr] = error_norm; }
             ntr++;
@@ -542,7 +701,25 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
             if (t_eval[nt - 1 - mid] < t_new) lo = mid + 1; else hi = mid;
         }
         const int t_eval_i_new = lo;
-        if (t_eval_i_new < t_eval_i) {
+        if (fused_attempt) {
+            // samples were written by the step kernel; only the gradient-to-velocity conversion is left
+            int ne = 0;
+            for (int ia = t_eval_i - 1; ia >= t_eval_i_new; ia--, ne++) {
+                const int kd = nt - 1 - ia;
+                n_out++;
+                if (d_vx && d_vy && kd >= 1) {
+                    const double *ph = d_phi ? d_phi + (size_t)kd * n : phi_scratch + (size_t)ne * n;
+                    const int sl = nt - 1 - kd;
+                    dim3 grid((s.Nx - 2 + 63) / 64, (s.Ny - 2 + 3) / 4);
+                    s.begin(1, 8.0 * (double)n * 3);
+                    vels_kernel<<<grid, NTHREADS, 0, s.st>>>(ph, s.Ny, s.Nx, prm->mu, prm->lim, 2 * ctx->dx, 2 * ctx->dy,
+                                                             d_vx + (size_t)sl * n_int, d_vy + (size_t)sl * n_int);
+                    s.end();
+                    s.launches++;
+                }
+            }
+            t_eval_i = t_eval_i_new;
+        } else if (t_eval_i_new < t_eval_i) {
             const double hh = t_new - t_old;
             int ia = t_eval_i - 1;
             while (ia >= t_eval_i_new) {
@@ -566,7 +743,11 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                 a.n_emit = e;
                 if (any) {
                     dim3 grid((s.Nx + DTX - 1) / DTX, (s.Ny + DTY - 1) / DTY);
+                    double words = 7.0;  // y_old + K[0], K[2..6]
+                    for (int q = 0; q < e; q++) words += (a.phi[q] ? 1.0 : 0.0) + (a.vx[q] ? 2.0 : 0.0);
+                    s.begin(1, 8.0 * (double)n * words);
                     hjb_dense_kernel<<<grid, NTHREADS, 0, s.st>>>(a, s.Ny, s.Nx);
+                    s.end();
                     s.launches++;
                 }
             }
@@ -583,6 +764,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     float ms = 0;
     OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     stats->gpu_ms = ms;
+    s.collect(stats);
     stats->status = status;
     stats->n_out = n_out;
     stats->launches = s.launches;

@@ -1,0 +1,259 @@
+// oc_hjb_fused.cuh -- stage-fused RK45 step kernel (temporal blocking across the 6 new RHS evaluations).
+//
+// One launch performs a whole Dormand-Prince step attempt (scipy rk.py:14-71 rk_step + :146-147 error
+// estimate) and the dense-output samples phi(t_e) of the t_eval points that fall inside the step
+// (rk.py:178-180,723-737), reading y, f = K[0] and coef once and writing y_new, f_new = K[6] and the
+// phi slices once: 40 B/cell/attempt + 8 B/cell/emitted slice instead of the 312 B/cell/attempt of the
+// stage-wise formulation.
+//
+// Scheme ("2.5-D" streaming): a CTA owns BX = 256 consecutive columns and marches down a chunk of rows.
+// Thread t owns ONE column; all RK state of that column lives in its registers as short row windows.
+// At iteration r the CTA loads row r (stage 1 input), and stage s = 2..7 evaluates the stencil on row
+// r-(s-1), i.e. every stage lags one row behind the previous one, so the 3-row stencil windows of all
+// six stage inputs are register-resident.  Only the left/right neighbours cross threads: each stage
+// input row is published once to a double-buffered shared-memory line (one __syncthreads per row).
+// Rows of y, f, coef are staged ahead of use through an 8-deep cp.async ring in shared memory.
+// Six stencil applications consume HALO = 6 columns per side (8 allocated for 64-byte aligned rows) and
+// 6 rows above/below the chunk, which are recomputed redundantly (about 7 % + 5 % extra work).
+//
+// Arithmetic: FP64, FMA contraction allowed.  The stage combination is evaluated as
+// y + (h a_s1) k_1 + (h a_s2) k_2 + ... with premultiplied coefficients; it differs from scipy's
+// (sum_j a_sj k_j) * h by rounding only (parity bar 1e-10, observed ~1e-13).
+#pragma once
+
+namespace fused {
+
+constexpr int BX = 256;             // threads per CTA = columns per tile incl. halo
+constexpr int HX = 8;               // halo columns per side (6 needed)
+constexpr int VX = BX - 2 * HX;     // valid output columns per tile (240)
+constexpr int HY = 6;               // halo rows per side
+constexpr int PF = 8;               // cp.async ring depth (rows), power of two
+constexpr int NE_MAX = 6;           // dense-output samples per launch
+
+struct Args {
+    const double *y, *k1, *coef;
+    double *ynew, *k7, *partial;
+    double *phi[NE_MAX];
+    double ha21;
+    double ha3[2], ha4[3], ha5[4], ha6[5];
+    double hb[6];            // h*B (B[1] = 0 unused)
+    double he[7];            // h*E (E[1] = 0 unused)
+    double w[NE_MAX][7];     // h * sum_q P[j][q] x_e^(q+1)
+    double A;                // -0.5 sigma^2 / (dx dy)
+    double rtol, atol;
+    int Ny, Nx, RC;          // RC = rows per chunk
+};
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// optimals.py:154-162 with mirror ghosts (:149-152) resolved by the caller
+__device__ __forceinline__ double rhs(double up, double dn, double lf, double rt, double C, double cf, double A) {
+    double lap = (up + dn) + (lf + rt) - 4.0 * C;
+    double r = A * lap - cf * C;
+    return (cf != cf) ? 0.0 : r;
+}
+
+struct Smem {
+    double ex[2][6][BX + 2];   // published stage-input rows (u2..u6, y_new), double buffered
+    double pf[PF][3][BX];      // cp.async ring: y, k1, coef
+    double red[BX / 32];
+};
+
+template <int NE>
+__global__ void __launch_bounds__(BX, 1) hjb_fused_kernel(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int gx = blockIdx.x * VX - HX + tid;
+    const int y0 = blockIdx.y * a.RC;
+    const int y1 = min(y0 + a.RC, a.Ny);
+    const bool col_ok = gx >= 0 && gx < a.Nx;
+    const bool col_out = tid >= HX && tid < BX - HX && gx < a.Nx;  // columns this thread stores
+    const bool x_first = gx == 0, x_last = gx == a.Nx - 1;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
+
+    // windows, indexed by lag (row r - lag)
+    double yw[7], k1w[7], cw[7], k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
+    double u2[3], u3[4], u4[5], u5[6], u6[7], un[8];
+#pragma unroll
+    for (int i = 0; i < 7; i++) { yw[i] = 0; k1w[i] = 0; cw[i] = qnan; k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 5; i++) k2w[i] = 0;
+    u2[0] = u2[1] = u2[2] = 0; u3[1] = u3[2] = u3[3] = 0; u4[2] = u4[3] = u4[4] = 0;
+    u5[3] = u5[4] = u5[5] = 0; u6[4] = u6[5] = u6[6] = 0; un[5] = un[6] = un[7] = 0;
+
+    const int r_begin = y0 - HY, r_end = y1 + HY;  // rows loaded: [r_begin, r_end)
+    auto issue = [&](int row) {
+        const int slot = row & (PF - 1);
+        if (row >= r_end) {
+            // past the chunk: nothing to stage (keeps one commit group per iteration)
+        } else if (col_ok && row >= 0 && row < a.Ny) {
+            const size_t g = (size_t)row * a.Nx + gx;
+            cp_async8(&sm.pf[slot][0][tid], a.y + g);
+            cp_async8(&sm.pf[slot][1][tid], a.k1 + g);
+            cp_async8(&sm.pf[slot][2][tid], a.coef + g);
+        } else {
+            sm.pf[slot][0][tid] = 0.0;
+            sm.pf[slot][1][tid] = 0.0;
+            sm.pf[slot][2][tid] = qnan;
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll 1
+    for (int q = 0; q < PF - 1; q++) issue(r_begin + q);
+    __syncthreads();
+
+    double acc = 0.0;
+    int buf = 0;
+#pragma unroll 2
+    for (int r = r_begin; r < r_end; r++) {
+        issue(r + PF - 1);
+        cp_async_wait<PF - 1>();
+        {
+            const int slot = r & (PF - 1);
+            yw[0] = sm.pf[slot][0][tid];
+            k1w[0] = sm.pf[slot][1][tid];
+            cw[0] = sm.pf[slot][2][tid];
+        }
+        const int cur = buf, prv = buf ^ 1;
+        // ---- stage 2 input on row r
+        u2[0] = fma(a.ha21, k1w[0], yw[0]);
+        sm.ex[cur][0][tid + 1] = u2[0];
+        // ---- k2 on row r-1
+        {
+            const int row = r - 1;
+            double lf = sm.ex[prv][0][tid], rt = sm.ex[prv][0][tid + 2];
+            double up = u2[2], dn = u2[0];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = u2[2];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][0][tid];
+            k2w[1] = rhs(up, dn, lf, rt, u2[1], cw[1], a.A);
+        }
+        u3[1] = fma(a.ha3[1], k2w[1], fma(a.ha3[0], k1w[1], yw[1]));
+        sm.ex[cur][1][tid + 1] = u3[1];
+        // ---- k3 on row r-2
+        {
+            const int row = r - 2;
+            double lf = sm.ex[prv][1][tid], rt = sm.ex[prv][1][tid + 2];
+            double up = u3[3], dn = u3[1];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = u3[3];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][1][tid];
+            k3w[2] = rhs(up, dn, lf, rt, u3[2], cw[2], a.A);
+        }
+        u4[2] = fma(a.ha4[2], k3w[2], fma(a.ha4[1], k2w[2], fma(a.ha4[0], k1w[2], yw[2])));
+        sm.ex[cur][2][tid + 1] = u4[2];
+        // ---- k4 on row r-3
+        {
+            const int row = r - 3;
+            double lf = sm.ex[prv][2][tid], rt = sm.ex[prv][2][tid + 2];
+            double up = u4[4], dn = u4[2];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = u4[4];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][2][tid];
+            k4w[3] = rhs(up, dn, lf, rt, u4[3], cw[3], a.A);
+        }
+        u5[3] = fma(a.ha5[3], k4w[3], fma(a.ha5[2], k3w[3], fma(a.ha5[1], k2w[3], fma(a.ha5[0], k1w[3], yw[3]))));
+        sm.ex[cur][3][tid + 1] = u5[3];
+        // ---- k5 on row r-4
+        {
+            const int row = r - 4;
+            double lf = sm.ex[prv][3][tid], rt = sm.ex[prv][3][tid + 2];
+            double up = u5[5], dn = u5[3];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = u5[5];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][3][tid];
+            k5w[4] = rhs(up, dn, lf, rt, u5[4], cw[4], a.A);
+        }
+        u6[4] = fma(a.ha6[4], k5w[4], fma(a.ha6[3], k4w[4], fma(a.ha6[2], k3w[4], fma(a.ha6[1], k2w[4],
+                    fma(a.ha6[0], k1w[4], yw[4])))));
+        sm.ex[cur][4][tid + 1] = u6[4];
+        // ---- k6 on row r-5
+        {
+            const int row = r - 5;
+            double lf = sm.ex[prv][4][tid], rt = sm.ex[prv][4][tid + 2];
+            double up = u6[6], dn = u6[4];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = u6[6];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][4][tid];
+            k6w[5] = rhs(up, dn, lf, rt, u6[5], cw[5], a.A);
+        }
+        // ---- y_new on row r-5 (rk.py:66; B[1] = 0)
+        un[5] = fma(a.hb[5], k6w[5], fma(a.hb[4], k5w[5], fma(a.hb[3], k4w[5], fma(a.hb[2], k3w[5],
+                    fma(a.hb[0], k1w[5], yw[5])))));
+        sm.ex[cur][5][tid + 1] = un[5];
+        // ---- k7 = f(y_new) on row r-6, error estimate, outputs
+        {
+            const int row = r - 6;
+            double lf = sm.ex[prv][5][tid], rt = sm.ex[prv][5][tid + 2];
+            double up = un[7], dn = un[5];
+            if (row == 0) up = dn;
+            if (row == a.Ny - 1) dn = un[7];
+            if (x_first) lf = rt;
+            if (x_last) rt = sm.ex[prv][5][tid];
+            const double k7 = rhs(up, dn, lf, rt, un[6], cw[6], a.A);
+            if (col_out && row >= y0 && row < y1) {
+                const size_t g = (size_t)row * a.Nx + gx;
+                a.ynew[g] = un[6];
+                a.k7[g] = k7;
+                // rk.py:106,146-147: err = h * K.E ; scale = atol + max(|y|,|y_new|) * rtol
+                double e = fma(a.he[6], k7, fma(a.he[5], k6w[6], fma(a.he[4], k5w[6], fma(a.he[3], k4w[6],
+                               fma(a.he[2], k3w[6], a.he[0] * k1w[6])))));
+                double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
+                double qq = e / sc;
+                acc = fma(qq, qq, acc);
+#pragma unroll
+                for (int ee = 0; ee < NE; ee++) {
+                    // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
+                    double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
+                                    fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
+                    a.phi[ee][g] = ph;
+                }
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+        // ---- shift windows by one row
+#pragma unroll
+        for (int l = 6; l > 0; l--) { yw[l] = yw[l - 1]; k1w[l] = k1w[l - 1]; cw[l] = cw[l - 1]; }
+        k2w[4] = k2w[3]; k2w[3] = k2w[2]; k2w[2] = k2w[1];
+        k3w[6] = k3w[5]; k3w[5] = k3w[4]; k3w[4] = k3w[3]; k3w[3] = k3w[2];
+        k4w[6] = k4w[5]; k4w[5] = k4w[4]; k4w[4] = k4w[3];
+        k5w[6] = k5w[5]; k5w[5] = k5w[4];
+        k6w[6] = k6w[5];
+        u2[2] = u2[1]; u2[1] = u2[0];
+        u3[3] = u3[2]; u3[2] = u3[1];
+        u4[4] = u4[3]; u4[3] = u4[2];
+        u5[5] = u5[4]; u5[4] = u5[3];
+        u6[6] = u6[5]; u6[5] = u6[4];
+        un[7] = un[6]; un[6] = un[5];
+    }
+    cp_async_wait<0>();
+    // fixed-order CTA reduction of the error partial sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < BX / 32; i++) s += sm.red[i];
+        a.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+}  // namespace fused

@@ -18,7 +18,7 @@ import warnings
 
 import numpy as np
 
-from . import _lib, optimals, pedestrians
+from . import _crowd, _lib, optimals, pedestrians
 from .optimals import _load_config, _load_room
 
 warnings.filterwarnings("ignore")  # simulations.py:15
@@ -69,35 +69,22 @@ class simulation:
         r_in = 0.2
         xs_all, ys_all, vdes_all, key_all, agents = [], [], [], [], []
         X1, Y1 = self._ctx.X, self._ctx.Y
+        box_count = {}
         for box_name in var_room['initial_boxes']:
             box = var_room['initial_boxes'][box_name]
             targets = box[5:]
             key = ' or '.join(targets)
-            V = self.create_potential(var_room, targets)
-            self.Vs[key] = V
-            self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config)
-            self.V += V
-            loc_N = int(box[4] * box[2] * box[3])
+            if key not in self.targets:
+                # The reference rebuilds the potential and the optimals object for every box and overwrites
+                # the dict entries of a repeated key with identical content (simulations.py:116-120,
+                # SURVEY App. C #12); building them once per key gives the same objects and the same RNG stream.
+                V = self.create_potential(var_room, targets)
+                self.Vs[key] = V
+                self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config)
+            box_count[key] = box_count.get(key, 0) + 1
+            xs, ys, v_des_all = _crowd.place_box(box, X1, Y1, self.place_ped, r_in)
+            loc_N = len(xs)
             N += loc_N
-            xs = np.empty(loc_N)
-            ys = np.empty(loc_N)
-            placed = 0
-            while placed < loc_N:
-                x_in = np.random.uniform(box[0] - box[2] / 2, box[0] + box[2] / 2, 1)
-                y_in = np.random.uniform(box[1] - box[3] / 2, box[1] + box[3] / 2, 1)
-                # nodes within r_in of the trial point: only a small window of the grid can qualify, and on
-                # that window the test below is the reference's expression (simulations.py:132-135) verbatim
-                j0, j1 = self._window(X1, x_in[0], r_in)
-                i0, i1 = self._window(Y1, y_in[0], r_in)
-                near = np.sqrt((X1[None, j0:j1] - x_in) ** 2 + (Y1[i0:i1, None] - y_in) ** 2) < r_in
-                sub = self.place_ped[i0:i1, j0:j1]
-                if 1 in sub[near]:
-                    continue
-                sub[near] = 1
-                xs[placed] = x_in[0]
-                ys[placed] = y_in[0]
-                placed += 1
-            v_des_all = np.random.normal(1.34, 0.26, size=loc_N)
             kid = list(self.targets).index(key)
             for i in range(loc_N):
                 a = pedestrians.ped(None, None, self.grid_step, self.Vs[key], key, var_room['targets'], targets,
@@ -107,6 +94,10 @@ class simulation:
                 agents.append(a)
             xs_all.append(xs); ys_all.append(ys); vdes_all.append(v_des_all)
             key_all.append(np.full(loc_N, kid, dtype=np.int32))
+        for key, cnt in box_count.items():
+            # simulations.py:121 adds the key's potential once per box; the values are small integers
+            # (-100, 0, 1), so cnt * V is exactly the repeated sum
+            self.V += cnt * self.Vs[key]
         self.V[self.V > np.min(self.V)] = 0                 # simulations.py:157
         self.N = N
         self.inside = self.N
@@ -134,13 +125,6 @@ class simulation:
         print('ABM simulation room created!')               # simulations.py:162
 
     # ---- helpers -------------------------------------------------------------------------------------
-    @staticmethod
-    def _window(coords, c, r):
-        step = coords[1] - coords[0]
-        lo = int(np.floor((c - r) / step)) - 2
-        hi = int(np.ceil((c + r) / step)) + 3
-        return max(lo, 0), min(hi, len(coords))
-
     @property
     def X_opt(self):
         return np.meshgrid(self._ctx.X, self._ctx.Y)[0]
@@ -177,8 +161,6 @@ class simulation:
     def _keys(self):
         out = []
         for key, opt in self.targets.items():
-            doors = np.array([self._room['targets'][t] for t in key.split(' or ')], dtype=np.float64) \
-                if key else np.zeros((0, 4))
             out.append(dict(V=opt.d_V, tiles=opt.d_tiles, v_min=opt.v_min, vx=opt.d_vx, vy=opt.d_vy,
                             nt_opt=opt.nt_opt, doors=self._doors[key]))
         return out

@@ -86,7 +86,8 @@ def hjb_rhs(phi, V, m, dx, dy, sigma, mu, g):
     return out
 
 
-def hjb_solve(V, m, T, nt, dx=0.05, dy=0.05, sigma=0.2, mu=5.0, g=-0.005, rtol=1e-3, atol=1e-6, trace_cap=100000):
+def hjb_solve(V, m, T, nt, dx=0.05, dy=0.05, sigma=0.2, mu=5.0, g=-0.005, rtol=1e-3, atol=1e-6, trace_cap=100000,
+              forced_h=None, forced_err=None):
     """Returns (phi_cols (nt, Ny*Nx) with row k = sol.y[:,k], stats dict, trace_h, trace_err)."""
     V = _d(V); Ny, Nx = V.shape
     m = None if m is None else _d(m)
@@ -97,7 +98,9 @@ def hjb_solve(V, m, T, nt, dx=0.05, dy=0.05, sigma=0.2, mu=5.0, g=-0.005, rtol=1
     ntr = C.c_int()
     lib().oco_hjb_solve(_p(V), _p(m), Ny, Nx, C.c_double(dx), C.c_double(dy), C.c_double(sigma), C.c_double(mu),
                         C.c_double(g), C.c_double(T), _p(t_eval), nt, C.c_double(rtol), C.c_double(atol), _p(phi),
-                        C.byref(st), _p(th), _p(te), trace_cap, C.byref(ntr))
+                        C.byref(st), _p(th), _p(te), trace_cap, C.byref(ntr),
+                        None if forced_h is None else _p(_d(forced_h)),
+                        None if forced_err is None else _p(_d(forced_err)), 0 if forced_h is None else len(forced_h))
     n = min(ntr.value, trace_cap)
     stats = {f: getattr(st, f) for f, _ in HjbStats._fields_}
     return phi, stats, th[:n].copy(), te[:n].copy()

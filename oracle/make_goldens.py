@@ -220,6 +220,30 @@ def unit_golden(name="units"):
     print("wrote", name)
 
 
+def run_golden(name, room, T, recompute=False, rooms=None, seed=0):
+    """Whole `simulation.run()` of the reference: trajectories, evacuation times, exit order."""
+    with rh.RefEnv(rooms) as env:
+        np.random.seed(seed)
+        with env.silence():
+            simu = env.simulations.simulation(room, T, recompute)
+            simu.run()
+        N = simu.N
+        steps = max(len(a.traj) for a in simu.agents)
+        traj = np.full((N, steps, 4), np.nan)
+        for i, a in enumerate(simu.agents):
+            traj[i, :len(a.traj), :2] = np.array(a.traj)
+            traj[i, :len(a.vels), 2:] = np.array(a.vels)
+        save = {"versions": versions(), "T": T, "seed": seed, "recompute": int(recompute),
+                "room": json.dumps(rooms[room] if rooms and room in rooms else json.load(open(f"rooms/{room}.json"))),
+                "traj": traj, "agent_time": np.array([a.time for a in simu.agents]),
+                "status": np.array([a.status for a in simu.agents], dtype=np.uint8), "time": simu.time,
+                "simu_step": simu.simu_step, "inside": simu.inside, "n_history": len(simu.history),
+                "v_des": np.array([a.v_des for a in simu.agents]),
+                "nt_opt_final": np.array([simu.targets[k].nt_opt for k in simu.targets])}
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+        print("wrote", name, "steps", simu.simu_step, "time", simu.time, "inside", simu.inside)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     os.chdir(os.path.dirname(OUT.rstrip("/")) + "/..")
@@ -230,3 +254,6 @@ if __name__ == "__main__":
     hjb_golden("hjb_exit_opposite_T1", "exit_opposite", 1.0)
     gcfm_golden("gcfm_dense", "dense", 6.0, rooms=rooms, n_steps=160, field_every=8)
     gcfm_golden("gcfm_small", "small", 6.0, rooms=rooms, n_steps=250, field_every=10)
+    run_golden("run_room_test_T30", "room_test", 30.0)
+    run_golden("run_room_test_T4", "room_test", 4.0)
+    run_golden("run_exit_opposite_T4_recompute", "exit_opposite", 4.0, recompute=True)

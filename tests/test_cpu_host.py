@@ -1,0 +1,91 @@
+"""CPU tests of the host-side logic: library exports, grid rule, crowd placement RNG parity, sampler index
+semantics, synthetic rooms."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO, golden, room_grid
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from optimal_crowds_b200 import _lib
+    from optimal_crowds_b200.build import build_lib
+    build_lib()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    hdr = open(os.path.join(REPO, "include", "optimal_crowds.h")).read()
+    declared = set(re.findall(r"\b(oc_[a-z_0-9]+)\s*\(", hdr))
+    assert {"oc_hjb_solve", "oc_gcfm_step", "oc_rasterise", "oc_density", "oc_ctx_create"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in optimal_crowds.h but not exported"
+    assert set(_lib.EXPORTS) <= declared
+    lib.oc_abi_version.restype = ctypes.c_int
+    assert lib.oc_abi_version() == 1
+
+
+def test_no_cpu_fallback_context_raises_without_gpu():
+    import torch
+    from optimal_crowds_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.Context(10.0, 6.0, 0.05)
+
+
+def test_grid_rule_quirk():
+    """simulations.py:63-64: 10//0.05 == 199.0 -> 200 nodes; nodes_to_length inverts the rule exactly."""
+    from optimal_crowds_b200 import _lib, synthetic
+    assert _lib.grid_shape(10.0, 6.0, 0.05) == (120, 200)
+    for n in (512, 2048, 4096, 16384):
+        L = synthetic.nodes_to_length(n)
+        assert _lib.grid_shape(L, L, 0.05) == (n, n)
+    assert abs(synthetic.nodes_to_length(16384) - 819.175) < 1e-9
+
+
+@pytest.mark.parametrize("rname", ["room_test", "exit_opposite", "dense", "small"])
+def test_crowd_placement_consumes_rng_like_reference(rname):
+    """same seed -> bit-identical initial positions and v_des as the reference's full-grid rejection sampler."""
+    from optimal_crowds_b200 import _crowd
+    u = golden("units")
+    room = json.loads(str(u[f"rast_{rname}_room"]))
+    L, H, Ny, Nx, X, Y = room_grid(room)
+    np.random.seed(2)
+    place = np.zeros((Ny, Nx))
+    xs, ys, vd = [], [], []
+    for box in room["initial_boxes"].values():
+        x, y, v = _crowd.place_box(box, X, Y, place)
+        xs.append(x); ys.append(y); vd.append(v)
+    xy = np.column_stack([np.concatenate(xs), np.concatenate(ys)])
+    assert np.array_equal(xy, u[f"dens_{rname}_xy"])
+    assert np.array_equal(np.concatenate(vd), u[f"init_{rname}_vdes"])
+
+
+def test_sampler_axis_nodes_match_reference_index_rule():
+    from optimal_crowds_b200.optimals import optimals
+    L, dx, Nx = 10.0, 0.05, 200
+    f = optimals._axis_nodes
+    assert f(0.02, L, dx, Nx) == [0]
+    assert f(0.05, L, dx, Nx) == [1]                 # x > dx is strict (optimals.py:236)
+    assert f(0.050001, L, dx, Nx) == [1, 2]
+    assert f(0.15000000000000002, L, dx, Nx) == [3, 4]
+    assert f(9.95, L, dx, Nx) == [Nx - 3]            # x >= L - dx  (optimals.py:238-239)
+    assert f(9.96, L, dx, Nx) == [Nx - 3]
+    assert f(9.9, L, dx, Nx) == [int(9.9 // dx), int(9.9 // dx) + 1]   # out of range for the (Nx-2) field: IndexError later
+
+
+def test_synthetic_rooms_follow_schema_and_counts():
+    from optimal_crowds_b200 import synthetic
+    for room, n_agents in ((synthetic.slalom_room(16384, 2048, 12500), 12500), (synthetic.metro_room(4096, 10000), 10000),
+                           (synthetic.ensemble_room(512, 1000), 1000)):
+        assert set(room) == {"room_length", "room_height", "initial_boxes", "targets", "walls", "holes", "cylinders"}
+        n = sum(int(b[4] * b[2] * b[3]) for b in room["initial_boxes"].values())
+        assert n == n_agents
+        for b in room["initial_boxes"].values():
+            assert all(t in room["targets"] for t in b[5:])
+    r = synthetic.slalom_room(16384, 2048, 12500)
+    assert len({" or ".join(b[5:]) for b in r["initial_boxes"].values()}) == 1   # one HJB key
+    m = synthetic.metro_room()
+    assert len({" or ".join(b[5:]) for b in m["initial_boxes"].values()}) == 4   # four HJB keys
