@@ -131,9 +131,16 @@ typedef struct {
     const double *d_V;            /* (Ny,Nx) remapped potential of this target set (simulation.Vs[key]) */
     const uint8_t *d_wall_tiles;  /* oc_wall_tiles() occupancy map of d_V (accelerates the exact argmin) */
     double v_min;                 /* min(V) over the grid, from oc_wall_tiles() */
-    const double *d_vx, *d_vy;    /* (n_slices,Ny-2,Nx-2) optimal velocity field */
+    const double *d_vx, *d_vy;    /* (n_slices,Ny-2,Nx-2) optimal velocity field, or NULL when d_phi is given */
     int nt_opt;                   /* optimals.nt_opt (optimals.py:140,231) */
     int n_slices;
+    /* phi storage (half the memory, no conversion pass): (n_phi,Ny,Nx) samples as written by oc_hjb_solve's
+     * d_phi (slice k = sol.y[:,k]); the sampler differentiates on the fly with the same device function the
+     * velocity epilogue uses: vx_opt[s] == vels(d_phi[nt_opt-1-s]) (optimals.py:200-204), mu/lim below */
+    const double *d_phi;
+    int n_phi;
+    int pad_;
+    double mu, lim;
     const double *doors;          /* host (n_doors,4): cx,cy,w,h of the box's targets (pedestrians.py:132-135) */
     int n_doors;
 } oc_key;

@@ -66,7 +66,9 @@ class GcfmParams(C.Structure):
 
 class Key(C.Structure):
     _fields_ = [("d_V", C.c_void_p), ("d_wall_tiles", C.c_void_p), ("v_min", C.c_double), ("d_vx", C.c_void_p),
-                ("d_vy", C.c_void_p), ("nt_opt", C.c_int), ("n_slices", C.c_int), ("doors", dp), ("n_doors", C.c_int)]
+                ("d_vy", C.c_void_p), ("nt_opt", C.c_int), ("n_slices", C.c_int), ("d_phi", C.c_void_p),
+                ("n_phi", C.c_int), ("pad_", C.c_int), ("mu", C.c_double), ("lim", C.c_double), ("doors", dp),
+                ("n_doors", C.c_int)]
 
 
 _lib = None
@@ -198,10 +200,10 @@ class Context:
 
     # ---- HJB
     def hjb_solve(self, V, m, prm: HjbParams, T, nt, want_phi=False, want_vel=True, trace=False, out_vx=None,
-                  out_vy=None):
+                  out_vy=None, out_phi=None):
         t_eval = np.linspace(T, 0, nt)  # optimals.py:194
         n = self.Ny * self.Nx
-        phi = self.empty(nt, self.Ny, self.Nx) if want_phi else None
+        phi = out_phi if out_phi is not None else (self.empty(nt, self.Ny, self.Nx) if want_phi else None)
         vx = vy = None
         if want_vel:
             vx = out_vx if out_vx is not None else self.empty(max(nt - 1, 0), self.Ny - 2, self.Nx - 2)
@@ -248,10 +250,13 @@ class Context:
         for q, k in enumerate(keys):
             doors = np.ascontiguousarray(np.asarray(k["doors"], dtype=np.float64).reshape(-1, 4))
             keep.append(doors)
+            phi = k.get("phi")
             karr[q] = Key(k["V"].data_ptr(), k["tiles"].data_ptr(), float(k["v_min"]),
                           k["vx"].data_ptr() if k.get("vx") is not None else None,
                           k["vy"].data_ptr() if k.get("vy") is not None else None, int(k["nt_opt"]),
-                          int(k["vx"].shape[0]) if k.get("vx") is not None else 0, _hp(doors), len(doors))
+                          int(k["vx"].shape[0]) if k.get("vx") is not None else 0,
+                          phi.data_ptr() if phi is not None else None, int(phi.shape[0]) if phi is not None else 0, 0,
+                          float(k.get("mu", 5.0)), float(k.get("lim", 10e-3)), _hp(doors), len(doors))
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 2)
         exit_log = np.empty(max(N, 1), dtype=np.int32)

@@ -33,7 +33,7 @@ def _stale(target, deps):
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(HERE, "..", "include", "optimal_crowds.h"))
     objs = []
     for src, extra in UNITS.items():

@@ -22,6 +22,7 @@
 
 #include "oc_common.h"
 #include "oc_math.h"
+#include "oc_vels.h"
 
 namespace {
 
@@ -34,8 +35,10 @@ struct KeyDev {
     const double *V;
     const uint8_t *tiles;
     const double *vx, *vy;
-    int nt_opt, n_slices, door_off, n_doors;
+    const double *phi;  // alternative field storage: phi samples, differentiated on the fly
+    int nt_opt, n_slices, door_off, n_doors, n_phi;
     double off_min;  // v_min * 10e3
+    double mu, lim;
 };
 
 struct Ws {  // device workspace carved out of ctx->gcfm_ws
@@ -93,14 +96,36 @@ __device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double 
         i0 = i1 = p.Ny - 3;
     }
     const int W = p.Nx - 2, H = p.Ny - 2;
-    if (j0 < 0 || j1 >= W || i0 < 0 || i1 >= H || t < 0 || t >= k.n_slices) return 1;
-    const double *sx = k.vx + (size_t)t * W * H, *sy = k.vy + (size_t)t * W * H;
+    if (j0 < 0 || j1 >= W || i0 < 0 || i1 >= H || t < 0) return 1;
+    double ax, ay, bx, by;
+    if (k.vx) {
+        if (t >= k.n_slices) return 1;
+        const double *sx = k.vx + (size_t)t * W * H, *sy = k.vy + (size_t)t * W * H;
+        ax = sx[i0 * W + j0]; ay = sy[i0 * W + j0];
+        bx = sx[i1 * W + j1]; by = sy[i1 * W + j1];
+    } else {
+        // vx_opt[t] = vels(sol.y[:, nt_opt-1-t]) (optimals.py:200-204), evaluated at the two sampled nodes
+        const int kd = k.nt_opt - 1 - t;
+        if (kd < 0 || kd >= k.n_phi) return 1;
+        const double *ph = k.phi + (size_t)kd * p.Ny * p.Nx;
+        const double i2x = 1.0 / (2 * p.dx), i2y = 1.0 / (2 * p.dy);
+        {
+            const double *c = ph + (size_t)(i0 + 1) * p.Nx + (j0 + 1);
+            vels_point(clamp_lim(c[0], k.lim), clamp_lim(c[-1], k.lim), clamp_lim(c[1], k.lim),
+                       clamp_lim(c[-p.Nx], k.lim), clamp_lim(c[p.Nx], k.lim), k.mu, k.lim, i2x, i2y, ax, ay);
+        }
+        {
+            const double *c = ph + (size_t)(i1 + 1) * p.Nx + (j1 + 1);
+            vels_point(clamp_lim(c[0], k.lim), clamp_lim(c[-1], k.lim), clamp_lim(c[1], k.lim),
+                       clamp_lim(c[-p.Nx], k.lim), clamp_lim(c[p.Nx], k.lim), k.mu, k.lim, i2x, i2y, bx, by);
+        }
+    }
     if (j0 == j1 && i0 == i1) {
-        ox = sx[i0 * W + j0];
-        oy = sy[i0 * W + j0];
+        ox = ax;
+        oy = ay;
     } else {  // two fancy-index lists pair up element-wise: (i0,j0),(i1,j1); np.mean = (a+b)/2
-        ox = (sx[i0 * W + j0] + sx[i1 * W + j1]) / 2.0;
-        oy = (sy[i0 * W + j0] + sy[i1 * W + j1]) / 2.0;
+        ox = (ax + bx) / 2.0;
+        oy = (ay + by) / 2.0;
     }
     return 0;
 }
@@ -696,8 +721,11 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     int off = 0;
     for (int k = 0; k < n_keys; k++) {
         OC_ARG(keys[k].d_V && keys[k].d_wall_tiles, "key without potential / wall tiles");
-        hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy, keys[k].nt_opt,
-                       keys[k].d_vx ? keys[k].n_slices : 0, off, keys[k].n_doors, keys[k].v_min * 10e3};
+        OC_ARG(!keys[k].d_vx == !keys[k].d_vy, "d_vx and d_vy must be given together");
+        hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy,
+                       keys[k].d_vx ? nullptr : keys[k].d_phi, keys[k].nt_opt, keys[k].d_vx ? keys[k].n_slices : 0, off,
+                       keys[k].n_doors, (keys[k].d_vx || !keys[k].d_phi) ? 0 : keys[k].n_phi, keys[k].v_min * 10e3,
+                       keys[k].mu, keys[k].lim};
         for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
         off += keys[k].n_doors;
     }

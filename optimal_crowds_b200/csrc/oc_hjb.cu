@@ -17,6 +17,7 @@
 
 #include "oc_common.h"
 #include "oc_hjb_fused.cuh"
+#include "oc_vels.h"
 
 namespace {
 
@@ -203,27 +204,8 @@ struct DenseArgs {
     double *phi[DMAX];    // (Ny,Nx) slice or NULL
     double *vx[DMAX];     // (Ny-2,Nx-2) slice or NULL
     double *vy[DMAX];
-    double mu, lim, two_dx, two_dy;
+    double mu, lim, inv_two_dx, inv_two_dy;
 };
-
-__device__ __forceinline__ double clamp_lim(double p, double lim) {
-    // optimals.py:172: phi*(phi > lim) + lim*(phi < lim)
-    return p * (p > lim ? 1.0 : 0.0) + lim * (p < lim ? 1.0 : 0.0);
-}
-
-__device__ __forceinline__ void vels_point(double pc0, double pW, double pE, double pS, double pN, double mu,
-                                           double lim, double two_dx, double two_dy, double &ox, double &oy) {
-    // inputs already clamped once (:172); :174-186
-    double gx = (pE - pW) / two_dx;
-    double gy = (pN - pS) / two_dy;
-    double pc = clamp_lim(pc0, lim);  // :177 second clamp
-    double ux = gx / (mu * pc), uy = gy / (mu * pc);
-    double nr = sqrt(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));  // no FMA: bit-equal to numpy (:182)
-    double gt = nr > lim ? 1.0 : 0.0, lt = nr < lim ? 1.0 : 0.0;
-    double den = nr * gt + lt;
-    ox = (ux * gt) / den;
-    oy = (uy * gt) / den;
-}
 
 __global__ void __launch_bounds__(NTHREADS) hjb_dense_kernel(DenseArgs a, int Ny, int Nx) {
     __shared__ double tile[DCELLS];
@@ -277,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS) hjb_dense_kernel(DenseArgs a, int Ny
                 if (gy >= 1 && gy < Ny - 1 && gx >= 1 && gx < Nx - 1) {
                     const double *t = tile + (ly + 1) * DSW + (lx + 1);
                     double ox, oy;
-                    vels_point(t[0], t[-1], t[1], t[-DSW], t[DSW], a.mu, a.lim, a.two_dx, a.two_dy, ox, oy);
+                    vels_point(t[0], t[-1], t[1], t[-DSW], t[DSW], a.mu, a.lim, a.inv_two_dx, a.inv_two_dy, ox, oy);
                     size_t o = (size_t)(gy - 1) * (Nx - 2) + (gx - 1);
                     a.vx[e][o] = ox;
                     a.vy[e][o] = oy;
@@ -289,14 +271,14 @@ __global__ void __launch_bounds__(NTHREADS) hjb_dense_kernel(DenseArgs a, int Ny
 
 // standalone vels (optimals.py:168-186) for unit parity
 __global__ void __launch_bounds__(NTHREADS)
-vels_kernel(const double *__restrict__ phi, int Ny, int Nx, double mu, double lim, double two_dx, double two_dy,
-            double *__restrict__ vx, double *__restrict__ vy) {
+vels_kernel(const double *__restrict__ phi, int Ny, int Nx, double mu, double lim, double inv_two_dx,
+            double inv_two_dy, double *__restrict__ vx, double *__restrict__ vy) {
     int gx = blockIdx.x * 64 + (threadIdx.x & 63) + 1, gy = blockIdx.y * 4 + (threadIdx.x >> 6) + 1;
     if (gy >= Ny - 1 || gx >= Nx - 1) return;
     size_t g = (size_t)gy * Nx + gx;
     double ox, oy;
     vels_point(clamp_lim(phi[g], lim), clamp_lim(phi[g - 1], lim), clamp_lim(phi[g + 1], lim),
-               clamp_lim(phi[g - Nx], lim), clamp_lim(phi[g + Nx], lim), mu, lim, two_dx, two_dy, ox, oy);
+               clamp_lim(phi[g - Nx], lim), clamp_lim(phi[g + Nx], lim), mu, lim, inv_two_dx, inv_two_dy, ox, oy);
     size_t o = (size_t)(gy - 1) * (Nx - 2) + (gx - 1);
     vx[o] = ox;
     vy[o] = oy;
@@ -481,8 +463,8 @@ extern "C" int oc_hjb_vels(oc_ctx *ctx, const double *d_phi, const oc_hjb_params
     OC_ARG(ctx && d_phi && prm && d_vx && d_vy, "NULL argument");
     OC_CUDA(cudaSetDevice(ctx->device));
     dim3 grid((ctx->Nx - 2 + 63) / 64, (ctx->Ny - 2 + 3) / 4);
-    vels_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(d_phi, ctx->Ny, ctx->Nx, prm->mu, prm->lim, 2 * ctx->dx,
-                                                             2 * ctx->dy, d_vx, d_vy);
+    vels_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(d_phi, ctx->Ny, ctx->Nx, prm->mu, prm->lim,
+                                                             1.0 / (2 * ctx->dx), 1.0 / (2 * ctx->dy), d_vx, d_vy);
     oc::count_launch();
     OC_CUDA(cudaGetLastError());
     return OC_OK;
@@ -712,7 +694,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                     const int sl = nt - 1 - kd;
                     dim3 grid((s.Nx - 2 + 63) / 64, (s.Ny - 2 + 3) / 4);
                     s.begin(1, 8.0 * (double)n * 3);
-                    vels_kernel<<<grid, NTHREADS, 0, s.st>>>(ph, s.Ny, s.Nx, prm->mu, prm->lim, 2 * ctx->dx, 2 * ctx->dy,
+                    vels_kernel<<<grid, NTHREADS, 0, s.st>>>(ph, s.Ny, s.Nx, prm->mu, prm->lim, 1.0 / (2 * ctx->dx), 1.0 / (2 * ctx->dy),
                                                              d_vx + (size_t)sl * n_int, d_vy + (size_t)sl * n_int);
                     s.end();
                     s.launches++;
@@ -726,7 +708,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                 DenseArgs a{};
                 a.yold = s.y;
                 for (int j = 0; j < 7; j++) { a.k[j] = s.K[j]; for (int p = 0; p < 4; p++) a.P[j][p] = RK_P[j][p]; }
-                a.h = hh; a.mu = prm->mu; a.lim = prm->lim; a.two_dx = 2 * ctx->dx; a.two_dy = 2 * ctx->dy;
+                a.h = hh; a.mu = prm->mu; a.lim = prm->lim; a.inv_two_dx = 1.0 / (2 * ctx->dx); a.inv_two_dy = 1.0 / (2 * ctx->dy);
                 int e = 0;
                 bool any = false;
                 for (; e < DMAX && ia >= t_eval_i_new; ia--) {

@@ -23,11 +23,13 @@
 
 namespace fused {
 
-constexpr int BX = 256;             // threads per CTA = columns per tile incl. halo
+constexpr int BX = 128;             // threads per CTA = columns per tile incl. halo
 constexpr int HX = 8;               // halo columns per side (6 needed)
-constexpr int VX = BX - 2 * HX;     // valid output columns per tile (240)
+constexpr int VX = BX - 2 * HX;     // valid output columns per tile (112)
 constexpr int HY = 6;               // halo rows per side
-constexpr int PF = 8;               // cp.async ring depth (rows), power of two
+constexpr int PF = 16;              // cp.async ring depth (rows), power of two: rows r-6 .. r+PD live
+constexpr int PD = 8;               // prefetch distance (rows in flight)
+constexpr int CTAS_PER_SM = 3;      // 3 x 61 KB shared memory, <= 170 registers/thread
 constexpr int NE_MAX = 6;           // dense-output samples per launch
 
 struct Args {
@@ -52,11 +54,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// optimals.py:154-162 with mirror ghosts (:149-152) resolved by the caller
-__device__ __forceinline__ double rhs(double up, double dn, double lf, double rt, double C, double cf, double A) {
-    double lap = (up + dn) + (lf + rt) - 4.0 * C;
-    double r = A * lap - cf * C;
-    return (cf != cf) ? 0.0 : r;
+// optimals.py:154-162.  Mirror ghosts (:149-152) need no special case here: rows/columns outside the grid
+// are LOADED from their mirror image (row -j -> row j, row Ny-1+j -> Ny-1-j), the stencil commutes with
+// that reflection, so every stage input is automatically even about the boundary and the value the
+// reference reads from its ghost cell (ghost(-1) = value(1)) is exactly what sits in the halo.
+// The newest row `dn` of the stage input is produced in the same iteration, so the evaluation is split
+// into a part that does not depend on it (`pre`) and one FMA that does: the serial chain through the six
+// stages of one row iteration is 2 FMAs per stage.
+__device__ __forceinline__ double rhs_pre(double up, double lf, double rt, double C, double cf, double A) {
+    double S = (up + lf) + fma(-4.0, C, rt);
+    return fma(A, S, -(cf * C));
+}
+__device__ __forceinline__ double rhs_fin(double pre, double dn, double cf, double A) {
+    double r = fma(A, dn, pre);
+    return (cf != cf) ? 0.0 : r;  // wall: optimals.py:162
+}
+
+// 1/x for finite x > 0 (the error scale is >= atol): hardware seed + two Newton steps (~1e-16), no slow path
+__device__ __forceinline__ double rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 }
 
 struct Smem {
@@ -65,26 +87,28 @@ struct Smem {
     double red[BX / 32];
 };
 
+__device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
 template <int NE>
-__global__ void __launch_bounds__(BX, 1) hjb_fused_kernel(const Args a) {
+__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
     const int gx = blockIdx.x * VX - HX + tid;
+    const int gxm = min(max(mirror(gx, a.Nx), 0), a.Nx - 1);  // column this thread loads (clamped far outside)
     const int y0 = blockIdx.y * a.RC;
     const int y1 = min(y0 + a.RC, a.Ny);
-    const bool col_ok = gx >= 0 && gx < a.Nx;
     const bool col_out = tid >= HX && tid < BX - HX && gx < a.Nx;  // columns this thread stores
-    const bool x_first = gx == 0, x_last = gx == a.Nx - 1;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
 
     // windows, indexed by lag (row r - lag)
-    double yw[7], k1w[7], cw[7], k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
+    // y, k1 = f and coef of rows r-6..r stay in the cp.async ring (read back by the owning thread, no sync);
+    // k2..k6 and the stage inputs are register windows
+    double k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
     double u2[3], u3[4], u4[5], u5[6], u6[7], un[8];
 #pragma unroll
-    for (int i = 0; i < 7; i++) { yw[i] = 0; k1w[i] = 0; cw[i] = qnan; k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
+    for (int i = 0; i < 7; i++) { k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
 #pragma unroll
     for (int i = 0; i < 5; i++) k2w[i] = 0;
     u2[0] = u2[1] = u2[2] = 0; u3[1] = u3[2] = u3[3] = 0; u4[2] = u4[3] = u4[4] = 0;
@@ -92,120 +116,75 @@ __global__ void __launch_bounds__(BX, 1) hjb_fused_kernel(const Args a) {
 
     const int r_begin = y0 - HY, r_end = y1 + HY;  // rows loaded: [r_begin, r_end)
     auto issue = [&](int row) {
-        const int slot = row & (PF - 1);
-        if (row >= r_end) {
-            // past the chunk: nothing to stage (keeps one commit group per iteration)
-        } else if (col_ok && row >= 0 && row < a.Ny) {
-            const size_t g = (size_t)row * a.Nx + gx;
+        if (row < r_end) {
+            const int slot = row & (PF - 1);
+            const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
+            const size_t g = (size_t)rm * a.Nx + gxm;
             cp_async8(&sm.pf[slot][0][tid], a.y + g);
             cp_async8(&sm.pf[slot][1][tid], a.k1 + g);
             cp_async8(&sm.pf[slot][2][tid], a.coef + g);
-        } else {
-            sm.pf[slot][0][tid] = 0.0;
-            sm.pf[slot][1][tid] = 0.0;
-            sm.pf[slot][2][tid] = qnan;
         }
-        cp_async_commit();
+        cp_async_commit();  // one group per iteration, possibly empty
     };
 
+    // rows older than r_begin are read (as don't-care values) during the first iterations: define them
 #pragma unroll 1
-    for (int q = 0; q < PF - 1; q++) issue(r_begin + q);
+    for (int q = 0; q < PF; q++) { sm.pf[q][0][tid] = 0.0; sm.pf[q][1][tid] = 0.0; sm.pf[q][2][tid] = 0.0; }
+#pragma unroll 1
+    for (int q = 0; q < PD; q++) issue(r_begin + q);
     __syncthreads();
 
     double acc = 0.0;
     int buf = 0;
 #pragma unroll 2
     for (int r = r_begin; r < r_end; r++) {
-        issue(r + PF - 1);
-        cp_async_wait<PF - 1>();
-        {
-            const int slot = r & (PF - 1);
-            yw[0] = sm.pf[slot][0][tid];
-            k1w[0] = sm.pf[slot][1][tid];
-            cw[0] = sm.pf[slot][2][tid];
+        issue(r + PD);
+        cp_async_wait<PD>();
+        double yw[7], k1w[7], cw[7];
+#pragma unroll
+        for (int l = 0; l < 7; l++) {
+            const int slot = (r - l) & (PF - 1);
+            yw[l] = sm.pf[slot][0][tid];
+            k1w[l] = sm.pf[slot][1][tid];
+            cw[l] = sm.pf[slot][2][tid];
         }
-        const int cur = buf, prv = buf ^ 1;
-        // ---- stage 2 input on row r
-        u2[0] = fma(a.ha21, k1w[0], yw[0]);
-        sm.ex[cur][0][tid + 1] = u2[0];
-        // ---- k2 on row r-1
-        {
-            const int row = r - 1;
-            double lf = sm.ex[prv][0][tid], rt = sm.ex[prv][0][tid + 2];
-            double up = u2[2], dn = u2[0];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = u2[2];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][0][tid];
-            k2w[1] = rhs(up, dn, lf, rt, u2[1], cw[1], a.A);
-        }
-        u3[1] = fma(a.ha3[1], k2w[1], fma(a.ha3[0], k1w[1], yw[1]));
-        sm.ex[cur][1][tid + 1] = u3[1];
-        // ---- k3 on row r-2
-        {
-            const int row = r - 2;
-            double lf = sm.ex[prv][1][tid], rt = sm.ex[prv][1][tid + 2];
-            double up = u3[3], dn = u3[1];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = u3[3];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][1][tid];
-            k3w[2] = rhs(up, dn, lf, rt, u3[2], cw[2], a.A);
-        }
-        u4[2] = fma(a.ha4[2], k3w[2], fma(a.ha4[1], k2w[2], fma(a.ha4[0], k1w[2], yw[2])));
-        sm.ex[cur][2][tid + 1] = u4[2];
-        // ---- k4 on row r-3
-        {
-            const int row = r - 3;
-            double lf = sm.ex[prv][2][tid], rt = sm.ex[prv][2][tid + 2];
-            double up = u4[4], dn = u4[2];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = u4[4];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][2][tid];
-            k4w[3] = rhs(up, dn, lf, rt, u4[3], cw[3], a.A);
-        }
-        u5[3] = fma(a.ha5[3], k4w[3], fma(a.ha5[2], k3w[3], fma(a.ha5[1], k2w[3], fma(a.ha5[0], k1w[3], yw[3]))));
-        sm.ex[cur][3][tid + 1] = u5[3];
-        // ---- k5 on row r-4
-        {
-            const int row = r - 4;
-            double lf = sm.ex[prv][3][tid], rt = sm.ex[prv][3][tid + 2];
-            double up = u5[5], dn = u5[3];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = u5[5];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][3][tid];
-            k5w[4] = rhs(up, dn, lf, rt, u5[4], cw[4], a.A);
-        }
-        u6[4] = fma(a.ha6[4], k5w[4], fma(a.ha6[3], k4w[4], fma(a.ha6[2], k3w[4], fma(a.ha6[1], k2w[4],
-                    fma(a.ha6[0], k1w[4], yw[4])))));
-        sm.ex[cur][4][tid + 1] = u6[4];
-        // ---- k6 on row r-5
-        {
-            const int row = r - 5;
-            double lf = sm.ex[prv][4][tid], rt = sm.ex[prv][4][tid + 2];
-            double up = u6[6], dn = u6[4];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = u6[6];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][4][tid];
-            k6w[5] = rhs(up, dn, lf, rt, u6[5], cw[5], a.A);
-        }
-        // ---- y_new on row r-5 (rk.py:66; B[1] = 0)
-        un[5] = fma(a.hb[5], k6w[5], fma(a.hb[4], k5w[5], fma(a.hb[3], k4w[5], fma(a.hb[2], k3w[5],
-                    fma(a.hb[0], k1w[5], yw[5])))));
-        sm.ex[cur][5][tid + 1] = un[5];
-        // ---- k7 = f(y_new) on row r-6, error estimate, outputs
+        const double *exp_ = &sm.ex[buf ^ 1][0][tid];  // previous iteration's rows: [s*(BX+2)] left, [+2] right
+        double *exc = &sm.ex[buf][0][tid + 1];
+        // parts of the six stencils that do not depend on this iteration's new rows
+        const double p2 = rhs_pre(u2[2], exp_[0 * (BX + 2)], exp_[0 * (BX + 2) + 2], u2[1], cw[1], a.A);
+        const double p3 = rhs_pre(u3[3], exp_[1 * (BX + 2)], exp_[1 * (BX + 2) + 2], u3[2], cw[2], a.A);
+        const double p4 = rhs_pre(u4[4], exp_[2 * (BX + 2)], exp_[2 * (BX + 2) + 2], u4[3], cw[3], a.A);
+        const double p5 = rhs_pre(u5[5], exp_[3 * (BX + 2)], exp_[3 * (BX + 2) + 2], u5[4], cw[4], a.A);
+        const double p6 = rhs_pre(u6[6], exp_[4 * (BX + 2)], exp_[4 * (BX + 2) + 2], u6[5], cw[5], a.A);
+        const double p7 = rhs_pre(un[7], exp_[5 * (BX + 2)], exp_[5 * (BX + 2) + 2], un[6], cw[6], a.A);
+        // stage-input partial sums that do not depend on this iteration's new k's (rk.py:63-64, premultiplied by h)
+        const double q3 = fma(a.ha3[0], k1w[1], yw[1]);
+        const double q4 = fma(a.ha4[1], k2w[2], fma(a.ha4[0], k1w[2], yw[2]));
+        const double q5 = fma(a.ha5[2], k3w[3], fma(a.ha5[1], k2w[3], fma(a.ha5[0], k1w[3], yw[3])));
+        const double q6 = fma(a.ha6[3], k4w[4], fma(a.ha6[2], k3w[4], fma(a.ha6[1], k2w[4], fma(a.ha6[0], k1w[4], yw[4]))));
+        const double qn = fma(a.hb[4], k5w[5], fma(a.hb[3], k4w[5], fma(a.hb[2], k3w[5], fma(a.hb[0], k1w[5], yw[5]))));
+        // ---- the serial chain of this row iteration
+        u2[0] = fma(a.ha21, k1w[0], yw[0]);            // stage 2 input on row r
+        k2w[1] = rhs_fin(p2, u2[0], cw[1], a.A);       // k2 on row r-1
+        u3[1] = fma(a.ha3[1], k2w[1], q3);
+        k3w[2] = rhs_fin(p3, u3[1], cw[2], a.A);       // k3 on row r-2
+        u4[2] = fma(a.ha4[2], k3w[2], q4);
+        k4w[3] = rhs_fin(p4, u4[2], cw[3], a.A);       // k4 on row r-3
+        u5[3] = fma(a.ha5[3], k4w[3], q5);
+        k5w[4] = rhs_fin(p5, u5[3], cw[4], a.A);       // k5 on row r-4
+        u6[4] = fma(a.ha6[4], k5w[4], q6);
+        k6w[5] = rhs_fin(p6, u6[4], cw[5], a.A);       // k6 on row r-5
+        un[5] = fma(a.hb[5], k6w[5], qn);              // y_new on row r-5 (rk.py:66; B[1] = 0)
+        const double k7 = rhs_fin(p7, un[5], cw[6], a.A);  // k7 = f(y_new) on row r-6
+        exc[0 * (BX + 2)] = u2[0];
+        exc[1 * (BX + 2)] = u3[1];
+        exc[2 * (BX + 2)] = u4[2];
+        exc[3 * (BX + 2)] = u5[3];
+        exc[4 * (BX + 2)] = u6[4];
+        exc[5 * (BX + 2)] = un[5];
+        // ---- outputs on row r-6
         {
             const int row = r - 6;
-            double lf = sm.ex[prv][5][tid], rt = sm.ex[prv][5][tid + 2];
-            double up = un[7], dn = un[5];
-            if (row == 0) up = dn;
-            if (row == a.Ny - 1) dn = un[7];
-            if (x_first) lf = rt;
-            if (x_last) rt = sm.ex[prv][5][tid];
-            const double k7 = rhs(up, dn, lf, rt, un[6], cw[6], a.A);
             if (col_out && row >= y0 && row < y1) {
                 const size_t g = (size_t)row * a.Nx + gx;
                 a.ynew[g] = un[6];
@@ -214,7 +193,7 @@ __global__ void __launch_bounds__(BX, 1) hjb_fused_kernel(const Args a) {
                 double e = fma(a.he[6], k7, fma(a.he[5], k6w[6], fma(a.he[4], k5w[6], fma(a.he[3], k4w[6],
                                fma(a.he[2], k3w[6], a.he[0] * k1w[6])))));
                 double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
-                double qq = e / sc;
+                double qq = e * rcp_pos(sc);
                 acc = fma(qq, qq, acc);
 #pragma unroll
                 for (int ee = 0; ee < NE; ee++) {
@@ -228,8 +207,6 @@ __global__ void __launch_bounds__(BX, 1) hjb_fused_kernel(const Args a) {
         __syncthreads();
         buf ^= 1;
         // ---- shift windows by one row
-#pragma unroll
-        for (int l = 6; l > 0; l--) { yw[l] = yw[l - 1]; k1w[l] = k1w[l - 1]; cw[l] = cw[l - 1]; }
         k2w[4] = k2w[3]; k2w[3] = k2w[2]; k2w[2] = k2w[1];
         k3w[6] = k3w[5]; k3w[5] = k3w[4]; k3w[4] = k3w[3]; k3w[3] = k3w[2];
         k4w[6] = k4w[5]; k4w[5] = k4w[4]; k4w[4] = k4w[3];

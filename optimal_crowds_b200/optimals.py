@@ -37,7 +37,7 @@ def _load_room(room):
 
 
 class optimals:
-    def __init__(self, room, V, T, target, _ctx=None, _config=None):
+    def __init__(self, room, V, T, target, _ctx=None, _config=None, field_storage="velocity", fused=1):
         var_config = _config if _config is not None else _load_config()
         var_room = _load_room(room)
         self.room_length = var_room['room_length']
@@ -55,7 +55,13 @@ class optimals:
         self.lim = 10e-3                       # optimals.py:95
         self._config = var_config
         self._ctx = _ctx if _ctx is not None else _lib.Context(self.room_length, self.room_height, self.grid_step)
-        self._prm = _lib.hjb_params(var_config)
+        self._prm = _lib.hjb_params(var_config, fused=fused)
+        if field_storage not in ("velocity", "phi"):
+            raise ValueError("field_storage must be 'velocity' or 'phi'")
+        # 'velocity': (nt-1,Ny-2,Nx-2) x 2 slices exactly like the reference (optimals.py:80-81).
+        # 'phi': the (nt,Ny,Nx) value-function samples only (half the memory, no conversion pass); the GCFM
+        # sampler differentiates on the fly and vx_opt / vy_opt are produced on demand by the same kernel.
+        self.field_storage = field_storage
         # potential: remap in place (optimals.py:89-91) and keep a device copy
         import torch
         if isinstance(V, np.ndarray):
@@ -70,8 +76,14 @@ class optimals:
             self.V = None  # materialised on demand by V_host()
         self.d_tiles, self.v_min = self._ctx.wall_tiles(self.d_V)
         n_slices = max(self.nt_opt - 1, 0)
-        self.d_vx = torch.empty((n_slices, self.Ny - 2, self.Nx - 2), dtype=torch.float64, device=self.d_V.device)
-        self.d_vy = torch.empty_like(self.d_vx)
+        self._n_slices = n_slices
+        if field_storage == "velocity":
+            self.d_vx = torch.empty((n_slices, self.Ny - 2, self.Nx - 2), dtype=torch.float64, device=self.d_V.device)
+            self.d_vy = torch.empty_like(self.d_vx)
+            self.d_phi = None
+        else:
+            self.d_vx = self.d_vy = None
+            self.d_phi = torch.empty((n_slices + 1, self.Ny, self.Nx), dtype=torch.float64, device=self.d_V.device)
         self._h_vx = self._h_vy = None
         self.phi_T = np.zeros((self.Ny, self.Nx), dtype=float).reshape(self.Nx * self.Ny) + 1  # optimals.py:83,93
         self.last_stats = None
@@ -85,17 +97,34 @@ class optimals:
     def Y_opt(self):
         return np.meshgrid(self._ctx.X, self._ctx.Y)[1]
 
+    def _materialise(self):
+        if self._h_vx is not None:
+            return
+        if self.d_vx is not None:
+            self._h_vx, self._h_vy = self.d_vx.cpu().numpy(), self.d_vy.cpu().numpy()
+            return
+        # phi storage: vx_opt[s] = vels(sol.y[:, nt-1-s]) for s < nt-1 (optimals.py:200-204); later slices were
+        # never written by the last solve (np.empty in the reference) and are left as zeros here
+        vx = np.zeros((self._n_slices, self.Ny - 2, self.Nx - 2)); vy = np.zeros_like(vx)
+        for s in range(min(self.nt_opt - 1, self._n_slices)):
+            a, b = self._ctx.hjb_vels(self.d_phi[self.nt_opt - 1 - s], self._prm)
+            vx[s], vy[s] = a.cpu().numpy(), b.cpu().numpy()
+        self._h_vx, self._h_vy = vx, vy
+
     @property
     def vx_opt(self):
-        if self._h_vx is None:
-            self._h_vx = self.d_vx.cpu().numpy()
+        self._materialise()
         return self._h_vx
 
     @property
     def vy_opt(self):
-        if self._h_vy is None:
-            self._h_vy = self.d_vy.cpu().numpy()
+        self._materialise()
         return self._h_vy
+
+    def field_key(self, doors):
+        """descriptor of this target set for oc_gcfm_step"""
+        return dict(V=self.d_V, tiles=self.d_tiles, v_min=self.v_min, vx=self.d_vx, vy=self.d_vy, phi=self.d_phi,
+                    mu=self.mu, lim=self.lim, nt_opt=self.nt_opt, doors=doors)
 
     def V_host(self):
         return self.V if self.V is not None else self.d_V.cpu().numpy()
@@ -118,10 +147,13 @@ class optimals:
             d_m = self._ctx.to_device(np.asarray(m, dtype=np.float64).reshape(self.Ny, self.Nx))
         else:
             d_m = m.reshape(self.Ny, self.Nx)
-        if nt - 1 > self.d_vx.shape[0]:
+        if nt - 1 > self._n_slices:
             raise IndexError("re-solve asks for more slices than the field was allocated for")  # as numpy would
-        res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_phi=False, want_vel=nt > 1,
-                                  out_vx=self.d_vx, out_vy=self.d_vy)
+        if self.field_storage == "velocity":
+            res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_phi=False, want_vel=nt > 1,
+                                      out_vx=self.d_vx, out_vy=self.d_vy)
+        else:
+            res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_vel=False, out_phi=self.d_phi)
         self._h_vx = self._h_vy = None
         self.last_stats = res["stats"]
         if res["rc"] == _lib.OC_ERR_STEP_TOO_SMALL:
@@ -142,12 +174,17 @@ class optimals:
         n = max(len(rows), len(cols))
         rows = rows * (n // len(rows))
         cols = cols * (n // len(cols))
-        sx, sy = self.d_vx[t], self.d_vy[t]  # IndexError for t beyond the allocation, like numpy
-        H, W = sx.shape
+        if t >= self._n_slices or t < -self._n_slices:
+            raise IndexError(f"index {t} is out of bounds for axis 0 with size {self._n_slices}")
+        H, W = self.Ny - 2, self.Nx - 2
         for i, j in zip(rows, cols):
             if not (-H <= i < H and -W <= j < W):
                 raise IndexError(f"index ({i},{j}) is out of bounds for the field of shape ({H},{W})")
         import torch
+        if self.d_vx is not None:
+            sx, sy = self.d_vx[t], self.d_vy[t]
+        else:
+            sx, sy = self._ctx.hjb_vels(self.d_phi[self.nt_opt - 1 - t], self._prm)
         ii = torch.tensor(rows, device=sx.device); jj = torch.tensor(cols, device=sx.device)
         vals = torch.stack([sx[ii, jj], sy[ii, jj]]).cpu().numpy()
         return np.array((np.mean(vals[0]), np.mean(vals[1])), dtype=float)

@@ -26,7 +26,7 @@ warnings.filterwarnings("ignore")  # simulations.py:15
 
 class simulation:
 
-    def __init__(self, room, T, recompute=False, record=True):
+    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1):
         import torch
         self.recompute = recompute
         var_config = _load_config()       # simulations.py:42
@@ -80,7 +80,8 @@ class simulation:
                 # SURVEY App. C #12); building them once per key gives the same objects and the same RNG stream.
                 V = self.create_potential(var_room, targets)
                 self.Vs[key] = V
-                self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config)
+                self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config,
+                                                      field_storage=field_storage, fused=fused)
             box_count[key] = box_count.get(key, 0) + 1
             xs, ys, v_des_all = _crowd.place_box(box, X1, Y1, self.place_ped, r_in)
             loc_N = len(xs)
@@ -159,11 +160,7 @@ class simulation:
         self._state["status"][i] = int(self._h_status[i])
 
     def _keys(self):
-        out = []
-        for key, opt in self.targets.items():
-            out.append(dict(V=opt.d_V, tiles=opt.d_tiles, v_min=opt.v_min, vx=opt.d_vx, vy=opt.d_vy,
-                            nt_opt=opt.nt_opt, doors=self._doors[key]))
-        return out
+        return [opt.field_key(self._doors[key]) for key, opt in self.targets.items()]
 
     @property
     def _doors(self):

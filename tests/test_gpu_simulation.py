@@ -25,12 +25,12 @@ def in_repo_cwd(monkeypatch):
     monkeypatch.chdir(REPO)  # rooms/<room>.json is CWD-relative like the reference (simulations.py:47)
 
 
-def _run(room, T, recompute, seed, max_steps=None):
+def _run(room, T, recompute, seed, max_steps=None, **kw):
     from optimal_crowds_b200 import simulations
     np.random.seed(seed)
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
-        simu = simulations.simulation(room, T, recompute)
+        simu = simulations.simulation(room, T, recompute, **kw)
         if max_steps is None:
             simu.run()
         else:
@@ -140,3 +140,27 @@ def test_whole_run_bit_exact_vs_cpu_restatement(in_repo_cwd, cfg):
     assert order == simu._exit_order
     assert np.array_equal(simu._h_status, st["status"])
     assert np.array_equal(simu._h_timev, st["time"])
+
+
+def test_phi_storage_equals_velocity_storage(in_repo_cwd):
+    """storing phi samples and differentiating in the sampler gives the same run, bit for bit, as storing the
+    velocity slices (same device function on the same phi), and the same vx_opt / vy_opt on demand."""
+    a, _ = _run("exit_opposite", 3.0, True, 3, field_storage="velocity")
+    b, _ = _run("exit_opposite", 3.0, True, 3, field_storage="phi")
+    assert a.simu_step == b.simu_step and a._exit_order == b._exit_order
+    for ta, tb in zip(a._track, b._track):
+        assert np.array_equal(ta, tb)
+    for k in a.targets:
+        oa, ob = a.targets[k], b.targets[k]
+        assert oa.nt_opt == ob.nt_opt
+        n = oa.nt_opt - 1
+        assert np.array_equal(oa.vx_opt[:n], ob.vx_opt[:n]) and np.array_equal(oa.vy_opt[:n], ob.vy_opt[:n])
+        p = (2.3, 1.7)
+        assert np.array_equal(oa.choose_optimal_velocity(p, 5), ob.choose_optimal_velocity(p, 5))
+
+
+def test_stagewise_and_fused_shim_agree(in_repo_cwd):
+    a, _ = _run("room_test", 3.0, False, 1, fused=0)
+    b, _ = _run("room_test", 3.0, False, 1, fused=1)
+    for ta, tb in zip(a._track[:60], b._track[:60]):
+        assert np.abs(ta - tb).max() < 1e-8
