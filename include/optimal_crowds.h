@@ -76,7 +76,9 @@ typedef struct {
      * differences of the error norm ~10x per 40 attempts, so long solves are compared step-for-step.) */
     const double *forced_h;
     int n_forced_h;
-    int reserved;
+    int chunk_rows;       /* fused path: rows per CTA chunk (0 = chosen per grid).  Fixing it makes the error-norm
+                             summation order, and therefore every bit of the result, independent of how the grid
+                             is split into row bands (bands must be multiples of it) */
 } oc_hjb_params;
 
 typedef struct {
@@ -105,6 +107,33 @@ typedef struct {
 int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, const oc_hjb_params *prm, double T,
                  const double *t_eval, int nt, double *d_phi, double *d_vx, double *d_vy, oc_hjb_stats *stats,
                  double *trace_h, double *trace_err, int trace_cap, int *trace_n, void *stream);
+
+/* ------------------------------------------------------------------ row-decomposed HJB solve (multi-GPU)
+ * The grid of the context is split into bands of rows.  Two modes:
+ *  - distributed: one process per GPU; call oc_dist_unique_id on rank 0, broadcast the 128 bytes (e.g. with
+ *    torch.distributed), then oc_dist_init on every rank.  Arrays passed to oc_hjb_solve_band are BAND shaped:
+ *    d_V, d_m (rows, Nx); d_phi (nt, rows+2, Nx) with one halo row on each side filled by the library;
+ *    d_vx, d_vy (nt-1, rows, Nx-2), row j <-> global row own0+j (global frame rows are not written).
+ *  - virtual (cfg.n_virtual > 1, no communicator needed): one process emulates n_virtual bands on one GPU with
+ *    device copies as the halo exchange; arrays are FULL-grid shaped as for oc_hjb_solve.  Used by the tests to
+ *    show that the decomposition does not change a bit of the result (with prm.chunk_rows fixed).
+ * Only the stage-fused path exists here (prm.fused is ignored).  Bands are equal and multiples of 16 rows. */
+typedef struct {
+    int n_virtual;   /* > 1: virtual bands in one process; otherwise the communicator of oc_dist_init is used */
+    int own0, own1;  /* distributed mode: global rows [own0, own1) of this rank (= rank*rows .. (rank+1)*rows) */
+    int reserved;
+} oc_band_cfg;
+int oc_dist_unique_id(void *out128);
+int oc_dist_init(oc_ctx *ctx, const void *id128, int rank, int nranks);
+int oc_dist_finalize(oc_ctx *ctx);
+int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const double *d_V, const double *d_m,
+                      const oc_hjb_params *prm, double T, const double *t_eval, int nt, double *d_phi, double *d_vx,
+                      double *d_vy, oc_hjb_stats *stats, double *trace_h, double *trace_err, int trace_cap,
+                      int *trace_n, void *stream);
+/* Rasterise only rows [row0, row0+rows) of the context's grid into a band-shaped array (rows, Nx). */
+int oc_rasterise_band(oc_ctx *ctx, const double *walls, int n_walls, const double *holes, int n_holes,
+                      const double *cyls, int n_cyls, const double *targets, int n_targets, int remap,
+                      double wall_value, double target_value, int row0, int rows, double *d_V, void *stream);
 
 /* One RHS evaluation, the `hjb` closure (optimals.py:144-164). d_phi,d_out: (Ny,Nx). */
 int oc_hjb_rhs(oc_ctx *ctx, const double *d_phi, const double *d_V, const double *d_m, const oc_hjb_params *prm,

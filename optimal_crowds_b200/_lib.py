@@ -31,7 +31,7 @@ OC_ERR_STEP_TOO_SMALL = -5
 class HjbParams(C.Structure):
     _fields_ = [("sigma", C.c_double), ("mu", C.c_double), ("g", C.c_double), ("rtol", C.c_double),
                 ("atol", C.c_double), ("lim", C.c_double), ("fused", C.c_int), ("profile", C.c_int),
-                ("forced_h", dp), ("n_forced_h", C.c_int), ("reserved", C.c_int)]
+                ("forced_h", dp), ("n_forced_h", C.c_int), ("chunk_rows", C.c_int)]
 
     def force_steps(self, h):
         """teacher-forced controller: replay the signed step sequence `h` (parity tests; see optimal_crowds.h)"""
@@ -57,6 +57,10 @@ class HjbStats(C.Structure):
         return d
 
 
+class BandCfg(C.Structure):
+    _fields_ = [("n_virtual", C.c_int), ("own0", C.c_int), ("own1", C.c_int), ("reserved", C.c_int)]
+
+
 class GcfmParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("dt", "dt2", "half_noise", "relaxation", "v_max", "cutoff", "a_min", "tau_a", "b_min", "b_max",
@@ -75,7 +79,8 @@ _lib = None
 
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
-           "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms"]
+           "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
+           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band"]
 
 
 def load():
@@ -102,6 +107,14 @@ def load():
     lib.oc_hjb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_double, dp, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbStats), dp, dp, C.c_int, ip,
                                  C.c_void_p]
+    lib.oc_hjb_solve_band.argtypes = [C.c_void_p, C.POINTER(BandCfg), C.c_void_p, C.c_void_p, C.POINTER(HjbParams),
+                                      C.c_double, dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbStats),
+                                      dp, dp, C.c_int, ip, C.c_void_p]
+    lib.oc_rasterise_band.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int,
+                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oc_dist_unique_id.argtypes = [C.c_void_p]
+    lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.oc_dist_finalize.argtypes = [C.c_void_p]
     lib.oc_hjb_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p,
                                C.c_void_p]
     lib.oc_hjb_vels.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p, C.c_void_p, C.c_void_p]
@@ -197,6 +210,56 @@ class Context:
         check(load().oc_rasterise(self.h, _hp(w), len(w), _hp(h), len(h), _hp(c), len(c), _hp(t), len(t),
                                   int(bool(remap)), float(wall_value), float(target_value), _dev(V), _stream()))
         return V
+
+    def rasterise_band(self, walls, holes, cyls, targets, row0, rows, remap=False, wall_value=-100.0,
+                       target_value=1.0):
+        """rows [row0, row0+rows) of the grid only (band-shaped result), for the row-decomposed solver"""
+        w, h, c, t = (np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, k))
+                      for a, k in ((walls, 4), (holes, 4), (cyls, 3), (targets, 4)))
+        V = self.empty(rows, self.Nx)
+        check(load().oc_rasterise_band(self.h, _hp(w), len(w), _hp(h), len(h), _hp(c), len(c), _hp(t), len(t),
+                                       int(bool(remap)), float(wall_value), float(target_value), int(row0), int(rows),
+                                       _dev(V), _stream()))
+        return V
+
+    # ---- row-decomposed HJB (multi-GPU or virtual bands)
+    def dist_init(self, id_bytes: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        check(load().oc_dist_init(self.h, buf, int(rank), int(nranks)))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def hjb_solve_band(self, V, m, prm: HjbParams, T, nt, n_virtual=0, own=None, want_phi=True, want_vel=False,
+                       trace=False, out_phi=None):
+        """V, m: full-grid tensors (virtual bands) or this rank's band (distributed, after dist_init)."""
+        t_eval = np.linspace(T, 0, nt)
+        if n_virtual and n_virtual > 1 or own is None:
+            rows, prow, own0, own1 = self.Ny, self.Ny, 0, self.Ny
+            vshape = (max(nt - 1, 0), self.Ny - 2, self.Nx - 2)
+        else:
+            own0, own1 = own
+            rows = own1 - own0
+            prow = rows + 2
+            vshape = (max(nt - 1, 0), rows, self.Nx - 2)
+        phi = out_phi if out_phi is not None else (self.empty(nt, prow, self.Nx) if want_phi else None)
+        vx = vy = None
+        if want_vel:
+            import torch
+            vx = torch.zeros(vshape, dtype=torch.float64, device=self.torch_device)
+            vy = torch.zeros(vshape, dtype=torch.float64, device=self.torch_device)
+        cfg = BandCfg(int(n_virtual or 0), int(own0), int(own1), 0)
+        st = HjbStats()
+        cap = 1 << 16 if trace else 0
+        th = np.empty(max(cap, 1)); te = np.empty(max(cap, 1))
+        ntr = C.c_int()
+        rc = load().oc_hjb_solve_band(self.h, C.byref(cfg), _dev(V), _dev(m), C.byref(prm), float(T), _hp(t_eval),
+                                      int(nt), _dev(phi), _dev(vx), _dev(vy), C.byref(st), _hp(th) if trace else None,
+                                      _hp(te) if trace else None, cap, C.byref(ntr), _stream())
+        check(rc, allow=(OC_ERR_STEP_TOO_SMALL,))
+        res = {"stats": st.asdict(), "phi": phi, "vx": vx, "vy": vy, "rc": rc}
+        if trace:
+            k = min(ntr.value, cap)
+            res["trace_h"], res["trace_err"] = th[:k].copy(), te[:k].copy()
+        return res
 
     # ---- HJB
     def hjb_solve(self, V, m, prm: HjbParams, T, nt, want_phi=False, want_vel=True, trace=False, out_vx=None,
@@ -313,9 +376,10 @@ def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: 
     return p
 
 
-def hjb_params(cfg: dict, fused: int = 0, profile: int = 0) -> HjbParams:
+def hjb_params(cfg: dict, fused: int = 0, profile: int = 0, chunk_rows: int = 0) -> HjbParams:
     h = cfg["hjb_params"]
-    return HjbParams(h["sigma"], h["mu"], h["g"], 1e-3, 1e-6, 10e-3, int(fused), int(profile), None, 0, 0)
+    return HjbParams(h["sigma"], h["mu"], h["g"], 1e-3, 1e-6, 10e-3, int(fused), int(profile), None, 0,
+                     int(chunk_rows))
 
 
 def launch_count(reset=False):

@@ -21,6 +21,7 @@ UNITS = {  # source -> extra flags
     "oc_api.cu": ["-fmad=false"],
     "oc_gcfm.cu": ["-fmad=false"],
     "oc_hjb.cu": [],
+    "oc_hjb_dist.cu": [],
 }
 
 
@@ -46,7 +47,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
-        subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs, check=True)
+        subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"], check=True)
     return LIB
 
 

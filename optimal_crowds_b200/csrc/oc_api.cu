@@ -64,6 +64,8 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->hjb_ws);
     cudaFree(c->hjb_partial);
     cudaFree(c->hjb_scratch);
+    cudaFree(c->dist_ws);
+    oc_dist_finalize(c);
     cudaFree(c->gcfm_ws);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
@@ -108,16 +110,19 @@ __device__ __forceinline__ int stage_shapes(const double *__restrict__ src, int 
     return *cnt;
 }
 
+// rows [row0, row0+rows) of the (Ny,Nx) grid are written to V (rows, Nx)
 __global__ void __launch_bounds__(256) rasterise_kernel(const double *__restrict__ X, const double *__restrict__ Y,
-                                                        int Ny, int Nx, RastArgs a, double *__restrict__ V) {
+                                                        int Ny, int Nx, RastArgs a, int row0, int rows,
+                                                        double *__restrict__ V) {
     __shared__ double sh[RAST_CHUNK * 4];
     __shared__ int cnt;
     const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const bool in = (i < Ny && j < Nx);
+    const int il = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int i = row0 + il;
+    const bool in = (il < rows && i < Ny && j < Nx);
     const double x = in ? X[j] : 0.0, y = in ? Y[i] : 0.0;
     const double bx0 = X[blockIdx.x * 32], bx1 = X[min(blockIdx.x * 32 + 31, Nx - 1)];
-    const double by0 = Y[blockIdx.y * 8], by1 = Y[min(blockIdx.y * 8 + 7, Ny - 1)];
+    const double by0 = Y[min(row0 + blockIdx.y * 8, Ny - 1)], by1 = Y[min(row0 + blockIdx.y * 8 + 7, Ny - 1)];
     double v = 0.0;
     for (int base = 0; base < a.n_walls; base += RAST_CHUNK) {  // simulations.py:538-547
         int n = stage_shapes<4>(a.walls, base, a.n_walls, bx0, bx1, by0, by1, sh, &cnt);
@@ -151,14 +156,24 @@ __global__ void __launch_bounds__(256) rasterise_kernel(const double *__restrict
         if (v < 0) v = a.wall_value;
         else if (v > 0) v = a.target_value;
     }
-    V[(size_t)i * Nx + j] = v;
+    V[(size_t)il * Nx + j] = v;
 }
 }  // namespace
 
 extern "C" int oc_rasterise(oc_ctx *ctx, const double *walls, int n_walls, const double *holes, int n_holes,
                             const double *cyls, int n_cyls, const double *targets, int n_targets, int remap,
                             double wall_value, double target_value, double *d_V, void *stream) {
+    OC_ARG(ctx, "ctx NULL");
+    return oc_rasterise_band(ctx, walls, n_walls, holes, n_holes, cyls, n_cyls, targets, n_targets, remap, wall_value,
+                             target_value, 0, ctx->Ny, d_V, stream);
+}
+
+extern "C" int oc_rasterise_band(oc_ctx *ctx, const double *walls, int n_walls, const double *holes, int n_holes,
+                                 const double *cyls, int n_cyls, const double *targets, int n_targets, int remap,
+                                 double wall_value, double target_value, int row0, int rows, double *d_V,
+                                 void *stream) {
     OC_ARG(ctx && d_V, "ctx/d_V NULL");
+    OC_ARG(row0 >= 0 && rows >= 1 && row0 + rows <= ctx->Ny, "row range outside the grid");
     cudaStream_t st = (cudaStream_t)stream;
     OC_CUDA(cudaSetDevice(ctx->device));
     size_t nd = (size_t)4 * n_walls + 4 * n_holes + 3 * n_cyls + 4 * n_targets;
@@ -179,8 +194,8 @@ extern "C" int oc_rasterise(oc_ctx *ctx, const double *walls, int n_walls, const
     a.n_walls = n_walls; a.n_holes = n_holes; a.n_cyls = n_cyls; a.n_targets = n_targets;
     a.remap = remap; a.wall_value = wall_value; a.target_value = target_value;
     if (nd) OC_CUDA(cudaMemcpyAsync(d_sh, h.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
-    dim3 grid((ctx->Nx + 31) / 32, (ctx->Ny + 7) / 8);
-    rasterise_kernel<<<grid, 256, 0, st>>>(ctx->d_X, ctx->d_Y, ctx->Ny, ctx->Nx, a, d_V);
+    dim3 grid((ctx->Nx + 31) / 32, (rows + 7) / 8);
+    rasterise_kernel<<<grid, 256, 0, st>>>(ctx->d_X, ctx->d_Y, ctx->Ny, ctx->Nx, a, row0, rows, d_V);
     oc::count_launch();
     OC_CUDA(cudaGetLastError());
     OC_CUDA(cudaStreamSynchronize(st));  // h / d_sh lifetimes

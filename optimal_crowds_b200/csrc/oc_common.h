@@ -31,6 +31,11 @@ struct oc_ctx {
     int gcfm_N = -1, gcfm_nbins = -1, gcfm_nkeys = -1, gcfm_ndoors = -1;  // layout the workspace was carved for
     void *gcfm_pinned = nullptr;
     size_t gcfm_pinned_bytes = 0;
+    // row-band (multi-GPU) solver
+    void *nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    void *dist_ws = nullptr;
+    size_t dist_ws_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double gcfm_last_ms = 0.0;
 };

@@ -17,27 +17,15 @@
 
 #include "oc_common.h"
 #include "oc_hjb_fused.cuh"
+#include "oc_rk45.h"
 #include "oc_vels.h"
 
 namespace {
 
-// scipy/rk.py:541-565
-const double RK_A[6][5] = {{0, 0, 0, 0, 0},
-                           {1.0 / 5, 0, 0, 0, 0},
-                           {3.0 / 40, 9.0 / 40, 0, 0, 0},
-                           {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
-                           {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
-                           {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
-const double RK_B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
-const double RK_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
-const double RK_P[7][4] = {
-    {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
-    {0, 0, 0, 0},
-    {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
-    {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
-    {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
-    {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
-    {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+#define RK_A rk45::A
+#define RK_B rk45::B
+#define RK_E rk45::E
+#define RK_P rk45::P
 
 constexpr int TX = 128, TY = 16, NTHREADS = 256;  // stage tile
 constexpr int SW = TX + 2;                        // smem row pitch (doubles)
@@ -347,8 +335,9 @@ struct Solver {
     }
     // ---- stage-fused step (oc_hjb_fused.cuh)
     int fused_rc = 0, fused_gx = 0, fused_gy = 0;
-    void fused_plan(int n_sm) {
+    void fused_plan(int n_sm, int forced_rc = 0) {
         fused_gx = (Nx + fused::VX - 1) / fused::VX;
+        if (forced_rc > 0) { fused_rc = forced_rc; fused_gy = (Ny + forced_rc - 1) / forced_rc; return; }
         static const int cand[] = {32, 48, 64, 96, 128, 192, 256, 384, 512};
         double best = 1e300;
         for (int rc : cand) {
@@ -547,7 +536,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     if (use_fused) {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-        s.fused_plan(n_sm);
+        s.fused_plan(n_sm, prm->chunk_rows);
         size_t np_need = (size_t)2 * s.fused_gx * s.fused_gy + s.fused_gy;
         if (ctx->hjb_partial_n < np_need || ctx->h_pinned_n < (size_t)s.fused_gy + 16) {
             oc::set_error("internal: fused partial buffers too small");
@@ -616,6 +605,7 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                 for (int j = 0; j < 7; j++) fa.he[j] = h * RK_E[j];
                 fa.A = s.diff_over_dxdy; fa.rtol = rtol; fa.atol = atol;
                 fa.Ny = s.Ny; fa.Nx = s.Nx; fa.RC = s.fused_rc;
+                fa.row_base = 0; fa.own0 = 0; fa.own1 = s.Ny; fa.phi_row_base = 0;
                 int ne = 0;
                 if (want_out) {
                     for (int ia = t_eval_i - 1; ia >= ia_lo; ia--, ne++) {

@@ -43,7 +43,11 @@ struct Args {
     double w[NE_MAX][7];     // h * sum_q P[j][q] x_e^(q+1)
     double A;                // -0.5 sigma^2 / (dx dy)
     double rtol, atol;
-    int Ny, Nx, RC;          // RC = rows per chunk
+    int Ny, Nx, RC;          // global grid, RC = rows per chunk
+    // row band (multi-GPU / virtual ranks): rows [own0, own1) are computed; y, k1, coef, ynew, k7 point to storage
+    // whose first row is global row `row_base` (halo rows from the neighbouring bands included); phi slices
+    // start at global row `phi_row_base`.  Single GPU: row_base = phi_row_base = 0, own = [0, Ny).
+    int row_base, own0, own1, phi_row_base;
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
@@ -96,8 +100,8 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     const int tid = threadIdx.x;
     const int gx = blockIdx.x * VX - HX + tid;
     const int gxm = min(max(mirror(gx, a.Nx), 0), a.Nx - 1);  // column this thread loads (clamped far outside)
-    const int y0 = blockIdx.y * a.RC;
-    const int y1 = min(y0 + a.RC, a.Ny);
+    const int y0 = a.own0 + blockIdx.y * a.RC;
+    const int y1 = min(y0 + a.RC, a.own1);
     const bool col_out = tid >= HX && tid < BX - HX && gx < a.Nx;  // columns this thread stores
 
     for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         if (row < r_end) {
             const int slot = row & (PF - 1);
             const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
-            const size_t g = (size_t)rm * a.Nx + gxm;
+            const size_t g = (size_t)(rm - a.row_base) * a.Nx + gxm;
             cp_async8(&sm.pf[slot][0][tid], a.y + g);
             cp_async8(&sm.pf[slot][1][tid], a.k1 + g);
             cp_async8(&sm.pf[slot][2][tid], a.coef + g);
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         {
             const int row = r - 6;
             if (col_out && row >= y0 && row < y1) {
-                const size_t g = (size_t)row * a.Nx + gx;
+                const size_t g = (size_t)(row - a.row_base) * a.Nx + gx;
                 a.ynew[g] = un[6];
                 a.k7[g] = k7;
                 // rk.py:106,146-147: err = h * K.E ; scale = atol + max(|y|,|y_new|) * rtol
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
                     // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
                     double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
                                     fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
-                    a.phi[ee][g] = ph;
+                    a.phi[ee][(size_t)(row - a.phi_row_base) * a.Nx + gx] = ph;
                 }
             }
         }

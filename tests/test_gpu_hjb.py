@@ -198,3 +198,37 @@ def test_long_horizon_is_reproducible_only_to_solver_tolerance(cfg, torch_mod):
         np.testing.assert_allclose(phi, phi_ref, rtol=2e-2)
         np.testing.assert_allclose(res["trace_h"][:80], h_ref[:80], rtol=1e-9)
     ctx.close()
+
+
+@pytest.mark.parametrize("n_virtual", [2, 4])
+def test_row_band_decomposition_is_bit_invariant(n_virtual, cfg, torch_mod):
+    """the row-decomposed solver (virtual ranks on one GPU: same kernels, device copies as the halo
+    exchange, per-band partial sums combined in global order) reproduces the undecomposed solve bit for bit."""
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    Ny, Nx, T = 256, 300, 0.6
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    rng = np.random.RandomState(7)
+    V = np.zeros((Ny, Nx)); V[0, :] = V[-1, :] = V[:, 0] = V[:, -1] = -100
+    V[60:70, 40:200] = -100; V[126:131, 100:260] = -100   # a wall straddling the band boundary at row 128
+    V[120:136, -1] = 1.0; V[0, 20:30] = 1.0
+    m = rng.uniform(0, 1, (Ny, Nx))
+    nt = round(T / 0.02)
+    ctx = _lib.Context(L, H, 0.05)
+    Vd, md = ctx.to_device(V), ctx.to_device(m)
+    prm = _lib.hjb_params(cfg, fused=1, chunk_rows=32)
+    one = ctx.hjb_solve_band(Vd, md, prm, T, nt, n_virtual=1, want_vel=True, trace=True)
+    many = ctx.hjb_solve_band(Vd, md, prm, T, nt, n_virtual=n_virtual, want_vel=True, trace=True)
+    assert one["stats"]["nfev"] == many["stats"]["nfev"]
+    assert np.array_equal(one["trace_h"], many["trace_h"]) and np.array_equal(one["trace_err"], many["trace_err"])
+    assert torch_mod.equal(one["phi"], many["phi"])
+    assert torch_mod.equal(one["vx"], many["vx"]) and torch_mod.equal(one["vy"], many["vy"])
+    # and both agree with the single-GPU entry point and the CPU oracle
+    ref = ctx.hjb_solve(Vd, md, _lib.hjb_params(cfg, fused=1), T, nt, want_phi=True, trace=True)
+    np.testing.assert_allclose(many["phi"].cpu().numpy(), ref["phi"].cpu().numpy(), rtol=1e-12)
+    phi_o, st_o, h_o, _ = co.hjb_solve(V, m, T, nt)
+    assert many["stats"]["nfev"] == st_o["nfev"]
+    np.testing.assert_allclose(many["phi"].cpu().numpy().reshape(nt, -1), phi_o, rtol=1e-10)
+    vx_o, vy_o = co.fill_field(phi_o, Ny, Nx)
+    assert np.abs(many["vx"].cpu().numpy() - vx_o).max() < 1e-10
+    ctx.close()
