@@ -450,7 +450,15 @@ def main():
     if os.path.exists(tr_file):
         try:
             with open(tr_file) as f:
-                roof["traffic"] = json.load(f).get("fused" if args.fused else "stage")
+                tj = json.load(f)
+                for tag in sorted(tj, reverse=True):   # latest capture of the dominant kernel
+                    for kname, v in tj[tag].items():
+                        if ("hjb_fused_kernel" in kname) == bool(args.fused) and ("hjb_" in kname):
+                            roof["traffic"] = v
+                            roof["traffic_source"] = f"profiles/{tag}.md ({kname.strip()})"
+                            break
+                    if roof["traffic"] is not None:
+                        break
         except Exception:
             pass
     cpu = None

@@ -337,15 +337,8 @@ struct Solver {
     int fused_rc = 0, fused_gx = 0, fused_gy = 0;
     void fused_plan(int n_sm, int forced_rc = 0) {
         fused_gx = (Nx + fused::VX - 1) / fused::VX;
-        if (forced_rc > 0) { fused_rc = forced_rc; fused_gy = (Ny + forced_rc - 1) / forced_rc; return; }
-        static const int cand[] = {32, 48, 64, 96, 128, 192, 256, 384, 512};
-        double best = 1e300;
-        for (int rc : cand) {
-            int gy = (Ny + rc - 1) / rc;
-            long long blocks = (long long)fused_gx * gy;
-            double cost = (double)((blocks + n_sm - 1) / n_sm) * (std::min(rc, Ny) + 2 * fused::HY);
-            if (cost < best) { best = cost; fused_rc = rc; fused_gy = gy; }
-        }
+        fused_rc = forced_rc > 0 ? forced_rc : fused::plan_chunk_rows(Nx, Ny, n_sm, 1, 0);
+        fused_gy = (Ny + fused_rc - 1) / fused_rc;
     }
     template <int NE>
     int launch_fused_ne(const fused::Args &a) {
@@ -405,7 +398,7 @@ int ensure_ws(oc_ctx *ctx, size_t n, int nbx, int nby) {
     // large enough for the stage tiles and for any fused-step plan (>= 32-row chunks, 240-column tiles)
     size_t np = (size_t)2 * nbx * nby + nby + 64;
     {
-        size_t fgx = (size_t)(nbx * TX + fused::VX - 1) / fused::VX + 1, fgy = (size_t)(nby * TY + 31) / 32 + 1;
+        size_t fgx = (size_t)(nbx * TX + fused::VX - 1) / fused::VX + 1, fgy = (size_t)(nby * TY + 15) / 16 + 1;
         np = std::max(np, 2 * fgx * fgy + fgy + 64);
     }
     if (ctx->hjb_partial_n < np) {
@@ -413,7 +406,7 @@ int ensure_ws(oc_ctx *ctx, size_t n, int nbx, int nby) {
         OC_CUDA(cudaMalloc(&ctx->hjb_partial, np * sizeof(double)));
         ctx->hjb_partial_n = np;
     }
-    size_t hp = (size_t)std::max(nby, (nby * TY + 31) / 32 + 1) + 16;
+    size_t hp = (size_t)std::max(nby, (nby * TY + 15) / 16 + 1) + 16;
     if (ctx->h_pinned_n < hp) {
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
         OC_CUDA(cudaMallocHost(&ctx->h_pinned, hp * sizeof(double)));

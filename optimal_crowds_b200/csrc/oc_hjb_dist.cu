@@ -245,17 +245,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
     int rc_rows = prm->chunk_rows;
-    if (rc_rows <= 0) {
-        static const int cand[] = {32, 48, 64, 96, 128, 192, 256, 384, 512};
-        double best = 1e300;
-        for (int c : cand) {
-            if (nbands > 1 && band_rows % c) continue;
-            long long blocks = (long long)gx_f * ((band_rows + c - 1) / c) * (dist ? 1 : nb_local);
-            double cost = (double)((blocks + n_sm - 1) / n_sm) * (std::min(c, band_rows) + 2 * HB);
-            if (cost < best) { best = cost; rc_rows = c; }
-        }
-        if (rc_rows <= 0) rc_rows = 16;
-    }
+    if (rc_rows <= 0) rc_rows = fused::plan_chunk_rows(Nx, band_rows, n_sm, dist ? 1 : nb_local, nbands > 1);
     OC_ARG(nbands == 1 || band_rows % rc_rows == 0, "band height must be a multiple of chunk_rows");
     const int gy_f = (band_rows + rc_rows - 1) / rc_rows, gy_t = (band_rows + TYS - 1) / TYS;
     const int rows_store = band_rows + 2 * HB;

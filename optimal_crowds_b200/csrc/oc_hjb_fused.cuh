@@ -32,6 +32,24 @@ constexpr int PD = 8;               // prefetch distance (rows in flight)
 constexpr int CTAS_PER_SM = 3;      // 3 x 61 KB shared memory, <= 170 registers/thread
 constexpr int NE_MAX = 6;           // dense-output samples per launch
 
+// rows per CTA chunk: balance the tail of the last wave (slots = SMs x resident CTAs) against the 2*HY halo rows
+// each chunk recomputes.  `rows` = rows of the band, `copies` = bands launched back to back on this GPU.
+inline int plan_chunk_rows(int Nx, int rows, int n_sm, int copies, int must_divide) {
+    static const int cand[] = {16, 32, 48, 64, 96, 128, 160, 192, 224, 256, 320, 384, 448, 512, 640, 768, 1024, 2048};
+    const long long slots = (long long)n_sm * CTAS_PER_SM;
+    const int gx = (Nx + VX - 1) / VX;
+    double best = 1e300;
+    int rc = 16;
+    for (int c : cand) {
+        if (must_divide && rows % c) continue;
+        const int cc = c < rows ? c : rows;
+        const long long blocks = (long long)gx * ((rows + cc - 1) / cc) * copies;
+        const double cost = (double)((blocks + slots - 1) / slots) * (cc + 2 * HY);
+        if (cost < best) { best = cost; rc = cc; }
+    }
+    return rc;
+}
+
 struct Args {
     const double *y, *k1, *coef;
     double *ynew, *k7, *partial;
