@@ -29,7 +29,8 @@ namespace {
 constexpr int WT = OC_WALL_TILE;
 constexpr double DISP_MARGIN = 1.0;  // max displacement per step assumed by the candidate search (checked)
 constexpr int SWEEP_WARPS = 4;       // warps per block in the sweep
-constexpr int LIST_CAP = 512;        // interacting neighbours per agent held in shared memory
+constexpr int LIST_CAP = 384;        // interacting neighbours per agent held in shared memory
+constexpr int CAND_CAP = 768;        // candidates (agents within cutoff + margin of the old position)
 
 struct KeyDev {
     const double *V;
@@ -42,7 +43,8 @@ struct KeyDev {
 };
 
 struct Ws {  // device workspace carved out of ctx->gcfm_ws
-    double *x0, *y0, *vx0, *vy0;            // snapshot at step start
+    double4 *snap4, *live4;                 // packed (x,y,vx,vy): snapshot at step start / state after the agent's turn
+    double *x0, *y0, *vx0, *vy0;            // snapshot at step start (SoA, used by prepare)
     double *des_x, *des_y, *wfx, *wfy;      // per-agent precomputed terms
     double *noise;                          // (N,2) device copy, consumption order
     double *doors;                          // flattened door rectangles of all keys
@@ -157,11 +159,16 @@ __device__ void pair_force(const oc_gcfm_params &p, const AgentEllipse &ei, doub
     double v_rel = 0.5 * (d + fabs(d));
     double k = 0.0;
     if (ei.ni > 0) k = fmax((vxi * ex + vyi * ey) / ei.ni - p.cos_fov, 0.0) / p.one_minus_cos_fov;
-    double alpha_i = ocm_atan2(Ry, Rx);
-    double alpha_j = ocm_atan2(-Ry, -Rx), beta_j = ocm_atan2(vyj, vxj);
-    double ci = ocm_cos(alpha_i - ei.beta_i) / ei.a_i, si = ocm_sin(alpha_i - ei.beta_i) / ei.b_i;
+    // alpha_i = atan2(Ry,Rx), alpha_j = atan2(-Ry,-Rx): one arctangent core, same bits as two calls
+    double alpha_i, alpha_j;
+    ocm_atan2_both(Ry, Rx, &alpha_i, &alpha_j);
+    double beta_j = ocm_atan2(vyj, vxj);
+    double sni, csi, snj, csj;
+    ocm_sincos(alpha_i - ei.beta_i, &sni, &csi);
+    ocm_sincos(alpha_j - beta_j, &snj, &csj);
+    double ci = csi / ei.a_i, si = sni / ei.b_i;
     double q_i = sqrt(1.0 / (ci * ci + si * si));
-    double cj = ocm_cos(alpha_j - beta_j) / a_j, sj = ocm_sin(alpha_j - beta_j) / b_j;
+    double cj = csj / a_j, sj = snj / b_j;
     double q_j = sqrt(1.0 / (cj * cj + sj * sj));
     double dist = nR - q_i - q_j;
     double rep = fmin(k * ocm_exp(-dist / (p.eta * (1.0 + v_rel))), 1.0);
@@ -178,7 +185,9 @@ __device__ void wall_force_from_node(const oc_gcfm_params &p, const AgentEllipse
     double d = vxi * ex + vyi * ey;
     double v_rel = 0.5 * (d + fabs(d));
     double alpha = ocm_atan2(Ry, Rx);
-    double c = ocm_cos(alpha - ei.beta_i) / ei.a_i, s = ocm_sin(alpha - ei.beta_i) / ei.b_i;
+    double sn, cs;
+    ocm_sincos(alpha - ei.beta_i, &sn, &cs);
+    double c = cs / ei.a_i, s = sn / ei.b_i;
     double q_i = 1.0 / (c * c + s * s);  // no sqrt: pedestrians.py:328
     double dist = nR - q_i;
     double rep = fmin(ocm_exp(-dist / (p.eta_walls * (1.0 + v_rel))), 1.0);
@@ -287,7 +296,9 @@ __global__ void setup_kernel(int N, const double *__restrict__ x, const double *
     if (i >= N) return;
     w.rank[w.perm[i]] = i;
     double xi = x[i], yi = y[i];
-    w.x0[i] = xi; w.y0[i] = yi; w.vx0[i] = vx[i]; w.vy0[i] = vy[i];
+    const double vxi = vx[i], vyi = vy[i];
+    w.x0[i] = xi; w.y0[i] = yi; w.vx0[i] = vxi; w.vy0[i] = vyi;
+    w.snap4[i] = make_double4(xi, yi, vxi, vyi);
     uint8_t s = status[i];
     w.status0[i] = s;
     int bx = min(max((int)floor(xi * inv_cs), 0), nbx - 1), by = min(max((int)floor(yi * inv_cs), 0), nby - 1);
@@ -375,21 +386,29 @@ __global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, W
     }
 }
 
-// K6: the sweep (simulations.py:271-332)
+// K6: the sweep (simulations.py:271-332).  Per agent (one warp):
+//  A. gather the candidates -- agents whose OLD position is within cutoff + margin of i's old position -- from the
+//     cell list into shared memory (no waiting: only the immutable snapshot is read);
+//  B. 32 candidates at a time: a candidate EARLIER in the sweep must have finished (acquire on its done-flag,
+//     which also carries its inside/exited status), then its NEW packed state is read; a LATER one is still in
+//     its snapshot state.  Cutoff test and pair force (simulations.py:291-295);
+//  C. sort the interacting neighbours by agent index, add the forces left to right, advance the agent, publish.
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
              uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
              double inv_cs, int nbx, int nby) {
+    __shared__ int s_c[SWEEP_WARPS][CAND_CAP];
     __shared__ int s_j[SWEEP_WARPS][LIST_CAP];
     __shared__ double s_fx[SWEEP_WARPS][LIST_CAP];
     __shared__ double s_fy[SWEEP_WARPS][LIST_CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int *lj = s_j[wid];
+    int *lc = s_c[wid], *lj = s_j[wid];
     double *lfx = s_fx[wid], *lfy = s_fy[wid];
     const double reach = p.cutoff + DISP_MARGIN;
     const double reach2 = reach * reach;
     const int span = (int)ceil(reach * inv_cs);
+    const unsigned lt_mask = (1u << lane) - 1;
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(&w.counters[0], 1);
@@ -397,54 +416,80 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         if (r >= N) break;
         const int i = w.perm[r];
         if (!w.status0[i]) continue;  // simulations.py:277
-        const double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i], vd = vdes[i];
+        const double4 si = w.snap4[i];
+        const double xi = si.x, yi = si.y, vxi = si.z, vyi = si.w, vd = vdes[i];
         const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
-        int cnt = 0;
+        // ---- A. candidates
+        int nc = 0;
         const int b = w.agent_bin[i];
         const int bix = b % nbx, biy = b / nbx;
         for (int by = max(biy - span, 0); by <= min(biy + span, nby - 1); by++) {
             const int c0 = by * nbx + max(bix - span, 0), c1 = by * nbx + min(bix + span, nbx - 1);
             const int beg = w.bin_start[c0], end = w.bin_start[c1 + 1];  // bins of one row are contiguous
             for (int base = beg; base < end; base += 32) {
-                int kk = base + lane;
-                bool hit = false;
-                double fx = 0.0, fy = 0.0;
+                const int kk = base + lane;
+                bool keep = false;
                 int j = -1;
                 if (kk < end) {
                     j = w.cell_agents[kk];
-                    double ox = w.x0[j] - xi, oy = w.y0[j] - yi;
-                    if (j != i && ox * ox + oy * oy < reach2) {  // symmetric prefilter on old positions
-                        double xj, yj, vxj, vyj;
-                        bool alive = true;
-                        if (w.rank[j] < r) {  // earlier in the sweep: needs j's NEW state
-                            while (ld_acquire(&w.flags[j]) != tag) __nanosleep(32);
-                            xj = __ldcg(x + j); yj = __ldcg(y + j); vxj = __ldcg(vx + j); vyj = __ldcg(vy + j);
-                            alive = __ldcg(status + j) != 0;
-                        } else {  // later: still in its old state
-                            xj = w.x0[j]; yj = w.y0[j]; vxj = w.vx0[j]; vyj = w.vy0[j];
-                        }
-                        if (alive) {
-                            double ddx = xj - xi, ddy = yj - yi;
-                            if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
-                                pair_force(p, ei, xi, yi, vxi, vyi, vd, xj, yj, vxj, vyj, fx, fy);
-                                hit = true;
-                            }
-                        }
+                    const double4 sj = w.snap4[j];
+                    const double ox = sj.x - xi, oy = sj.y - yi;
+                    keep = (j != i) && (ox * ox + oy * oy < reach2);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int pos = nc + __popc(m & lt_mask);
+                    if (pos < CAND_CAP) lc[pos] = j;
+                }
+                nc += __popc(m);
+            }
+        }
+        if (nc > CAND_CAP) {
+            if (lane == 0) atomicOr(&w.counters[1], 2);
+            nc = CAND_CAP;
+        }
+        __syncwarp();
+        // ---- B. forces
+        int cnt = 0;
+        for (int base = 0; base < nc; base += 32) {
+            const int c = base + lane;
+            bool hit = false;
+            double fx = 0.0, fy = 0.0;
+            int j = -1;
+            if (c < nc) {
+                j = lc[c];
+                double4 sj;
+                bool alive = true;
+                if (w.rank[j] < r) {  // earlier in the sweep: needs j's NEW state
+                    int f;
+                    while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(20);
+                    alive = (f & 1) != 0;
+                    const double2 a = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j));
+                    const double2 bb = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j) + 1);
+                    sj = make_double4(a.x, a.y, bb.x, bb.y);
+                } else {  // later: still in its old state
+                    sj = w.snap4[j];
+                }
+                if (alive) {
+                    const double ddx = sj.x - xi, ddy = sj.y - yi;
+                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
+                        pair_force(p, ei, xi, yi, vxi, vyi, vd, sj.x, sj.y, sj.z, sj.w, fx, fy);
+                        hit = true;
                     }
                 }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    int pos = cnt + __popc(m & ((1u << lane) - 1));
-                    if (pos < LIST_CAP) { lj[pos] = j; lfx[pos] = fx; lfy[pos] = fy; }
-                }
-                cnt += __popc(m);
             }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = cnt + __popc(m & lt_mask);
+                if (pos < LIST_CAP) { lj[pos] = j; lfx[pos] = fx; lfy[pos] = fy; }
+            }
+            cnt += __popc(m);
         }
         if (cnt > LIST_CAP) {
             if (lane == 0) atomicOr(&w.counters[1], 2);
             cnt = LIST_CAP;
         }
-        // sort the interacting neighbours by agent index (bitonic, in shared memory)
+        // ---- C. sort by agent index (bitonic, in shared memory), ascending-j sum (simulations.py:285-295)
         int m2 = 1;
         while (m2 < cnt) m2 <<= 1;
         for (int t = cnt + lane; t < m2; t += 32) lj[t] = 0x7fffffff;
@@ -452,10 +497,10 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         for (int k = 2; k <= m2; k <<= 1)
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 for (int t = lane; t < m2; t += 32) {
-                    int u = t ^ jj;
+                    const int u = t ^ jj;
                     if (u > t) {
-                        bool up = ((t & k) == 0);
-                        int a = lj[t], bb = lj[u];
+                        const bool up = ((t & k) == 0);
+                        const int a = lj[t], bb = lj[u];
                         if ((a > bb) == up) {
                             lj[t] = bb; lj[u] = a;
                             double q = lfx[t]; lfx[t] = lfx[u]; lfx[u] = q;
@@ -465,9 +510,8 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 }
                 __syncwarp();
             }
-        // ascending-j sum (simulations.py:285-295): lane 0 -> x component, lane 1 -> y component
         double acc = 0.0;
-        if (lane < 2) {
+        if (lane < 2) {  // lane 0 -> x component, lane 1 -> y component
             const double *src = lane == 0 ? lfx : lfy;
             for (int t = 0; t < cnt; t++) acc = acc + src[t];
         }
@@ -494,6 +538,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 const double *door = w.doors + 4 * (k.door_off + d);
                 if (fabs(nx_ - door[0]) < door[2] * 0.5 && fabs(ny_ - door[1]) < door[3] * 0.5) out = true;
             }
+            w.live4[i] = make_double4(nx_, ny_, nvx, nvy);
             x[i] = nx_; y[i] = ny_; vx[i] = nvx; vy[i] = nvy;
             tim[i] = tim[i] + p.dt;  // pedestrians.py:191
             if (out) {
@@ -501,7 +546,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 w.exit_mark[r] = i + 1;  // simulations.py:331-332, ordered by sweep position
             }
             __threadfence();
-            st_release(&w.flags[i], tag);
+            st_release(&w.flags[i], tag * 2 + (out ? 0 : 1));
         }
         __syncwarp();
     }
@@ -649,6 +694,8 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     size_t need = 0;
     auto al = [&](size_t b) { need += ((b + 255) / 256) * 256; };
     for (int q = 0; q < 8; q++) al(sizeof(double) * N);
+    al(sizeof(double4) * N);
+    al(sizeof(double4) * N);
     al(sizeof(double) * 2 * N);
     al(sizeof(double) * 4 * std::max(n_doors, 1));
     for (int q = 0; q < 7; q++) al(sizeof(int) * N);
@@ -671,6 +718,8 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     char *p = (char *)ctx->gcfm_ws;
     // flags first so that it keeps its place (and contents) while N is unchanged
     w.flags = carve<int>(p, N);
+    w.snap4 = carve<double4>(p, N);
+    w.live4 = carve<double4>(p, N);
     w.x0 = carve<double>(p, N); w.y0 = carve<double>(p, N); w.vx0 = carve<double>(p, N); w.vy0 = carve<double>(p, N);
     w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
     w.noise = carve<double>(p, 2 * (size_t)N);
@@ -738,7 +787,7 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     OC_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int) * (nbins + 1), st));
     OC_CUDA(cudaMemsetAsync(w.exit_mark, 0, sizeof(int) * N, st));
     OC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * 8, st));
-    if (++g_tag == 0x7fffffff) g_tag = 1;
+    if (++g_tag >= 0x3fffffff) g_tag = 1;
     const int tag = g_tag;
     const int nb = (N + 255) / 256;
     setup_kernel<<<nb, 256, 0, st>>>(N, d_x, d_y, d_vx, d_vy, d_status, w, inv_cs, nbx, nby);

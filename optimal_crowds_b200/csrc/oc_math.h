@@ -260,4 +260,48 @@ OCM_FN double ocm_cos(double x) {
     }
 }
 
+/* ---------------------------------------------------------------- shared-work variants
+ * Same bits as the separate calls (tests/test_cpu_oracle.py), less work: the GCFM pair force needs
+ * atan2(y,x) AND atan2(-y,-x) (pedestrians.py:266,268) and sin AND cos of the same angle (:270-271). */
+OCM_FN void ocm_sincos(double x, double *s, double *c) {
+    double ax = ocm_abs(x);
+    if (ocm_isnan(x) || ax == INFINITY || ax <= 7.85398163397448278999e-01) {
+        *s = ocm_sin(x);
+        *c = ocm_cos(x);
+        return;
+    }
+    double r, t;
+    int n = ocm_rem_pio2(x, &r, &t);
+    double ks = ocm_ksin(r, t), kc = ocm_kcos(r, t);
+    switch (n) {
+        case 0: *s = ks; *c = kc; break;
+        case 1: *s = kc; *c = -ks; break;
+        case 2: *s = -ks; *c = -kc; break;
+        default: *s = -kc; *c = ks; break;
+    }
+}
+
+OCM_FN void ocm_atan2_both(double y, double x, double *a_pos, double *a_neg) {
+    const double pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
+    double ay = ocm_abs(y), ax = ocm_abs(x);
+    int ky = (int)((ocm_bits(y) >> 52) & 0x7ff), kx = (int)((ocm_bits(x) >> 52) & 0x7ff);
+    int k = ky - kx;
+    /* anything that takes a special path in ocm_atan2 is evaluated by the two plain calls */
+    if (ocm_isnan(x) || ocm_isnan(y) || ay == 0.0 || ax == 0.0 || ax == INFINITY || ay == INFINITY || ax == 1.0 ||
+        k > 60 || k < -60) {
+        *a_pos = ocm_atan2(y, x);
+        *a_neg = ocm_atan2(-y, -x);
+        return;
+    }
+    int sy = (int)(ocm_bits(y) >> 63), sx = (int)(ocm_bits(x) >> 63);
+    double z = ocm_atan(ocm_abs(y / x)); /* |(-y)/(-x)| == |y/x| exactly */
+    double zq = z - pi_lo;
+    /* (y,x): signs (sy,sx); (-y,-x): signs (!sy,!sx) -- same quadrant rules as ocm_atan2 */
+    double p, n;
+    if (!sx) p = sy ? -z : z; else p = (!sy) ? pi - zq : zq - pi;
+    if (sx) n = (!sy) ? -z : z; else n = sy ? pi - zq : zq - pi;
+    *a_pos = p;
+    *a_neg = n;
+}
+
 #endif /* OC_MATH_H */

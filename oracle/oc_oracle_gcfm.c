@@ -40,6 +40,12 @@ void oco_math_atan2(const double *y, const double *x, double *o, int n) {
     for (int i = 0; i < n; i++) o[i] = ocm_atan2(y[i], x[i]);
 }
 
+/* shared-work variants used by the CUDA kernels: must return the bits of the separate calls */
+void oco_math_sincos(const double *x, double *s, double *c, int n) { for (int i = 0; i < n; i++) ocm_sincos(x[i], &s[i], &c[i]); }
+void oco_math_atan2_both(const double *y, const double *x, double *p, double *q, int n) {
+    for (int i = 0; i < n; i++) ocm_atan2_both(y[i], x[i], &p[i], &q[i]);
+}
+
 /* Parameters computed on the host by the SAME Python expressions the reference evaluates
  * (e.g. dt**2, noise_intensity/2, np.cos(0.7*np.pi)), so constants are bit-identical. */
 typedef struct {
