@@ -27,9 +27,13 @@ constexpr int BX = 128;             // threads per CTA = columns per tile incl. 
 constexpr int HX = 8;               // halo columns per side (6 needed)
 constexpr int VX = BX - 2 * HX;     // valid output columns per tile (112)
 constexpr int HY = 6;               // halo rows per side
-constexpr int PF = 16;              // cp.async ring depth (rows), power of two: rows r-6 .. r+PD live
-constexpr int PD = 8;               // prefetch distance (rows in flight)
-constexpr int CTAS_PER_SM = 3;      // 3 x 61 KB shared memory, <= 170 registers/thread
+constexpr int PF = 6;               // cp.async ring depth (rows): rows r .. r+PD
+constexpr int PD = 5;               // prefetch distance (rows in flight)
+constexpr int UNROLL = 12;          // rows per unrolled loop body (multiple of PF and of 2)
+#ifndef OC_CTAS
+#define OC_CTAS 3
+#endif
+constexpr int CTAS_PER_SM = OC_CTAS;      // 3 x 30.5 KB shared memory, <= 168 registers/thread
 constexpr int NE_MAX = 6;           // dense-output samples per launch
 
 // rows per CTA chunk: balance the tail of the last wave (slots = SMs x resident CTAs) against the 2*HY halo rows
@@ -121,27 +125,29 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     const int y0 = a.own0 + blockIdx.y * a.RC;
     const int y1 = min(y0 + a.RC, a.own1);
     const bool col_out = tid >= HX && tid < BX - HX && gx < a.Nx;  // columns this thread stores
+    const int phi_shift = (a.row_base - a.phi_row_base) * a.Nx;    // phi slices may start at another global row
 
     for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
 
     // windows, indexed by lag (row r - lag)
-    // y, k1 = f and coef of rows r-6..r stay in the cp.async ring (read back by the owning thread, no sync);
-    // k2..k6 and the stage inputs are register windows
-    double k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
+    // all windows are registers.  Shared memory is the bottleneck resource of this kernel (every LDS.64 of a
+    // warp costs 2 cycles of the SM's 128 B/cycle), so each loaded value is read from the ring exactly once.
+    double yw[7], k1w[7], cw[7], k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
     double u2[3], u3[4], u4[5], u5[6], u6[7], un[8];
 #pragma unroll
-    for (int i = 0; i < 7; i++) { k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
+    for (int i = 0; i < 7; i++) { yw[i] = 0; k1w[i] = 0; cw[i] = 0; k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
 #pragma unroll
     for (int i = 0; i < 5; i++) k2w[i] = 0;
     u2[0] = u2[1] = u2[2] = 0; u3[1] = u3[2] = u3[3] = 0; u4[2] = u4[3] = u4[4] = 0;
     u5[3] = u5[4] = u5[5] = 0; u6[4] = u6[5] = u6[6] = 0; un[5] = un[6] = un[7] = 0;
 
     const int r_begin = y0 - HY, r_end = y1 + HY;  // rows loaded: [r_begin, r_end)
-    auto issue = [&](int row) {
+    // ring slot of row `row` = (row - r_begin) mod PF, tracked incrementally (PF is not a power of two)
+    auto issue = [&](int row, int slot) {
         if (row < r_end) {
-            const int slot = row & (PF - 1);
+            // element offsets fit 32 bits (one field < 2^31 elements); one IMAD instead of 64-bit multiplies
             const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
-            const size_t g = (size_t)(rm - a.row_base) * a.Nx + gxm;
+            const int g = (rm - a.row_base) * a.Nx + gxm;
             cp_async8(&sm.pf[slot][0][tid], a.y + g);
             cp_async8(&sm.pf[slot][1][tid], a.k1 + g);
             cp_async8(&sm.pf[slot][2][tid], a.coef + g);
@@ -149,27 +155,28 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         cp_async_commit();  // one group per iteration, possibly empty
     };
 
-    // rows older than r_begin are read (as don't-care values) during the first iterations: define them
 #pragma unroll 1
-    for (int q = 0; q < PF; q++) { sm.pf[q][0][tid] = 0.0; sm.pf[q][1][tid] = 0.0; sm.pf[q][2][tid] = 0.0; }
-#pragma unroll 1
-    for (int q = 0; q < PD; q++) issue(r_begin + q);
+    for (int q = 0; q < PD; q++) issue(r_begin + q, q);
     __syncthreads();
 
     double acc = 0.0;
-    int buf = 0;
-#pragma unroll 2
-    for (int r = r_begin; r < r_end; r++) {
-        issue(r + PD);
-        cp_async_wait<PD>();
-        double yw[7], k1w[7], cw[7];
+    // The row loop is unrolled by the ring depth: inside the unrolled body the ring slot of every window row, the
+    // exchange buffer and the register holding each window entry are compile-time constants -- no address
+    // arithmetic and no register moves for the shifting windows.
+#pragma unroll 1
+    for (int rb = r_begin; rb < r_end; rb += UNROLL) {
 #pragma unroll
-        for (int l = 0; l < 7; l++) {
-            const int slot = (r - l) & (PF - 1);
-            yw[l] = sm.pf[slot][0][tid];
-            k1w[l] = sm.pf[slot][1][tid];
-            cw[l] = sm.pf[slot][2][tid];
-        }
+      for (int uu = 0; uu < UNROLL; uu++) {
+        const int r = rb + uu;
+        // rows past r_end are harmless (no loads are issued, every store is guarded): no early exit, so the
+        // unrolled body is one straight-line block and the window shifts below are pure register renaming
+        const int s0 = uu % PF;      // ring slot of row r: (r - r_begin) mod PF
+        const int buf = uu & 1;
+        issue(r + PD, (s0 + PD) % PF);
+        cp_async_wait<PD>();
+        yw[0] = sm.pf[s0][0][tid];
+        k1w[0] = sm.pf[s0][1][tid];
+        cw[0] = sm.pf[s0][2][tid];
         const double *exp_ = &sm.ex[buf ^ 1][0][tid];  // previous iteration's rows: [s*(BX+2)] left, [+2] right
         double *exc = &sm.ex[buf][0][tid + 1];
         // parts of the six stencils that do not depend on this iteration's new rows
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         {
             const int row = r - 6;
             if (col_out && row >= y0 && row < y1) {
-                const size_t g = (size_t)(row - a.row_base) * a.Nx + gx;
+                const int g = (row - a.row_base) * a.Nx + gx;
                 a.ynew[g] = un[6];
                 a.k7[g] = k7;
                 // rk.py:106,146-147: err = h * K.E ; scale = atol + max(|y|,|y_new|) * rtol
@@ -222,13 +229,14 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
                     // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
                     double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
                                     fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
-                    a.phi[ee][(size_t)(row - a.phi_row_base) * a.Nx + gx] = ph;
+                    a.phi[ee][g + phi_shift] = ph;
                 }
             }
         }
         __syncthreads();
-        buf ^= 1;
-        // ---- shift windows by one row
+        // ---- shift windows by one row (pure renaming inside the unrolled body)
+#pragma unroll
+        for (int l = 6; l > 0; l--) { yw[l] = yw[l - 1]; k1w[l] = k1w[l - 1]; cw[l] = cw[l - 1]; }
         k2w[4] = k2w[3]; k2w[3] = k2w[2]; k2w[2] = k2w[1];
         k3w[6] = k3w[5]; k3w[5] = k3w[4]; k3w[4] = k3w[3]; k3w[3] = k3w[2];
         k4w[6] = k4w[5]; k4w[5] = k4w[4]; k4w[4] = k4w[3];
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         u5[5] = u5[4]; u5[4] = u5[3];
         u6[6] = u6[5]; u6[5] = u6[4];
         un[7] = un[6]; un[6] = un[5];
+      }
     }
     cp_async_wait<0>();
     // fixed-order CTA reduction of the error partial sum
