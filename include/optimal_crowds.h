@@ -47,6 +47,9 @@ const char *oc_last_error(void);
 /* number of this library's kernels launched since the last call with reset != 0 (bench.py gpu_launches) */
 long long oc_launch_count(int reset);
 
+/* Host -> device copy on `stream` (cudaMemcpyAsync): asynchronous when `host` is page-locked, staged otherwise. */
+int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream);
+
 /* Grid context.  X (Nx) and Y (Ny) are the np.linspace node coordinates of simulations.py:69-70 /
  * optimals.py:61-62, computed by the host with numpy so they are bit-identical to the reference's. */
 int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length, double room_height,
@@ -191,6 +194,15 @@ int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, dou
                  double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
                  const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
                  int simu_step, int *exit_log, int *n_exit, void *stream);
+
+/* The same step split in two so that the host can work (e.g. draw the next step's random numbers) while the GPU
+ * runs: _launch enqueues everything on `stream` and returns without waiting (perm / noise must stay valid until
+ * _finish); _finish waits for the step and returns the exit log and status exactly like oc_gcfm_step. */
+int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx,
+                        double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
+                        const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
+                        int simu_step, void *stream);
+int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit);
 
 /* CUDA-event time (ms) of the last oc_gcfm_step on this context (H2D of perm/noise, all kernels, exit-log copy). */
 double oc_gcfm_last_ms(oc_ctx *ctx);

@@ -80,7 +80,8 @@ _lib = None
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
-           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band"]
+           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_gcfm_step_launch",
+           "oc_gcfm_step_finish"]
 
 
 def load():
@@ -112,6 +113,7 @@ def load():
                                       dp, dp, C.c_int, ip, C.c_void_p]
     lib.oc_rasterise_band.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oc_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.oc_dist_unique_id.argtypes = [C.c_void_p]
     lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.oc_dist_finalize.argtypes = [C.c_void_p]
@@ -121,6 +123,9 @@ def load():
     lib.oc_wall_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, dp, C.c_void_p]
     lib.oc_gcfm_step.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 8 + \
                                 [C.POINTER(Key), C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, C.c_void_p]
+    lib.oc_gcfm_step_launch.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 8 + \
+                                       [C.POINTER(Key), C.c_int, ip, dp, C.c_int, C.c_int, C.c_void_p]
+    lib.oc_gcfm_step_finish.argtypes = [C.c_void_p, ip, ip]
     lib.oc_wall_force.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_void_p, C.c_int] + [C.c_void_p] * 8 + \
                                  [C.c_void_p]
     lib.oc_pair_force.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 6 + [C.c_void_p]
@@ -196,11 +201,18 @@ class Context:
         return torch.empty(*shape, dtype=dtype or torch.float64, device=self.torch_device)
 
     def to_device(self, a, dtype=None):
+        """numpy -> new device tensor through one cudaMemcpyAsync on the current stream (full DMA speed when the
+        array lives in page-locked memory, e.g. a view of a pinned torch tensor; staged by the driver otherwise)"""
         import torch
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        if dtype is not None:
-            t = t.to(dtype)
-        return t.to(self.torch_device)
+        a = np.ascontiguousarray(a)
+        if dtype is not None or a.dtype == object or a.size == 0:
+            t = torch.from_numpy(a)
+            return (t.to(dtype) if dtype is not None else t).to(self.torch_device)
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0] if a.ndim else a.reshape(1)[:0]).dtype,
+                        device=self.torch_device)
+        check(load().oc_upload(self.h, a.ctypes.data_as(C.c_void_p), C.c_void_p(t.data_ptr()), a.nbytes, _stream()))
+        torch.cuda.current_stream().synchronize()  # the caller may reuse / free `a`
+        return t
 
     # ---- K8
     def rasterise(self, walls, holes, cyls, targets, remap=False, wall_value=-100.0, target_value=1.0, out=None):
@@ -306,7 +318,11 @@ class Context:
 
     def gcfm_step(self, prm: GcfmParams, state, vdes, key_id, keys, perm, noise, simu_step):
         """state: dict of CUDA tensors x,y,vx,vy,time (float64) and status (uint8), updated in place.
-        keys: list of dicts(V, tiles, v_min, vx, vy, nt_opt, doors(np (n,4)))."""
+        keys: list of dicts(V, tiles, v_min, vx, vy | phi, nt_opt, doors(np (n,4)))."""
+        return self.gcfm_step_finish(self.gcfm_step_launch(prm, state, vdes, key_id, keys, perm, noise, simu_step))
+
+    def gcfm_step_launch(self, prm: GcfmParams, state, vdes, key_id, keys, perm, noise, simu_step):
+        """enqueue one step and return at once; pass the result to gcfm_step_finish()"""
         N = state["x"].numel()
         karr = (Key * len(keys))()
         keep = []
@@ -322,12 +338,17 @@ class Context:
                           float(k.get("mu", 5.0)), float(k.get("lim", 10e-3)), _hp(doors), len(doors))
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 2)
+        check(load().oc_gcfm_step_launch(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]),
+                                         _dev(state["vx"]), _dev(state["vy"]), _dev(state["time"]),
+                                         _dev(state["status"]), _dev(vdes), _dev(key_id), karr, len(keys),
+                                         perm.ctypes.data_as(ip), _hp(noise), len(noise), int(simu_step), _stream()))
+        return (N, perm, noise, karr, keep)  # keeps the host buffers alive until the step has finished
+
+    def gcfm_step_finish(self, pending):
+        N = pending[0]
         exit_log = np.empty(max(N, 1), dtype=np.int32)
         n_exit = C.c_int()
-        rc = load().oc_gcfm_step(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]), _dev(state["vx"]),
-                                 _dev(state["vy"]), _dev(state["time"]), _dev(state["status"]), _dev(vdes),
-                                 _dev(key_id), karr, len(keys), perm.ctypes.data_as(ip), _hp(noise), len(noise),
-                                 int(simu_step), exit_log.ctypes.data_as(ip), C.byref(n_exit), _stream())
+        rc = load().oc_gcfm_step_finish(self.h, exit_log.ctypes.data_as(ip), C.byref(n_exit))
         check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
         return exit_log[: n_exit.value].copy(), rc
 

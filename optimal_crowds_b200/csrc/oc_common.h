@@ -38,6 +38,8 @@ struct oc_ctx {
     size_t dist_ws_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double gcfm_last_ms = 0.0;
+    void *gcfm_stream = nullptr;
+    bool gcfm_pending = false;
 };
 
 namespace oc {

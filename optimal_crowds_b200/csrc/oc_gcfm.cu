@@ -746,6 +746,16 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
                             double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
                             const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
                             int simu_step, int *exit_log, int *n_exit, void *stream) {
+    int rc = oc_gcfm_step_launch(ctx, prm, N, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key, keys, n_keys, perm,
+                                 noise, n_noise, simu_step, stream);
+    if (rc) return rc;
+    return oc_gcfm_step_finish(ctx, exit_log, n_exit);
+}
+
+extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y,
+                                   double *d_vx, double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes,
+                                   const int *d_key, const oc_key *keys, int n_keys, const int *perm,
+                                   const double *noise, int n_noise, int simu_step, void *stream) {
     OC_ARG(ctx && prm && d_x && d_y && d_vx && d_vy && d_time && d_status && d_vdes && d_key && keys && perm,
            "NULL argument");
     OC_ARG(N >= 1 && n_keys >= 1 && n_noise >= 0 && n_noise <= N, "bad sizes");
@@ -806,12 +816,23 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     oc::count_launch(7);
     OC_CUDA(cudaGetLastError());
     OC_CUDA(cudaEventRecord(ctx->ev1, st));
-    OC_CUDA(cudaStreamSynchronize(st));  // hk/hd lifetimes + host-visible exit log
+    // hk / hd are pageable: cudaMemcpyAsync has already staged them when it returned
+    ctx->gcfm_stream = st;
+    ctx->gcfm_pending = true;
+    return OC_OK;
+}
+
+extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
+    OC_ARG(ctx && ctx->gcfm_pending, "no GCFM step in flight");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    ctx->gcfm_pending = false;
+    OC_CUDA(cudaStreamSynchronize((cudaStream_t)ctx->gcfm_stream));  // host-visible exit log
     {
         float ms = 0;
         OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->gcfm_last_ms = ms;
     }
+    const int *pinned = (const int *)ctx->gcfm_pinned;
     int ne = pinned[0], fl = pinned[1];
     if (n_exit) *n_exit = ne;
     if (exit_log)

@@ -18,7 +18,7 @@ import warnings
 
 import numpy as np
 
-from . import _crowd, _lib, optimals, pedestrians
+from . import _crowd, _lib, _rng, optimals, pedestrians
 from .optimals import _load_config, _load_room
 
 warnings.filterwarnings("ignore")  # simulations.py:15
@@ -26,7 +26,7 @@ warnings.filterwarnings("ignore")  # simulations.py:15
 
 class simulation:
 
-    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1):
+    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1, lookahead=True):
         import torch
         self.recompute = recompute
         var_config = _load_config()       # simulations.py:42
@@ -55,6 +55,8 @@ class simulation:
         self.recompute_step = var_config['recompute_frequency']
         self.history = {}
         self._record = record
+        # host RNG draws of step k+1 overlap the GPU's step k (same stream as the reference, see _rng.py)
+        self._rng = _rng.StepRandomness(lookahead)
         self._gcfm_prm = _lib.gcfm_params(var_config, self.room_length, self.room_height, self.Ny, self.Nx)
         diag = float(np.hypot(self.room_length, self.room_height))
         if abs(self.pot) * 10e3 <= diag:
@@ -180,12 +182,14 @@ class simulation:
         else:
             prm = self._gcfm_prm
         if self.N > 0:
-            perm = np.random.choice(np.arange(self.N), self.N, replace=False)      # simulations.py:271
             n_active = int(self._h_status.sum())
-            # one pair per active agent in sweep order == N calls of normal(size=2)   simulations.py:303
-            noise = np.random.normal(size=(n_active, 2)) if n_active else np.zeros((0, 2))
-            exits, rc = self._ctx.gcfm_step(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm, noise,
-                                            self.simu_step)
+            # np.random.choice(np.arange(N), N, replace=False) (simulations.py:271) and one normal pair per active
+            # agent in sweep order == N calls of normal(size=2) (simulations.py:303)
+            perm, noise = self._rng.draw(self.N, n_active)
+            pending = self._ctx.gcfm_step_launch(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm,
+                                                 noise, self.simu_step)
+            self._rng.lookahead(self.N, n_active)   # next step's draws while the GPU sweeps
+            exits, rc = self._ctx.gcfm_step_finish(pending)
             if rc == _lib.OC_ERR_SAMPLER_RANGE:
                 raise IndexError("agent position outside the velocity field's index range "
                                  "(the reference raises here too: optimals.py:247)")

@@ -89,3 +89,39 @@ def test_synthetic_rooms_follow_schema_and_counts():
     assert len({" or ".join(b[5:]) for b in r["initial_boxes"].values()}) == 1   # one HJB key
     m = synthetic.metro_room()
     assert len({" or ".join(b[5:]) for b in m["initial_boxes"].values()}) == 4   # four HJB keys
+
+
+def test_step_randomness_lookahead_is_stream_exact():
+    """the look-ahead draws give the same permutations, the same normal pairs and leave the global generator in the
+    same state as the reference's plain sequence of calls, whatever the exit pattern and even if other code uses
+    np.random between steps."""
+    from optimal_crowds_b200._rng import StepRandomness
+    N = 9000
+    rng_exits = np.random.RandomState(99)
+    exits = [0, 0, 3, 0, 1500, 7, 0, 0, 1, 400, 0, 1000, 90, 0, 0]   # incl. exits beyond every checkpoint but the first
+    # reference sequence
+    np.random.seed(42)
+    ref, n = [], N
+    for k, e in enumerate(exits):
+        perm = np.random.choice(np.arange(N), N, replace=False)
+        z = np.random.normal(size=(n, 2)) if n else np.zeros((0, 2))
+        if k == 6:
+            extra_ref = np.random.uniform()      # foreign consumer between steps
+        ref.append((perm, z))
+        n -= e
+    end_ref = np.random.get_state()
+    # look-ahead sequence
+    np.random.seed(42)
+    sr = StepRandomness(lookahead=True)
+    sr.MIN_N = 0
+    n = N
+    for k, e in enumerate(exits):
+        perm, z = sr.draw(N, n)
+        assert np.array_equal(perm, ref[k][0]) and np.array_equal(z, ref[k][1]), k
+        sr.lookahead(N, n)                       # "while the GPU runs"; must not move the global stream
+        if k == 6:
+            assert np.random.uniform() == extra_ref
+        n -= e
+    end = np.random.get_state()
+    assert end[2] == end_ref[2] and np.array_equal(end[1], end_ref[1]) and end[3:] == end_ref[3:]
+    assert sr.hits >= len(exits) - 3 and sr.misses >= 2          # first step + the step after the foreign draw
