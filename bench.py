@@ -26,9 +26,28 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BAND_NX, BAND_NY, BAND_AGENTS, T_DEFAULT = 16384, 2048, 12500, 2.0
-CPU_SAMPLE_NX, CPU_SAMPLE_NY, CPU_SAMPLE_T = 2048, 1024, 0.5
+CPU_SAMPLE_NX, CPU_SAMPLE_NY, CPU_SAMPLE_T = 2048, 1024, 0.5   # per-thread sample of the multi-core CPU arm
+CPU_BASELINE_T = 1.5                                            # single-core cpu_baseline sample (~12 s)
+
+
+def ncu_traffic(fused=True):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the latest ncu --set full
+    capture summarised under profiles/ (scripts/summarize_ncu.py); None if no capture is tracked."""
+    tr_file = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        with open(tr_file) as f:
+            tj = json.load(f)
+        for tag in sorted(tj, reverse=True):
+            for kname, v in tj[tag].items():
+                if "hjb_" in kname and ("hjb_fused_kernel" in kname) == bool(fused):
+                    return v, f"profiles/{tag}.md ({kname.strip()}, 16384x2048, per launch)"
+    except Exception:
+        pass
+    return None, None
 
 
 def load_peaks():
@@ -85,8 +104,8 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_hjb_sample(threads=1):
-    """Bounded sample of the same workload on the host: the slalom room at 2048 x 1024 nodes, T = 0.5,
+def cpu_hjb_sample(T=CPU_SAMPLE_T):
+    """Bounded sample of the same workload on the host: the slalom room at 2048 x 1024 nodes, short horizon,
     solved by the C port of the reference's algorithm (oracle/oc_oracle_hjb.c)."""
     from oracle import cpu_oracle as co
     from optimal_crowds_b200 import synthetic
@@ -95,12 +114,12 @@ def cpu_hjb_sample(threads=1):
     X, Y = np.linspace(0, L, CPU_SAMPLE_NX), np.linspace(0, H, CPU_SAMPLE_NY)
     V = co.create_potential(X, Y, [], [], list(room["cylinders"].values()), list(room["targets"].values()))
     V[V < 0] = -100; V[V > 0] = 1
-    nt = round(CPU_SAMPLE_T / 0.02)
+    nt = round(T / 0.02)
     t0 = time.perf_counter()
-    _, st, _, _ = co.hjb_solve(V, None, CPU_SAMPLE_T, nt)
+    _, st, _, _ = co.hjb_solve(V, None, T, nt)
     dt = time.perf_counter() - t0
     cu = st["nfev"] * CPU_SAMPLE_NX * CPU_SAMPLE_NY
-    return cu / dt / 1e9, dt, st, f"slalom room at {CPU_SAMPLE_NX}x{CPU_SAMPLE_NY} nodes, T={CPU_SAMPLE_T} (nfev={st['nfev']}), {dt:.1f} s"
+    return cu / dt / 1e9, dt, st, f"slalom room at {CPU_SAMPLE_NX}x{CPU_SAMPLE_NY} nodes, T={T} (nfev={st['nfev']}), {dt:.1f} s"
 
 
 def cpu_gcfm_sample(n_agents=150, steps=2):
@@ -140,7 +159,7 @@ def run_reference_arm(args):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import cpu_oracle as co
     co.lib()
-    cores = max(1, min(os.cpu_count() or 1, 16))
+    cores = max(1, min(os.cpu_count() or 1, 64))
     vals, dts, last = [], [], None
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -276,7 +295,8 @@ def run_dist(args, world, rank, local_rank):
                         "api": "oc_hjb_solve_band with the density band as a pinned host array + checksum read"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "fused::hjb_fused_kernel<NE>", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "traffic": ncu_traffic(True)[0], "traffic_source": ncu_traffic(True)[1],
                              "launches": int(step_n), "avg_launch_ms": step_ms_max / max(step_n, 1),
                              "share_of_step": step_ms_max / ms_max},
                 "cpu_baseline": None,
@@ -293,7 +313,7 @@ def run_dist(args, world, rank, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--T", type=float, default=T_DEFAULT)
@@ -446,27 +466,13 @@ def main():
             "other_classes": {"dense_output+velocity": {"ms": float(cls_ms[1]), "GBps": float(cls_bytes[1] / max(cls_ms[1], 1e-9) / 1e6),
                                                        "launches": int(cls_n[1])},
                               "reductions": {"ms": float(cls_ms[2]), "launches": int(cls_n[2])}}}
-    tr_file = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tr_file):
-        try:
-            with open(tr_file) as f:
-                tj = json.load(f)
-                for tag in sorted(tj, reverse=True):   # latest capture of the dominant kernel
-                    for kname, v in tj[tag].items():
-                        if ("hjb_fused_kernel" in kname) == bool(args.fused) and ("hjb_" in kname):
-                            roof["traffic"] = v
-                            roof["traffic_source"] = f"profiles/{tag}.md ({kname.strip()})"
-                            break
-                    if roof["traffic"] is not None:
-                        break
-        except Exception:
-            pass
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(args.fused)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        g, dt, stc, sample = cpu_hjb_sample()
+        g, dt, stc, sample = cpu_hjb_sample(CPU_BASELINE_T)
         cpu = {"value": g, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample}
         try:
-            gc, gsample = cpu_gcfm_sample()
+            gc, gsample = cpu_gcfm_sample(n_agents=300, steps=4)
             gcfm["cpu_baseline"] = {"value": gc, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": gsample}
         except Exception as e:  # pragma: no cover
             gcfm["cpu_baseline"] = {"error": str(e)}

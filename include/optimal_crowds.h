@@ -47,9 +47,6 @@ const char *oc_last_error(void);
 /* number of this library's kernels launched since the last call with reset != 0 (bench.py gpu_launches) */
 long long oc_launch_count(int reset);
 
-/* Host -> device copy on `stream` (cudaMemcpyAsync): asynchronous when `host` is page-locked, staged otherwise. */
-int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream);
-
 /* Grid context.  X (Nx) and Y (Ny) are the np.linspace node coordinates of simulations.py:69-70 /
  * optimals.py:61-62, computed by the host with numpy so they are bit-identical to the reference's. */
 int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length, double room_height,

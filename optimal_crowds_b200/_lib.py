@@ -80,7 +80,7 @@ _lib = None
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
-           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_gcfm_step_launch",
+           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_gcfm_step_launch",
            "oc_gcfm_step_finish"]
 
 
@@ -113,7 +113,6 @@ def load():
                                       dp, dp, C.c_int, ip, C.c_void_p]
     lib.oc_rasterise_band.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    lib.oc_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.oc_dist_unique_id.argtypes = [C.c_void_p]
     lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.oc_dist_finalize.argtypes = [C.c_void_p]
@@ -201,18 +200,12 @@ class Context:
         return torch.empty(*shape, dtype=dtype or torch.float64, device=self.torch_device)
 
     def to_device(self, a, dtype=None):
-        """numpy -> new device tensor through one cudaMemcpyAsync on the current stream (full DMA speed when the
-        array lives in page-locked memory, e.g. a view of a pinned torch tensor; staged by the driver otherwise)"""
+        """numpy -> new device tensor (torch's copy path: DMA from page-locked memory, staged otherwise)"""
         import torch
-        a = np.ascontiguousarray(a)
-        if dtype is not None or a.dtype == object or a.size == 0:
-            t = torch.from_numpy(a)
-            return (t.to(dtype) if dtype is not None else t).to(self.torch_device)
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0] if a.ndim else a.reshape(1)[:0]).dtype,
-                        device=self.torch_device)
-        check(load().oc_upload(self.h, a.ctypes.data_as(C.c_void_p), C.c_void_p(t.data_ptr()), a.nbytes, _stream()))
-        torch.cuda.current_stream().synchronize()  # the caller may reuse / free `a`
-        return t
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.torch_device)
 
     # ---- K8
     def rasterise(self, walls, holes, cyls, targets, remap=False, wall_value=-100.0, target_value=1.0, out=None):

@@ -56,13 +56,6 @@ extern "C" int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, d
     return OC_OK;
 }
 
-extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream) {
-    OC_ARG(ctx && host && d_dst && bytes >= 0, "bad arguments");
-    OC_CUDA(cudaSetDevice(ctx->device));
-    OC_CUDA(cudaMemcpyAsync(d_dst, host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    return OC_OK;
-}
-
 extern "C" void oc_ctx_destroy(oc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);

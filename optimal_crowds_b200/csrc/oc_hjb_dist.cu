@@ -1,10 +1,11 @@
 // oc_hjb_dist.cu -- row-decomposed HJB solve: the grid is split into bands of rows,
 // one band per GPU (one process per GPU, NCCL over NVLink) or, for tests on one GPU, several "virtual" bands in
-// one process.  Every band runs the stage-fused RK45 step kernel (oc_hjb_fused.cuh) on its rows; after each
-// ACCEPTED step the 6 boundary rows of the new y and f are exchanged with the neighbouring bands (a rejected
-// attempt changes nothing, so it needs no exchange); the error norm is a sum of per-chunk partial sums that
-// are all-gathered and added in global chunk order on every rank, so each rank takes the same accept/reject
-// decision and -- with prm.chunk_rows fixed -- the result is bit-identical to the undecomposed solve.
+// one process.  Every band runs the stage-fused RK45 step kernel (oc_hjb_fused.cuh) on its rows.  After each
+// attempt ONE ncclGroup carries (a) the all-gather of the per-chunk error partial sums, which every rank adds
+// in global chunk order, so each rank takes the same accept/reject decision and -- with prm.chunk_rows fixed --
+// the result is bit-identical to the undecomposed solve, and (b) speculatively, the 6 boundary rows of y_new and
+// f_new for the neighbouring bands (if the attempt is rejected they are never used), so that an accepted step
+// needs no further communication before the next attempt can be launched.
 //
 // Exchange traffic per accepted step and neighbour: 2 arrays x 6 rows x Nx x 8 B (1.5 MB at Nx = 16384) plus
 // one row per emitted phi slice when velocities are requested; all messages of a step go out in ONE
@@ -308,6 +309,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     OC_CUDA(cudaEventRecord(ctx->ev0, st));
 
     // ---- halo exchange of `rows` boundary rows of one array per band (arr(b) selects the array)
+    bool in_group = false;  // the caller has already opened an ncclGroup
     auto exchange = [&](std::initializer_list<double *Band::*> arrays, int phi_ne, double *const *phi_ptrs) -> int {
         // phi_ptrs: per local band, phi_ne slice pointers (only in dist mode, 1 halo row each side)
         if (nbands == 1) return OC_OK;
@@ -325,7 +327,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
             return OC_OK;
         }
         Band &b = bands[0];
-        OC_NCCL(g_nccl.GroupStart());
+        if (!in_group) OC_NCCL(g_nccl.GroupStart());
         for (auto arr : arrays) {
             double *p = b.*arr;
             if (rank > 0) {
@@ -348,20 +350,33 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                 OC_NCCL(g_nccl.Recv(p + (size_t)(band_rows + 1) * Nx, Nx, ncclFloat64, rank + 1, comm, st));
             }
         }
-        OC_NCCL(g_nccl.GroupEnd());
+        if (!in_group) OC_NCCL(g_nccl.GroupEnd());
         return OC_OK;
     };
 
     // ---- sum of per-band partial sums (layout gx x gy per band at partial+off) in global order, on every rank
-    auto reduce = [&](size_t off, int gx, int gy, double *out) -> int {
+    // with_halo: also ship the boundary rows of y_new / f_new in the SAME ncclGroup (one launch latency per
+    // attempt).  The exchange is speculative: if the attempt is rejected the received rows are simply never used.
+    auto reduce = [&](size_t off, int gx, int gy, double *out, bool with_halo = false) -> int {
         for (int q = 0; q < nb_local; q++) {
             rowsum_band_kernel<<<gy, NT, 0, st>>>(bands[q].partial + off, gx, rowsum_loc + (size_t)q * gy);
             launches++;
         }
         const double *src = rowsum_loc;
         if (dist && nranks > 1) {
+            OC_NCCL(g_nccl.GroupStart());
             OC_NCCL(g_nccl.AllGather(rowsum_loc, rowsum_all, gy, ncclFloat64, comm, st));
+            if (with_halo) {
+                in_group = true;
+                int erc = exchange({&Band::ynew, &Band::fnew}, 0, nullptr);
+                in_group = false;
+                if (erc) return erc;
+            }
+            OC_NCCL(g_nccl.GroupEnd());
             src = rowsum_all;
+        } else if (with_halo) {
+            int erc = exchange({&Band::ynew, &Band::fnew}, 0, nullptr);
+            if (erc) return erc;
         }
         OC_CUDA(cudaMemcpyAsync(rowsum_h, src, sizeof(double) * gy * nbands, cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaStreamSynchronize(st));
@@ -507,7 +522,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
             } while (done < n_emit && !(want_v && !d_phi));  // scratch holds one batch only (see below)
             stats->nfev += 6;
             double se;
-            if ((rc = reduce(2 * nb_t, gx_f, gy_f, &se))) return rc;
+            if ((rc = reduce(2 * nb_t, gx_f, gy_f, &se, true))) return rc;
             if (prm->profile) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, pe0, pe1);
@@ -546,7 +561,8 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                     phis.push_back(d_phi ? d_phi + (size_t)kd * b.phi_slice : b.scratch + (size_t)e * b.phi_slice);
             }
         for (Band &b : bands) { std::swap(b.y, b.ynew); std::swap(b.f, b.fnew); }  // FSAL (rk.py:167-174)
-        if ((rc = exchange({&Band::y, &Band::f}, dist ? (int)phis.size() : 0, phis.data()))) return rc;
+        // the halo rows of the new y, f travelled with the error sums; only phi rows (velocity output) are left
+        if (dist && !phis.empty() && (rc = exchange({}, (int)phis.size(), phis.data()))) return rc;
         if (want_v) {
             size_t pi = 0;
             for (int e = 0; e < n_emit; e++) {
