@@ -26,8 +26,23 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class StdoutToStderr:
+    """stdout must carry exactly ONE JSON line: while the benchmark runs, file descriptor 1 is pointed at stderr so
+    that banners printed by libraries (e.g. NCCL's version line) cannot precede it; restored for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 BAND_NX, BAND_NY, BAND_AGENTS, T_DEFAULT = 16384, 2048, 12500, 2.0
 CPU_SAMPLE_NX, CPU_SAMPLE_NY, CPU_SAMPLE_T = 2048, 1024, 0.5   # per-thread sample of the multi-core CPU arm
@@ -498,4 +513,17 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    _lines = []
+    _real_print = print
+
+    def print(*a, **k):  # noqa: A001 -- JSON lines are collected and emitted after stdout is restored
+        if k.get("file") is None:
+            _lines.append(" ".join(str(x) for x in a))
+        else:
+            _real_print(*a, **k)
+
+    with StdoutToStderr():
+        _rc = main()
+    for _l in _lines:
+        _real_print(_l, flush=True)
+    sys.exit(_rc)
