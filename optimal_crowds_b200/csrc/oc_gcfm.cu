@@ -44,6 +44,8 @@ struct KeyDev {
 
 struct Ws {  // device workspace carved out of ctx->gcfm_ws
     double4 *snap4, *live4;                 // packed (x,y,vx,vy): snapshot at step start / state after the agent's turn
+    double4 *cell_state;                    // snapshot of the agents in cell-list order (coalesced candidate scan)
+    int2 *cell_jr;                          // (agent id, sweep rank) in cell-list order
     double *x0, *y0, *vx0, *vy0;            // snapshot at step start (SoA, used by prepare)
     double *des_x, *des_y, *wfx, *wfy;      // per-agent precomputed terms
     double *noise;                          // (N,2) device copy, consumption order
@@ -214,27 +216,37 @@ __device__ long long wall_argmin_warp(const double *__restrict__ X, const double
     const int kmax = max(max(tcx, ntx - 1 - tcx), max(tcy, nty - 1 - tcy));
     for (int k = 0; k <= kmax; k++) {
         const int ty_lo = tcy - k, ty_hi = tcy + k, tx_lo = tcx - k, tx_hi = tcx + k;
-        // ring k = border of the (2k+1)^2 tile square
+        // ring k = border of the (2k+1)^2 tile square.  The occupancy bytes of 32 ring tiles are fetched at once
+        // (one lane each) and only the occupied ones are scanned: the ring costs one memory round trip instead
+        // of one per tile.
         const int side = 2 * k + 1;
         const int ring_n = (k == 0) ? 1 : 8 * k;
-        for (int r = 0; r < ring_n; r++) {
-            int tx, ty;
-            if (k == 0) { tx = tcx; ty = tcy; }
-            else if (r < side) { tx = tx_lo + r; ty = ty_lo; }
-            else if (r < 2 * side) { tx = tx_lo + (r - side); ty = ty_hi; }
-            else if (r < 2 * side + (side - 2)) { tx = tx_lo; ty = ty_lo + 1 + (r - 2 * side); }
-            else { tx = tx_hi; ty = ty_lo + 1 + (r - 2 * side - (side - 2)); }
-            if (tx < 0 || tx >= ntx || ty < 0 || ty >= nty) continue;
-            if (!tiles[ty * ntx + tx]) continue;
-            for (int c = lane; c < WT * WT; c += 32) {
-                int iy = ty * WT + c / WT, ix = tx * WT + (c % WT);
-                if (iy < Ny && ix < Nx) {
-                    double v = V[(size_t)iy * Nx + ix];
-                    if (v < 0) {
-                        double ddx = X[ix] - x, ddy = Y[iy] - y;
-                        double key = sqrt(ddx * ddx + ddy * ddy) + v * 10e3;
-                        long long fi = (long long)iy * Nx + ix;
-                        if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
+        for (int rbase = 0; rbase < ring_n; rbase += 32) {
+            const int r = rbase + lane;
+            int tx = -1, ty = -1;
+            if (r < ring_n) {
+                if (k == 0) { tx = tcx; ty = tcy; }
+                else if (r < side) { tx = tx_lo + r; ty = ty_lo; }
+                else if (r < 2 * side) { tx = tx_lo + (r - side); ty = ty_hi; }
+                else if (r < 2 * side + (side - 2)) { tx = tx_lo; ty = ty_lo + 1 + (r - 2 * side); }
+                else { tx = tx_hi; ty = ty_lo + 1 + (r - 2 * side - (side - 2)); }
+            }
+            const bool occ = tx >= 0 && tx < ntx && ty >= 0 && ty < nty && tiles[ty * ntx + tx] != 0;
+            unsigned todo = __ballot_sync(0xffffffffu, occ);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int ttx = __shfl_sync(0xffffffffu, tx, src), tty = __shfl_sync(0xffffffffu, ty, src);
+                for (int c = lane; c < WT * WT; c += 32) {
+                    int iy = tty * WT + c / WT, ix = ttx * WT + (c % WT);
+                    if (iy < Ny && ix < Nx) {
+                        double v = V[(size_t)iy * Nx + ix];
+                        if (v < 0) {
+                            double ddx = X[ix] - x, ddy = Y[iy] - y;
+                            double key = sqrt(ddx * ddx + ddy * ddy) + v * 10e3;
+                            long long fi = (long long)iy * Nx + ix;
+                            if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
+                        }
                     }
                 }
             }
@@ -333,6 +345,8 @@ __global__ void scatter_kernel(int N, Ws w) {
     int b = w.agent_bin[i];
     int pos = w.bin_start[b] + atomicAdd(&w.bin_cursor[b], 1);
     w.cell_agents[pos] = i;
+    w.cell_state[pos] = w.snap4[i];
+    w.cell_jr[pos] = make_int2(i, w.rank[i]);
 }
 
 // nzidx[agent] = number of agents active at step start that precede it in the sweep (simulations.py:303
@@ -419,30 +433,46 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         const double4 si = w.snap4[i];
         const double xi = si.x, yi = si.y, vxi = si.z, vyi = si.w, vd = vdes[i];
         const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
-        // ---- A. candidates
+        // ---- A. candidates.  Each of the (2 span + 1) bin rows is one contiguous range of the cell list; lanes fetch the
+        // range bounds in parallel, then the concatenated ranges are scanned 32 entries at a time.
         int nc = 0;
         const int b = w.agent_bin[i];
         const int bix = b % nbx, biy = b / nbx;
-        for (int by = max(biy - span, 0); by <= min(biy + span, nby - 1); by++) {
-            const int c0 = by * nbx + max(bix - span, 0), c1 = by * nbx + min(bix + span, nbx - 1);
-            const int beg = w.bin_start[c0], end = w.bin_start[c1 + 1];  // bins of one row are contiguous
-            for (int base = beg; base < end; base += 32) {
-                const int kk = base + lane;
-                bool keep = false;
-                int j = -1;
-                if (kk < end) {
-                    j = w.cell_agents[kk];
-                    const double4 sj = w.snap4[j];
-                    const double ox = sj.x - xi, oy = sj.y - yi;
-                    keep = (j != i) && (ox * ox + oy * oy < reach2);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int pos = nc + __popc(m & lt_mask);
-                    if (pos < CAND_CAP) lc[pos] = j;
-                }
-                nc += __popc(m);
+        const int by0 = max(biy - span, 0), nrows = min(biy + span, nby - 1) - by0 + 1;
+        int my_beg = 0, my_len = 0;
+        if (lane < nrows) {
+            const int by = by0 + lane;
+            my_beg = w.bin_start[by * nbx + max(bix - span, 0)];
+            my_len = w.bin_start[by * nbx + min(bix + span, nbx - 1) + 1] - my_beg;  // bins of one row are contiguous
+        }
+        int my_off = my_len;  // inclusive scan over the (few) rows
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, my_off, o);
+            if (lane >= o) my_off += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, my_off, 7);  // nrows <= 7
+        my_off -= my_len;                                        // exclusive
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            int kk = -1;
+            for (int q = 0; q < nrows; q++) {
+                const int o = __shfl_sync(0xffffffffu, my_off, q), l = __shfl_sync(0xffffffffu, my_len, q),
+                          bq = __shfl_sync(0xffffffffu, my_beg, q);
+                if (t >= o && t < o + l) kk = bq + (t - o);
             }
+            bool keep = false;
+            if (kk >= 0) {
+                const double2 pj = *reinterpret_cast<const double2 *>(w.cell_state + kk);  // (x, y)
+                const double ox = pj.x - xi, oy = pj.y - yi;
+                keep = (ox * ox + oy * oy < reach2);  // the agent itself is dropped in phase B (id test)
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = nc + __popc(m & lt_mask);
+                if (pos < CAND_CAP) lc[pos] = kk;
+            }
+            nc += __popc(m);
         }
         if (nc > CAND_CAP) {
             if (lane == 0) atomicOr(&w.counters[1], 2);
@@ -457,10 +487,14 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             double fx = 0.0, fy = 0.0;
             int j = -1;
             if (c < nc) {
-                j = lc[c];
+                const int kk = lc[c];
+                const int2 jr = w.cell_jr[kk];
+                j = jr.x;
                 double4 sj;
-                bool alive = true;
-                if (w.rank[j] < r) {  // earlier in the sweep: needs j's NEW state
+                bool alive = j != i;
+                if (!alive) {
+                    sj = si;
+                } else if (jr.y < r) {  // earlier in the sweep: needs j's NEW state
                     int f;
                     while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(20);
                     alive = (f & 1) != 0;
@@ -468,7 +502,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                     const double2 bb = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j) + 1);
                     sj = make_double4(a.x, a.y, bb.x, bb.y);
                 } else {  // later: still in its old state
-                    sj = w.snap4[j];
+                    sj = w.cell_state[kk];
                 }
                 if (alive) {
                     const double ddx = sj.x - xi, ddy = sj.y - yi;
@@ -696,6 +730,8 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     for (int q = 0; q < 8; q++) al(sizeof(double) * N);
     al(sizeof(double4) * N);
     al(sizeof(double4) * N);
+    al(sizeof(double4) * N);
+    al(sizeof(int2) * N);
     al(sizeof(double) * 2 * N);
     al(sizeof(double) * 4 * std::max(n_doors, 1));
     for (int q = 0; q < 7; q++) al(sizeof(int) * N);
@@ -720,6 +756,8 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.flags = carve<int>(p, N);
     w.snap4 = carve<double4>(p, N);
     w.live4 = carve<double4>(p, N);
+    w.cell_state = carve<double4>(p, N);
+    w.cell_jr = carve<int2>(p, N);
     w.x0 = carve<double>(p, N); w.y0 = carve<double>(p, N); w.vx0 = carve<double>(p, N); w.vy0 = carve<double>(p, N);
     w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
     w.noise = carve<double>(p, 2 * (size_t)N);

@@ -524,7 +524,8 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     stats->h0 = h_abs;
 
     // stage-fused path (prm->fused): needs room for NE_MAX phi slices when only velocities are requested
-    bool use_fused = prm->fused != 0, fused_attempt = false;
+    // the fused kernel mirrors up to 6 rows / 8 columns across the boundary: tiny grids take the stage-wise path
+    bool use_fused = prm->fused != 0 && s.Ny > fused::HY + 1 && s.Nx > fused::HX + 1, fused_attempt = false;
     double *phi_scratch = nullptr;
     if (use_fused) {
         int n_sm = 148;

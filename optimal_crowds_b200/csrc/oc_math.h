@@ -27,8 +27,12 @@
 
 #if defined(__CUDACC__)
 #define OCM_FN __host__ __device__ __forceinline__
+/* the polynomial cores are called from several places of the GCFM kernels: keeping one copy of each keeps the
+ * sweep kernel inside the instruction cache (ncu: no_instruction stalls with everything inlined) */
+#define OCM_CORE static __host__ __device__ __noinline__
 #else
 #define OCM_FN static inline
+#define OCM_CORE static inline
 #endif
 
 OCM_FN uint64_t ocm_bits(double x) {
@@ -61,7 +65,7 @@ OCM_FN double ocm_norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
 OCM_FN double ocm_pow2i(int k) { return ocm_from_bits((uint64_t)(k + 1023) << 52); }
 
 /* ---------------------------------------------------------------- exp */
-OCM_FN double ocm_exp(double x) {
+OCM_CORE double ocm_exp(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                  inv_ln2 = 1.44269504088896338700e+00;
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
@@ -98,7 +102,7 @@ OCM_FN double ocm_exp(double x) {
 }
 
 /* ---------------------------------------------------------------- atan / atan2 */
-OCM_FN double ocm_atan(double x) {
+OCM_CORE double ocm_atan(double x) {
     const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
                  aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
                  aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
@@ -210,7 +214,7 @@ OCM_FN double ocm_kcos(double x, double y) {
     return w + (((1.0 - w) - hz) + (z * r - x * y));
 }
 /* reduce x (|x| < ~1e5) to r + t = x - n*pi/2, |r| <= pi/4(+eps); returns n & 3 */
-OCM_FN int ocm_rem_pio2(double x, double *r, double *t) {
+OCM_CORE int ocm_rem_pio2(double x, double *r, double *t) {
     const double inv_pio2 = 6.36619772367581382433e-01, p1 = 1.57079632673412561417e+00,
                  p2 = 6.07710050630396597660e-11, p3 = 2.02226624871116645580e-21,
                  p3t = 8.47842766036889956997e-32;
@@ -263,7 +267,7 @@ OCM_FN double ocm_cos(double x) {
 /* ---------------------------------------------------------------- shared-work variants
  * Same bits as the separate calls (tests/test_cpu_oracle.py), less work: the GCFM pair force needs
  * atan2(y,x) AND atan2(-y,-x) (pedestrians.py:266,268) and sin AND cos of the same angle (:270-271). */
-OCM_FN void ocm_sincos(double x, double *s, double *c) {
+OCM_CORE void ocm_sincos(double x, double *s, double *c) {
     double ax = ocm_abs(x);
     if (ocm_isnan(x) || ax == INFINITY || ax <= 7.85398163397448278999e-01) {
         *s = ocm_sin(x);

@@ -258,3 +258,47 @@ def test_rasteriser_and_density_vs_reference(rname, cfg):
     d2 = co.density(ctx.X, ctx.Y, u[f"rast_{rname}_Vglobal"], xy[:, 0], xy[:, 1], st, 0.5)
     assert np.array_equal(d, d2)
     ctx.close()
+
+
+def test_step_with_nobody_inside_and_single_agent(cfg):
+    """edge cases: every agent already left (no noise consumed, nothing moves) and a crowd of one."""
+    from oracle import cpu_oracle as co
+    u = golden("units")
+    room = json.loads(str(u["room"]))
+    ctx, prm = _setup(room, cfg)
+    Ny, Nx = ctx.Ny, ctx.Nx
+    P = co.gcfm_params(cfg, room["room_length"], room["room_height"], Ny, Nx)
+    Vd = ctx.to_device(u["wall_V"])
+    tiles, vmin = ctx.wall_tiles(Vd)
+    vx = ctx.to_device(u["samp_vx"]); vy = ctx.to_device(u["samp_vy"])
+    doors = np.array([[10.0, 3.0, 0.6, 1.2]])
+    key = dict(V=Vd, tiles=tiles, v_min=vmin, vx=vx, vy=vy, nt_opt=5, doors=doors)
+    kc = co.KeyData(u["wall_V"], u["samp_vx"], u["samp_vy"], 5, doors)
+    # (a) nobody inside
+    N = 5
+    st = dict(x=np.linspace(1, 3, N), y=np.full(N, 2.0), vx=np.zeros(N), vy=np.zeros(N), time=np.full(N, 1.5),
+              status=np.zeros(N, dtype=np.uint8))
+    dev = {k: ctx.to_device(v) for k, v in st.items()}
+    ex, rc = ctx.gcfm_step(prm, dev, ctx.to_device(np.full(N, 1.3)), ctx.to_device(np.zeros(N, dtype=np.int32)), [key],
+                           np.arange(N)[::-1].copy(), np.zeros((0, 2)), 0)
+    assert rc == 0 and len(ex) == 0
+    for k in st:
+        assert np.array_equal(dev[k].cpu().numpy(), st[k])
+    # (b) one agent next to the door: leaves within a few steps, bit-exact vs the oracle
+    st = dict(x=np.array([9.6]), y=np.array([3.0]), vx=np.array([1.0]), vy=np.array([0.0]), time=np.zeros(1),
+              status=np.ones(1, dtype=np.uint8))
+    dev = {k: ctx.to_device(v) for k, v in st.items()}
+    rng = np.random.RandomState(4)
+    left = False
+    for s in range(4):
+        if not st["status"][0]:
+            break
+        nz = rng.normal(size=(1, 2)) * 0.01
+        ex, rc = ctx.gcfm_step(prm, dev, ctx.to_device(np.array([1.3])), ctx.to_device(np.zeros(1, dtype=np.int32)), [key],
+                               np.array([0]), nz, s)
+        ex2, bad, _ = co.gcfm_step(P, st, np.array([1.3]), np.zeros(1, dtype=np.int32), [kc], ctx.X, ctx.Y, np.array([0]), nz, s)
+        assert rc == 0 and bad == 0 and np.array_equal(ex, ex2)
+        for k in st:
+            assert np.array_equal(dev[k].cpu().numpy(), st[k])
+        left = left or len(ex) == 1
+    ctx.close()

@@ -232,3 +232,24 @@ def test_row_band_decomposition_is_bit_invariant(n_virtual, cfg, torch_mod):
     vx_o, vy_o = co.fill_field(phi_o, Ny, Nx)
     assert np.abs(many["vx"].cpu().numpy() - vx_o).max() < 1e-10
     ctx.close()
+
+
+@FUSED
+@pytest.mark.parametrize("shape", [(5, 7), (7, 9), (8, 10), (9, 40)])
+def test_tiny_grids_and_single_sample(shape, fused, cfg, torch_mod):
+    """grids smaller than the fused kernel's halo (automatic stage-wise path) and nt = 1 (only t = T is sampled)."""
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    Ny, Nx = shape
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    V = np.zeros((Ny, Nx)); V[0, :] = V[-1, :] = V[:, 0] = V[:, -1] = -100; V[Ny // 2, -1] = 1.0
+    ctx = _lib.Context(L, H, 0.05)
+    for T, nt in ((0.2, 10), (0.06, 1)):
+        phi_ref, st_ref, h_ref, _ = co.hjb_solve(V, None, T, nt)
+        res = ctx.hjb_solve(ctx.to_device(V), None, _lib.hjb_params(cfg, fused=fused), T, nt, want_phi=True, trace=True)
+        assert res["stats"]["nfev"] == st_ref["nfev"] and res["stats"]["n_out"] == nt
+        np.testing.assert_allclose(res["phi"].cpu().numpy().reshape(nt, -1), phi_ref, rtol=RTOL)
+        if nt > 1:
+            vx_ref, vy_ref = co.fill_field(phi_ref, Ny, Nx)
+            assert np.abs(res["vx"].cpu().numpy() - vx_ref).max() < RTOL
+    ctx.close()
