@@ -53,6 +53,13 @@ int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_
                   const double *X, const double *Y, oc_ctx **out);
 void oc_ctx_destroy(oc_ctx *ctx);
 
+/* Host -> device copy of a caller-owned input array (e.g. the density `m` that
+ * optimals.compute_optimal_velocity(t, m) receives as a numpy array, optimals.py:124) onto `stream`.
+ * Page-locked `host` memory goes to the copy engine directly and must stay valid until `stream` has passed the
+ * copy; pageable memory is staged through the context's pinned buffers (memcpy overlapped with DMA) and has been
+ * read completely when the call returns. */
+int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream);
+
 /* ------------------------------------------------------------------ room rasteriser (K8)
  * Replaces simulation.create_potential (simulations.py:516-576) followed by the value remap of
  * optimals.__init__ (optimals.py:89-91) when remap != 0 (V<0 -> wall_value, V>0 -> target_value).

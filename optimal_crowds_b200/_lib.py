@@ -80,7 +80,7 @@ _lib = None
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
-           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_gcfm_step_launch",
+           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_gcfm_step_launch",
            "oc_gcfm_step_finish"]
 
 
@@ -113,6 +113,7 @@ def load():
                                       dp, dp, C.c_int, ip, C.c_void_p]
     lib.oc_rasterise_band.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oc_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.oc_dist_unique_id.argtypes = [C.c_void_p]
     lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.oc_dist_finalize.argtypes = [C.c_void_p]
@@ -206,6 +207,15 @@ class Context:
         if dtype is not None:
             t = t.to(dtype)
         return t.to(self.torch_device)
+
+    def upload(self, a, out):
+        """numpy array -> existing device tensor `out` of the same dtype/size through oc_upload (one DMA from
+        page-locked memory, pipelined staging otherwise).  Asynchronous on the current stream for page-locked
+        sources: the next library call that synchronises (e.g. the solve) covers it."""
+        a = np.ascontiguousarray(a)
+        assert a.nbytes == out.numel() * out.element_size() and out.is_contiguous()
+        check(load().oc_upload(self.h, a.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()), a.nbytes, _stream()))
+        return a  # keep alive until the stream has been synchronised
 
     # ---- K8
     def rasterise(self, walls, holes, cyls, targets, remap=False, wall_value=-100.0, target_value=1.0, out=None):

@@ -1,4 +1,5 @@
 // oc_api.cu -- context management, error text, rasteriser (K8) and density (K7) of liboc_b200.so.
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 
@@ -69,9 +70,46 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->gcfm_ws);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
+    for (int q = 0; q < 2; q++) {
+        if (c->up_stage[q]) cudaFreeHost(c->up_stage[q]);
+        if (c->up_ev[q]) cudaEventDestroy(c->up_ev[q]);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host -> device transfer of an input array (the density `m` of optimals.compute_optimal_velocity arrives as a
+// numpy array, optimals.py:124).  Page-locked sources are handed to the copy engine directly; pageable ones are
+// staged through two pinned buffers so that the host memcpy of chunk k+1 overlaps the DMA of chunk k.
+extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream) {
+    OC_ARG(ctx && (bytes == 0 || (host && d_dst)) && bytes >= 0, "NULL argument");
+    if (bytes == 0) return OC_OK;
+    OC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaPointerAttributes at{};
+    bool pinned = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        OC_CUDA(cudaMemcpyAsync(d_dst, host, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        return OC_OK;  // the caller keeps `host` alive until `stream` has passed this point
+    }
+    constexpr size_t CH = (size_t)16 << 20;
+    for (int q = 0; q < 2; q++) {
+        if (!ctx->up_stage[q]) OC_CUDA(cudaMallocHost(&ctx->up_stage[q], CH));
+        if (!ctx->up_ev[q]) OC_CUDA(cudaEventCreateWithFlags(&ctx->up_ev[q], cudaEventDisableTiming));
+    }
+    size_t off = 0;
+    for (int k = 0; off < (size_t)bytes; k++, off += CH) {
+        const int q = k & 1;
+        const size_t nb = std::min(CH, (size_t)bytes - off);
+        if (k >= 2) OC_CUDA(cudaEventSynchronize(ctx->up_ev[q]));  // the DMA that last used this buffer is done
+        memcpy(ctx->up_stage[q], (const char *)host + off, nb);
+        OC_CUDA(cudaMemcpyAsync((char *)d_dst + off, ctx->up_stage[q], nb, cudaMemcpyHostToDevice, st));
+        OC_CUDA(cudaEventRecord(ctx->up_ev[q], st));
+    }
+    return OC_OK;  // `host` has been read completely; the staging buffers are reused only after their events
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,8 @@ struct oc_ctx {
     double gcfm_last_ms = 0.0;
     void *gcfm_stream = nullptr;
     bool gcfm_pending = false;
+    void *up_stage[2] = {nullptr, nullptr};  // pinned staging buffers of oc_upload (pageable sources)
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
 };
 
 namespace oc {

@@ -85,6 +85,7 @@ class optimals:
             self.d_vx = self.d_vy = None
             self.d_phi = torch.empty((n_slices + 1, self.Ny, self.Nx), dtype=torch.float64, device=self.d_V.device)
         self._h_vx = self._h_vy = None
+        self._d_m = None
         self.phi_T = np.zeros((self.Ny, self.Nx), dtype=float).reshape(self.Nx * self.Ny) + 1  # optimals.py:83,93
         self.last_stats = None
 
@@ -144,7 +145,12 @@ class optimals:
         if m is None or (np.isscalar(m) and m == 0):
             d_m = None
         elif isinstance(m, np.ndarray):
-            d_m = self._ctx.to_device(np.asarray(m, dtype=np.float64).reshape(self.Ny, self.Nx))
+            # host density -> persistent device buffer; the solve below synchronises the stream, which also
+            # covers the (asynchronous) copy from a page-locked source
+            if self._d_m is None:
+                self._d_m = self._ctx.empty(self.Ny, self.Nx)
+            _keep = self._ctx.upload(np.asarray(m, dtype=np.float64).reshape(self.Ny, self.Nx), self._d_m)
+            d_m = self._d_m
         else:
             d_m = m.reshape(self.Ny, self.Nx)
         if nt - 1 > self._n_slices:

@@ -8,7 +8,7 @@ tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 os.makedirs("profiles", exist_ok=True)
 out = [f"# ncu summary `{tag}`", ""]
 
-rows = list(csv.reader(open(launches_csv)))
+rows = list(csv.reader(open(launches_csv))) if launches_csv != "-" else [["ID", "Kernel Name", "Metric Value"]]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr, data = rows[hi], rows[hi + 1:]
 ki, mi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -24,7 +24,8 @@ for r in data:
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
-out += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)",
+if agg:
+  out += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)",
         "", f"command: see scripts/profile_hjb.sh; {sum(a[0] for a in agg.values())} launches, {tot/1e6:.1f} ms total", "",
         "| share | launches | avg us | kernel |", "|---:|---:|---:|---|"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -40,7 +41,14 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
-        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
+        "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_lsu.sum",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.per_cycle_active"]
 stalls = [n for n in h if "issue_stalled" in n and n.endswith("per_issue_active.ratio")]
 out += ["## Full capture (`ncu --set full --clock-control none --import-source on`)", ""]
 traffic = {}
