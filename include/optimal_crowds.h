@@ -115,6 +115,20 @@ int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, const oc_hjb
                  const double *t_eval, int nt, double *d_phi, double *d_vx, double *d_vy, oc_hjb_stats *stats,
                  double *trace_h, double *trace_err, int trace_cap, int *trace_n, void *stream);
 
+/* ------------------------------------------------------------------ batched HJB solve (ensembles)
+ * n_rooms independent solves on the context's grid shape (BASELINE configs[4]: ensembles of rooms / seeds, one
+ * batch per GPU; the reference would call optimals.compute_optimal_velocity once per room, optimals.py:124-206).
+ * Every room keeps its own RK45 controller state and runs on its own CUDA stream, so the rooms' kernels overlap
+ * and the host's per-attempt round trip is hidden behind the other rooms' work.  A room's result is bit-identical
+ * to oc_hjb_solve of that room alone with the same prm->chunk_rows (same kernels, same reduction order).
+ * d_V[b], d_m[b] (d_m or entries nullable), d_phi[b] (nt,Ny,Nx), d_vx[b], d_vy[b] (nt-1,Ny-2,Nx-2): arrays of
+ * n_rooms device pointers held in HOST memory; d_phi or (d_vx and d_vy) may be NULL.  stats: n_rooms entries.
+ * prm->fused, forced_h and profile are ignored (always the stage-fused kernel, free-running controller).
+ * Returns OC_ERR_STEP_TOO_SMALL if any room's integration stopped early (its stats.status == -1). */
+int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const *d_V, const double *const *d_m,
+                       const oc_hjb_params *prm, double T, const double *t_eval, int nt, double *const *d_phi,
+                       double *const *d_vx, double *const *d_vy, oc_hjb_stats *stats, void *stream);
+
 /* ------------------------------------------------------------------ row-decomposed HJB solve (multi-GPU)
  * The grid of the context is split into bands of rows.  Two modes:
  *  - distributed: one process per GPU; call oc_dist_unique_id on rank 0, broadcast the 128 bytes (e.g. with

@@ -80,7 +80,7 @@ _lib = None
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
-           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_gcfm_step_launch",
+           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
            "oc_gcfm_step_finish"]
 
 
@@ -113,6 +113,9 @@ def load():
                                       dp, dp, C.c_int, ip, C.c_void_p]
     lib.oc_rasterise_band.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    vpp = C.POINTER(C.c_void_p)
+    lib.oc_hjb_solve_batch.argtypes = [C.c_void_p, C.c_int, vpp, vpp, C.POINTER(HjbParams), C.c_double, dp, C.c_int,
+                                       vpp, vpp, vpp, C.POINTER(HjbStats), C.c_void_p]
     lib.oc_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.oc_dist_unique_id.argtypes = [C.c_void_p]
     lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -299,6 +302,35 @@ class Context:
             k = min(ntr.value, cap)
             res["trace_h"], res["trace_err"] = th[:k].copy(), te[:k].copy()
         return res
+
+    def hjb_solve_batch(self, Vs, ms, prm: HjbParams, T, nt, out_phi=None, out_vx=None, out_vy=None, want_vel=False):
+        """Independent solves of len(Vs) rooms on this context's grid, overlapped on the GPU (oc_hjb_solve_batch).
+        Vs: list of (Ny,Nx) CUDA tensors; ms: None or list of tensors / None; out_*: lists of tensors or None
+        (phi slices (nt,Ny,Nx) are allocated when no output is given).  Returns a list of per-room dicts."""
+        B = len(Vs)
+        t_eval = np.linspace(T, 0, nt)
+        if out_phi is None and not (want_vel or out_vx is not None):
+            out_phi = [self.empty(nt, self.Ny, self.Nx) for _ in range(B)]
+        if want_vel and out_vx is None:
+            out_vx = [self.empty(max(nt - 1, 0), self.Ny - 2, self.Nx - 2) for _ in range(B)]
+            out_vy = [self.empty(max(nt - 1, 0), self.Ny - 2, self.Nx - 2) for _ in range(B)]
+
+        def ptrs(ts):
+            if ts is None:
+                return None
+            arr = (C.c_void_p * B)()
+            for q, t in enumerate(ts):
+                if t is not None:
+                    assert t.is_cuda and t.is_contiguous()
+                    arr[q] = t.data_ptr()
+            return arr
+        st = (HjbStats * B)()
+        rc = load().oc_hjb_solve_batch(self.h, B, ptrs(Vs), ptrs(ms), C.byref(prm), float(T), _hp(t_eval), int(nt),
+                                       ptrs(out_phi), ptrs(out_vx), ptrs(out_vy), st, _stream())
+        check(rc, allow=(OC_ERR_STEP_TOO_SMALL,))
+        return [{"stats": st[q].asdict(), "phi": out_phi[q] if out_phi is not None else None,
+                 "vx": out_vx[q] if out_vx is not None else None, "vy": out_vy[q] if out_vx is not None else None,
+                 "rc": rc if st[q].status == -1 else 0} for q in range(B)]
 
     def hjb_rhs(self, phi, V, m, prm: HjbParams):
         out = self.empty(self.Ny, self.Nx)

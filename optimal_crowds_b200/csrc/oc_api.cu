@@ -70,6 +70,10 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->gcfm_ws);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
+    cudaFree(c->batch_ws);
+    if (c->batch_pinned) cudaFreeHost(c->batch_pinned);
+    for (auto s : c->batch_streams) cudaStreamDestroy(s);
+    for (auto e : c->batch_events) cudaEventDestroy(e);
     for (int q = 0; q < 2; q++) {
         if (c->up_stage[q]) cudaFreeHost(c->up_stage[q]);
         if (c->up_ev[q]) cudaEventDestroy(c->up_ev[q]);

@@ -40,6 +40,13 @@ struct oc_ctx {
     double gcfm_last_ms = 0.0;
     void *gcfm_stream = nullptr;
     bool gcfm_pending = false;
+    // batched (ensemble) HJB solve: per-room workspace, streams and events
+    double *batch_ws = nullptr;
+    size_t batch_ws_bytes = 0;
+    double *batch_pinned = nullptr;
+    size_t batch_pinned_n = 0;
+    std::vector<cudaStream_t> batch_streams;
+    std::vector<cudaEvent_t> batch_events;
     void *up_stage[2] = {nullptr, nullptr};  // pinned staging buffers of oc_upload (pageable sources)
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
 };

@@ -742,3 +742,318 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     }
     return OC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Batched solve for ensembles of independent rooms on one grid shape (BASELINE configs[4]).
+// Every room keeps its own RK45 controller (t, h, accept/reject, t_eval cursor: the reference integrates each
+// room separately, optimals.py:193-196) and its own CUDA stream; a room's step attempt is ONE launch of the
+// stage-fused kernel followed by the fixed-order reduction, exactly the launches oc_hjb_solve issues, so every
+// room's result is bit-identical to solving it alone (with the same prm->chunk_rows).  The host serves the rooms
+// round-robin: while it reads room b's error norm and enqueues b's next attempt, the other rooms' kernels keep
+// the GPU busy -- small grids (512^2: ~10 us of device work per attempt) are launch-latency bound one at a time.
+namespace {
+
+struct BatchRoom {
+    Solver s;
+    enum Phase { START, INIT0, INIT1, STEP, DONE } phase = START;
+    const double *V = nullptr, *m = nullptr;
+    double *phi = nullptr, *vx = nullptr, *vy = nullptr;
+    double *rs_d = nullptr, *rs_h = nullptr;  // row-group sums (device / pinned host), 3 regions of `rs_stride`
+    int rs_stride = 0;
+    cudaEvent_t ev = nullptr;
+    // controller state (rk.py:111-176, base.py:179-210, ivp.py:659-728)
+    double t = 0, h_abs = 0, h = 0, t_new = 0, min_step = 0, h0 = 0, d1 = 0;
+    bool rejected = false;
+    int status = 1, t_eval_i = 0, n_out = 0, ia_lo = 0;
+    oc_hjb_stats st{};
+};
+
+}  // namespace
+
+extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const *d_V, const double *const *d_m,
+                                  const oc_hjb_params *prm, double T, const double *t_eval, int nt,
+                                  double *const *d_phi, double *const *d_vx, double *const *d_vy,
+                                  oc_hjb_stats *stats, void *stream) {
+    OC_ARG(ctx && d_V && prm && stats && n_rooms >= 1, "NULL argument");
+    OC_ARG(nt >= 1 && t_eval, "t_eval required");
+    OC_ARG(d_phi || (d_vx && d_vy), "an output (d_phi or d_vx,d_vy) is required");
+    const int Ny = ctx->Ny, Nx = ctx->Nx;
+    OC_ARG(Ny > fused::HY + 1 && Nx > fused::HX + 1, "grid too small for the stage-fused kernel");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t main_st = (cudaStream_t)stream;
+    const size_t n = (size_t)Ny * Nx, n_int = (size_t)(Ny - 2) * (Nx - 2);
+    const int nbx = (Nx + TX - 1) / TX, nby = (Ny + TY - 1) / TY;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int fgx = (Nx + fused::VX - 1) / fused::VX;
+    const int frc = prm->chunk_rows > 0 ? prm->chunk_rows : fused::plan_chunk_rows(Nx, Ny, n_sm, 1, 0);
+    const int fgy = (Ny + frc - 1) / frc;
+    // per room: coef, y, y_new, f, f_new (+ NE_MAX phi slices when only velocities are kept) ; partial sums
+    const bool need_scratch = !d_phi;
+    const size_t np = std::max((size_t)2 * nbx * nby, (size_t)fgx * fgy) + 8;
+    const int rs_stride = std::max(nby, fgy) + 8;
+    const size_t per_room = (5 + (need_scratch ? fused::NE_MAX : 0)) * n + np + 3 * (size_t)rs_stride;
+    const size_t need = per_room * n_rooms * sizeof(double);
+    if (ctx->batch_ws_bytes < need) {
+        if (ctx->batch_ws) cudaFree(ctx->batch_ws);
+        ctx->batch_ws = nullptr; ctx->batch_ws_bytes = 0;
+        if (cudaMalloc(&ctx->batch_ws, need) != cudaSuccess) {
+            cudaGetLastError();
+            oc::set_error("cannot allocate %zu bytes of batched HJB workspace (%d rooms)", need, n_rooms);
+            return OC_ERR_NOMEM;
+        }
+        ctx->batch_ws_bytes = need;
+    }
+    const size_t pin_need = (size_t)3 * rs_stride * n_rooms;
+    if (ctx->batch_pinned_n < pin_need) {
+        if (ctx->batch_pinned) cudaFreeHost(ctx->batch_pinned);
+        ctx->batch_pinned = nullptr; ctx->batch_pinned_n = 0;
+        OC_CUDA(cudaMallocHost(&ctx->batch_pinned, pin_need * sizeof(double)));
+        ctx->batch_pinned_n = pin_need;
+    }
+    constexpr int MAX_STREAMS = 32;
+    const int n_streams = std::min(n_rooms, MAX_STREAMS);
+    while ((int)ctx->batch_streams.size() < n_streams) {
+        cudaStream_t s;
+        OC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        ctx->batch_streams.push_back(s);
+    }
+    while ((int)ctx->batch_events.size() < n_rooms + 1) {
+        cudaEvent_t e;
+        OC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->batch_events.push_back(e);
+    }
+    // inputs produced on the caller's stream are visible to the room streams
+    OC_CUDA(cudaEventRecord(ctx->ev0, main_st));
+    cudaEvent_t ev_in = ctx->batch_events[n_rooms];
+    OC_CUDA(cudaEventRecord(ev_in, main_st));
+    for (int q = 0; q < n_streams; q++) OC_CUDA(cudaStreamWaitEvent(ctx->batch_streams[q], ev_in, 0));
+
+    const double s2 = prm->sigma * prm->sigma;
+    const double rtol = prm->rtol, atol = prm->atol, sqrt_n = std::sqrt((double)n);
+    const double t_bound = 0.0, direction = (t_bound != T) ? (t_bound > T ? 1.0 : -1.0) : 1.0;
+    const double error_exponent = -1.0 / 5.0;
+    const bool want_v = d_vx && d_vy;
+    std::vector<BatchRoom> rooms(n_rooms);
+    for (int b = 0; b < n_rooms; b++) {
+        BatchRoom &r = rooms[b];
+        OC_ARG(d_V[b] && (!d_phi || d_phi[b]) && (!want_v || (d_vx[b] && d_vy[b])), "NULL room pointer");
+        double *ws = ctx->batch_ws + per_room * b;
+        Solver &s = r.s;
+        s.ctx = ctx; s.st = ctx->batch_streams[b % n_streams]; s.Ny = Ny; s.Nx = Nx; s.n = n; s.nbx = nbx; s.nby = nby;
+        s.coef = ws; s.y = ws + n; s.ynew = ws + 2 * n; s.K[0] = ws + 3 * n; s.K[6] = ws + 4 * n;
+        s.K[1] = s.K[6];  // f(y0 + h0 f0) of select_initial_step lives in the (still unused) f_new array
+        double *scratch = need_scratch ? ws + 5 * n : nullptr;
+        s.partial = ws + (5 + (need_scratch ? fused::NE_MAX : 0)) * n;
+        r.rs_d = s.partial + np;
+        r.rs_h = ctx->batch_pinned + (size_t)3 * rs_stride * b;
+        r.rs_stride = rs_stride;
+        s.diff_over_dxdy = (-0.5 * s2) / (ctx->dx * ctx->dy);
+        s.fused_gx = fgx; s.fused_rc = frc; s.fused_gy = fgy;
+        r.V = d_V[b]; r.m = d_m ? d_m[b] : nullptr;
+        r.phi = d_phi ? d_phi[b] : scratch;
+        r.vx = want_v ? d_vx[b] : nullptr; r.vy = want_v ? d_vy[b] : nullptr;
+        r.ev = ctx->batch_events[b];
+        r.t = T; r.t_eval_i = nt;
+    }
+    // room-local helpers ------------------------------------------------------------------------------
+    auto reduce_async = [&](BatchRoom &r, size_t off, int gx, int gy, int slot) {
+        rowgroup_sum_kernel<<<gy, NTHREADS, 0, r.s.st>>>(r.s.partial + off, gx, r.rs_d + (size_t)slot * r.rs_stride);
+        r.s.launches++;
+        cudaMemcpyAsync(r.rs_h + (size_t)slot * r.rs_stride, r.rs_d + (size_t)slot * r.rs_stride, sizeof(double) * gy,
+                        cudaMemcpyDeviceToHost, r.s.st);
+    };
+    auto host_sum = [&](BatchRoom &r, int gy, int slot) {
+        double s = 0.0;
+        const double *p = r.rs_h + (size_t)slot * r.rs_stride;
+        for (int i = 0; i < gy; i++) s += p[i];  // fixed global order
+        return s;
+    };
+    auto lower_index = [&](double t_new) {  // ivp.py:715-728, direction < 0: first ascending index with t_eval >= t_new
+        int lo = 0, hi = nt;
+        while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if (t_eval[nt - 1 - mid] < t_new) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    // enqueue one step attempt of room r (fused kernel + reduction); returns false when the room has finished
+    auto attempt = [&](BatchRoom &r) -> int {
+        if (r.h_abs < r.min_step) { r.status = -1; r.phase = BatchRoom::DONE; return OC_OK; }
+        double h = r.h_abs * direction;
+        double t_new = r.t + h;
+        if (direction * (t_new - t_bound) > 0) t_new = t_bound;
+        h = t_new - r.t;
+        r.h = h; r.t_new = t_new; r.h_abs = std::fabs(h);
+        r.ia_lo = std::min(lower_index(t_new), r.t_eval_i);
+        fused::Args fa{};
+        Solver &s = r.s;
+        fa.y = s.y; fa.k1 = s.K[0]; fa.coef = s.coef; fa.ynew = s.ynew; fa.k7 = s.K[6]; fa.partial = s.partial;
+        fa.ha21 = h * RK_A[1][0];
+        for (int j = 0; j < 2; j++) fa.ha3[j] = h * RK_A[2][j];
+        for (int j = 0; j < 3; j++) fa.ha4[j] = h * RK_A[3][j];
+        for (int j = 0; j < 4; j++) fa.ha5[j] = h * RK_A[4][j];
+        for (int j = 0; j < 5; j++) fa.ha6[j] = h * RK_A[5][j];
+        for (int j = 0; j < 6; j++) fa.hb[j] = h * RK_B[j];
+        for (int j = 0; j < 7; j++) fa.he[j] = h * RK_E[j];
+        fa.A = s.diff_over_dxdy; fa.rtol = rtol; fa.atol = atol;
+        fa.Ny = Ny; fa.Nx = Nx; fa.RC = frc;
+        fa.row_base = 0; fa.own0 = 0; fa.own1 = Ny; fa.phi_row_base = 0;
+        // the samples this attempt emits if accepted, NE_MAX per launch; with more than NE_MAX samples inside one
+        // step (only when h >> dt) the step is simply launched again for the remaining samples: the re-launch
+        // recomputes identical y_new / f_new / error sums
+        int ia = r.t_eval_i - 1;
+        do {
+            int ne = 0;
+            for (; ia >= r.ia_lo && ne < fused::NE_MAX; ia--, ne++) {
+                const int kd = nt - 1 - ia;
+                const double x = (t_eval[kd] - r.t) / h;  // RkDenseOutput: (t - t_old)/h
+                const double pw[4] = {x, x * x, x * x * x, x * x * x * x};
+                for (int j = 0; j < 7; j++) {
+                    double acc = 0.0;
+                    for (int q = 0; q < 4; q++) acc += RK_P[j][q] * pw[q];
+                    fa.w[ne][j] = h * acc;
+                }
+                // without a phi output the samples go to the room's scratch slices (velocities are derived on accept)
+                fa.phi[ne] = d_phi ? r.phi + (size_t)kd * n : r.phi + (size_t)((r.t_eval_i - 1 - ia) % fused::NE_MAX) * n;
+            }
+            int rc = s.launch_fused(ne, fa);
+            if (rc) return rc;
+            if (!d_phi && ia >= r.ia_lo) {
+                oc::set_error("batched solve without a phi output supports at most %d samples per step", fused::NE_MAX);
+                return OC_ERR_ARG;
+            }
+        } while (ia >= r.ia_lo);
+        r.st.nfev += 6;
+        reduce_async(r, 0, fgx, fgy, 0);
+        cudaEventRecord(r.ev, s.st);
+        r.phase = BatchRoom::STEP;
+        return OC_OK;
+    };
+    auto start_step = [&](BatchRoom &r) -> int {  // base.py:179-210 step(): one call of _step_impl
+        if (r.t == t_bound) { r.status = 0; r.phase = BatchRoom::DONE; return OC_OK; }
+        r.min_step = 10 * std::fabs(std::nextafter(r.t, direction * INFINITY) - r.t);
+        if (r.h_abs < r.min_step) r.h_abs = r.min_step;
+        r.rejected = false;
+        return attempt(r);
+    };
+    auto advance = [&](BatchRoom &r) -> int {
+        Solver &s = r.s;
+        switch (r.phase) {
+        case BatchRoom::START: {
+            prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(r.V, r.m, prm->g, 1.0 / (prm->mu * s2), n, s.coef, s.y);
+            s.launches++;
+            Comb c{};
+            c.y = s.y;
+            s.stage(0, c, s.K[0]);  // rk.py:94
+            r.st.nfev++;
+            if (std::fabs(t_bound - T) == 0.0) { r.h_abs = 0.0; r.st.h0 = 0.0; return start_step(r); }
+            init_norm_kernel<<<dim3(nbx, nby), NTHREADS, 0, s.st>>>(s.y, s.K[0], nullptr, rtol, atol, Ny, Nx, s.partial, 0);
+            s.launches++;
+            reduce_async(r, 0, nbx, nby, 0);
+            reduce_async(r, (size_t)nbx * nby, nbx, nby, 1);
+            cudaEventRecord(r.ev, s.st);
+            r.phase = BatchRoom::INIT0;
+            return OC_OK;
+        }
+        case BatchRoom::INIT0: {  // common.py:109-127
+            const double d0 = std::sqrt(host_sum(r, nby, 0)) / sqrt_n, d1 = std::sqrt(host_sum(r, nby, 1)) / sqrt_n;
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = std::min(h0, std::fabs(t_bound - T));
+            r.h0 = h0; r.d1 = d1;
+            Comb c{};
+            c.y = s.y; c.k[0] = s.K[0]; c.a[0] = 1.0; c.h = h0 * direction;
+            s.stage(1, c, s.K[1]);
+            r.st.nfev++;
+            init_norm_kernel<<<dim3(nbx, nby), NTHREADS, 0, s.st>>>(s.y, s.K[0], s.K[1], rtol, atol, Ny, Nx, s.partial, 1);
+            s.launches++;
+            reduce_async(r, 0, nbx, nby, 2);
+            cudaEventRecord(r.ev, s.st);
+            r.phase = BatchRoom::INIT1;
+            return OC_OK;
+        }
+        case BatchRoom::INIT1: {  // common.py:127-134
+            const double d2 = std::sqrt(host_sum(r, nby, 2)) / sqrt_n / r.h0;
+            double h1;
+            if (r.d1 <= 1e-15 && d2 <= 1e-15) h1 = std::max(1e-6, r.h0 * 1e-3);
+            else h1 = std::pow(0.01 / std::max(r.d1, d2), 1.0 / 5.0);
+            r.h_abs = std::min(std::min(100 * r.h0, h1), std::fabs(t_bound - T));
+            r.st.h0 = r.h_abs;
+            return start_step(r);
+        }
+        case BatchRoom::STEP: {  // rk.py:146-165
+            const double error_norm = std::sqrt(host_sum(r, fgy, 0)) / sqrt_n;
+            if (!(error_norm < 1)) {
+                r.h_abs *= std::max(0.2, 0.9 * std::pow(error_norm, error_exponent));
+                r.rejected = true;
+                r.st.n_rejected++;
+                return attempt(r);
+            }
+            double factor = (error_norm == 0) ? 10.0 : std::min(10.0, 0.9 * std::pow(error_norm, error_exponent));
+            if (r.rejected) factor = std::min(1.0, factor);
+            r.h_abs *= factor;
+            r.st.n_accepted++;
+            const int t_eval_i_new = lower_index(r.t_new);
+            for (int ia = r.t_eval_i - 1; ia >= t_eval_i_new; ia--) {
+                const int kd = nt - 1 - ia;
+                r.n_out++;
+                if (want_v && kd >= 1) {  // slice s = vels(sol.y[:, nt-1-s]) (optimals.py:200-204)
+                    const double *ph = d_phi ? r.phi + (size_t)kd * n : r.phi + (size_t)((r.t_eval_i - 1 - ia) % fused::NE_MAX) * n;
+                    const int sl = nt - 1 - kd;
+                    dim3 grid((Nx - 2 + 63) / 64, (Ny - 2 + 3) / 4);
+                    vels_kernel<<<grid, NTHREADS, 0, s.st>>>(ph, Ny, Nx, prm->mu, prm->lim, 1.0 / (2 * ctx->dx), 1.0 / (2 * ctx->dy),
+                                                             r.vx + (size_t)sl * n_int, r.vy + (size_t)sl * n_int);
+                    s.launches++;
+                }
+            }
+            r.t_eval_i = t_eval_i_new;
+            const bool finished = direction * (r.t_new - t_bound) >= 0;  // base.py:205-208
+            r.t = r.t_new;
+            std::swap(s.y, s.ynew);
+            std::swap(s.K[0], s.K[6]);
+            if (finished) { r.status = 0; r.phase = BatchRoom::DONE; return OC_OK; }
+            return start_step(r);
+        }
+        default: return OC_OK;
+        }
+    };
+    int rc = OC_OK, live = n_rooms;
+    for (int b = 0; b < n_rooms && !rc; b++) {
+        rc = advance(rooms[b]);
+        if (rooms[b].phase == BatchRoom::DONE) live--;
+    }
+    while (live > 0 && !rc) {
+        for (int b = 0; b < n_rooms && !rc; b++) {
+            BatchRoom &r = rooms[b];
+            if (r.phase == BatchRoom::DONE) continue;
+            OC_CUDA(cudaEventSynchronize(r.ev));
+            rc = advance(r);
+            if (r.phase == BatchRoom::DONE) live--;
+        }
+    }
+    // the caller's stream continues after every room stream
+    for (int q = 0; q < n_streams; q++) {
+        cudaEventRecord(ctx->batch_events[q], ctx->batch_streams[q]);
+        cudaStreamWaitEvent(main_st, ctx->batch_events[q], 0);
+    }
+    OC_CUDA(cudaEventRecord(ctx->ev1, main_st));
+    OC_CUDA(cudaStreamSynchronize(main_st));
+    OC_CUDA(cudaGetLastError());
+    if (rc) return rc;
+    float ms = 0;
+    OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    int bad = -1, total_launches = 0;
+    for (int b = 0; b < n_rooms; b++) {
+        BatchRoom &r = rooms[b];
+        r.st.status = r.status; r.st.n_out = r.n_out; r.st.launches = r.s.launches; r.st.gpu_ms = ms;
+        total_launches += r.s.launches;
+        stats[b] = r.st;
+        if (r.status == -1 && bad < 0) bad = b;
+    }
+    oc::count_launch(total_launches);
+    if (bad >= 0) {
+        oc::set_error("RK45: required step size is less than spacing between numbers (room %d, t=%g)", bad, rooms[bad].t);
+        return OC_ERR_STEP_TOO_SMALL;
+    }
+    return OC_OK;
+}

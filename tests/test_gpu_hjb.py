@@ -253,3 +253,47 @@ def test_tiny_grids_and_single_sample(shape, fused, cfg, torch_mod):
             vx_ref, vy_ref = co.fill_field(phi_ref, Ny, Nx)
             assert np.abs(res["vx"].cpu().numpy() - vx_ref).max() < RTOL
     ctx.close()
+
+
+@pytest.mark.parametrize("store", ["phi", "velocity"])
+def test_batched_solve_is_bitwise_the_single_solves(store, cfg, torch_mod):
+    """ensemble path (oc_hjb_solve_batch): rooms with different potentials / densities, each with its own RK45
+    controller, overlapped on streams -- every room must reproduce its stand-alone solve bit for bit, and the
+    oracle to 1e-10."""
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    Ny, Nx, T, nt = 70, 150, 0.5, 25
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    ctx = _lib.Context(L, H, 0.05)
+    rng = np.random.RandomState(7)
+    B = 5
+    Vs, ms = [], []
+    for b in range(B):
+        V = np.zeros((Ny, Nx)); V[0, :] = V[-1, :] = V[:, 0] = V[:, -1] = -100
+        V[10 + 5 * b:14 + 5 * b, 40:44 + 10 * b] = -100          # an obstacle that differs per room
+        V[Ny // 2 - 3 + b:Ny // 2 + 3 + b, -1] = 1.0              # door
+        Vs.append(V)
+        ms.append(rng.uniform(0, 1, size=(Ny, Nx)) if b % 2 else None)
+    dV = [ctx.to_device(v) for v in Vs]
+    dm = [ctx.to_device(m) if m is not None else None for m in ms]
+    prm = _lib.hjb_params(cfg, fused=1, chunk_rows=32)
+    vel = store == "velocity"
+    batch = ctx.hjb_solve_batch(dV, dm, prm, T, nt, want_vel=vel)
+    nfevs = set()
+    for b in range(B):
+        one = ctx.hjb_solve(dV[b], dm[b], prm, T, nt, want_phi=not vel, want_vel=vel)
+        assert batch[b]["stats"]["status"] == 0 and batch[b]["stats"]["n_out"] == nt
+        for k in ("nfev", "n_accepted", "n_rejected"):
+            assert batch[b]["stats"][k] == one["stats"][k]
+        nfevs.add(one["stats"]["nfev"])
+        phi_ref, st_ref, _, _ = co.hjb_solve(Vs[b], ms[b], T, nt)
+        assert st_ref["nfev"] == one["stats"]["nfev"]
+        if vel:
+            assert torch_mod.equal(batch[b]["vx"], one["vx"]) and torch_mod.equal(batch[b]["vy"], one["vy"])
+            vx_ref, _ = co.fill_field(phi_ref, Ny, Nx)
+            assert np.abs(batch[b]["vx"].cpu().numpy() - vx_ref).max() < RTOL
+        else:
+            assert torch_mod.equal(batch[b]["phi"], one["phi"])
+            np.testing.assert_allclose(batch[b]["phi"].cpu().numpy().reshape(nt, -1), phi_ref, rtol=RTOL)
+    assert len(nfevs) > 1, "rooms should need different numbers of attempts (independent controllers)"
+    ctx.close()
