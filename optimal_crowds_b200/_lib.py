@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboc_b200.so")
+# OC_B200_LIB: alternative build of the same library (kernel-variant experiments, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("OC_B200_LIB") or os.path.join(_HERE, "liboc_b200.so")
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

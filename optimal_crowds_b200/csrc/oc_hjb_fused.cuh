@@ -23,17 +23,33 @@
 
 namespace fused {
 
-constexpr int BX = 128;             // threads per CTA = columns per tile incl. halo
+#ifndef OC_BX
+#define OC_BX 128
+#endif
+#ifndef OC_PF
+#define OC_PF 6
+#endif
+#ifndef OC_PD
+#define OC_PD (OC_PF - 1)
+#endif
+constexpr int BX = OC_BX;           // threads per CTA = columns per tile incl. halo
 constexpr int HX = 8;               // halo columns per side (6 needed)
 constexpr int VX = BX - 2 * HX;     // valid output columns per tile (112)
 constexpr int HY = 6;               // halo rows per side
-constexpr int PF = 6;               // cp.async ring depth (rows): rows r .. r+PD
-constexpr int PD = 5;               // prefetch distance (rows in flight)
+constexpr int PF = OC_PF;           // cp.async ring depth (rows): rows r .. r+PD
+constexpr int PD = OC_PD;           // prefetch distance (rows in flight)
 constexpr int UNROLL = 12;          // rows per unrolled loop body (multiple of PF and of 2)
+static_assert(UNROLL % PF == 0 && UNROLL % 2 == 0 && PD < PF, "ring / unroll geometry");
 #ifndef OC_CTAS
-#define OC_CTAS 3
+#define OC_CTAS 2
 #endif
-constexpr int CTAS_PER_SM = OC_CTAS;      // 3 x 30.5 KB shared memory, <= 168 registers/thread
+#if !defined(OC_BRANCHY) && !defined(OC_BRANCHLESS)
+#define OC_BRANCHLESS 1
+#endif
+// 2 CTAs (8 warps) per SM with 192 registers/thread beat 3 CTAs at 164: the row body is one long straight-line block
+// and the extra registers buy instruction-level parallelism across the six stage chains (measured 0.75 vs 0.70 of
+// the HBM peak, profiles/r1_fused_v4.md)
+constexpr int CTAS_PER_SM = OC_CTAS;
 constexpr int NE_MAX = 6;           // dense-output samples per launch
 
 // rows per CTA chunk: balance the tail of the last wave (slots = SMs x resident CTAs) against the 2*HY halo rows
@@ -76,6 +92,16 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
+// predicated forms: the unrolled row body has no divergent region (a branch around the loads / stores makes ptxas save
+// and restore the uniform registers that hold the RK coefficients on both sides of it)
+__device__ __forceinline__ void cp_async8_if(void *smem, const void *gmem, bool ok) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 8; }"
+                 ::"r"(s), "l"(gmem), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void st_if(double *p, double v, bool ok) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.global.f64 [%0], %1; }" ::"l"(p), "d"(v), "r"((int)ok) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -93,7 +119,11 @@ __device__ __forceinline__ double rhs_pre(double up, double lf, double rt, doubl
 }
 __device__ __forceinline__ double rhs_fin(double pre, double dn, double cf, double A) {
     double r = fma(A, dn, pre);
+#ifdef OC_WALLINT
+    return (__double2hiint(cf) == 0x7ff80000) ? 0.0 : r;  // wall marker written by prep_kernel (integer pipe)
+#else
     return (cf != cf) ? 0.0 : r;  // wall: optimals.py:162
+#endif
 }
 
 // 1/x for finite x > 0 (the error scale is >= atol): hardware seed + two Newton steps (~1e-16), no slow path
@@ -111,6 +141,9 @@ struct Smem {
     double ex[2][6][BX + 2];   // published stage-input rows (u2..u6, y_new), double buffered
     double pf[PF][3][BX];      // cp.async ring: y, k1, coef
     double red[BX / 32];
+#ifdef OC_LDSCONST
+    double cst[(1 + NE_MAX) * 6];  // h*E and the dense-output weights, read as broadcast LDS.128 (frees uniform registers)
+#endif
 };
 
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
@@ -128,6 +161,14 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     const int phi_shift = (a.row_base - a.phi_row_base) * a.Nx;    // phi slices may start at another global row
 
     for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
+#ifdef OC_LDSCONST
+    if (tid < 6) {
+        const int j = tid == 0 ? 0 : tid + 1;  // stages 1,3,4,5,6,7 (B[1] = E[1] = P[1] = 0)
+        sm.cst[tid] = a.he[j];
+#pragma unroll
+        for (int ee = 0; ee < NE; ee++) sm.cst[6 * (ee + 1) + tid] = a.w[ee][j];
+    }
+#endif
 
     // windows, indexed by lag (row r - lag)
     // all windows are registers.  Shared memory is the bottleneck resource of this kernel (every LDS.64 of a
@@ -144,7 +185,19 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     const int r_begin = y0 - HY, r_end = y1 + HY;  // rows loaded: [r_begin, r_end)
     // ring slot of row `row` = (row - r_begin) mod PF, tracked incrementally (PF is not a power of two)
     auto issue = [&](int row, int slot) {
+#ifdef OC_BRANCHLESS
+        {
+            const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
+            const int g = (rm - a.row_base) * a.Nx + gxm;
+            const bool ok = row < r_end;
+            cp_async8_if(&sm.pf[slot][0][tid], a.y + g, ok);
+            cp_async8_if(&sm.pf[slot][1][tid], a.k1 + g, ok);
+            cp_async8_if(&sm.pf[slot][2][tid], a.coef + g, ok);
+        }
+        if (false) {
+#else
         if (row < r_end) {
+#endif
             // element offsets fit 32 bits (one field < 2^31 elements); one IMAD instead of 64-bit multiplies
             const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
             const int g = (rm - a.row_base) * a.Nx + gxm;
@@ -212,6 +265,48 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         exc[4 * (BX + 2)] = u6[4];
         exc[5 * (BX + 2)] = un[5];
         // ---- outputs on row r-6
+#if defined(OC_LDSCONST)
+        {
+            const int row = r - 6;
+            const bool ok = col_out && row >= y0 && row < y1;
+            const int g = (row - a.row_base) * a.Nx + gx;
+            const double2 *cs = reinterpret_cast<const double2 *>(sm.cst);
+            const double2 e01 = cs[0], e23 = cs[1], e45 = cs[2];
+            double e = fma(e45.y, k7, fma(e45.x, k6w[6], fma(e23.y, k5w[6], fma(e23.x, k4w[6], fma(e01.y, k3w[6], e01.x * k1w[6])))));
+            double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
+            double qq = e * rcp_pos(sc);
+            acc = ok ? fma(qq, qq, acc) : acc;
+            st_if(a.ynew + g, un[6], ok);
+            st_if(a.k7 + g, k7, ok);
+#pragma unroll
+            for (int ee = 0; ee < NE; ee++) {
+                const double2 w01 = cs[3 * (ee + 1)], w23 = cs[3 * (ee + 1) + 1], w45 = cs[3 * (ee + 1) + 2];
+                double ph = fma(w45.y, k7, fma(w45.x, k6w[6], fma(w23.y, k5w[6], fma(w23.x, k4w[6], fma(w01.y, k3w[6], fma(w01.x, k1w[6], yw[6]))))));
+                st_if(a.phi[ee] + (g + phi_shift), ph, ok);
+            }
+        }
+#elif defined(OC_BRANCHLESS)
+        {
+            // the arithmetic is unconditional (halo threads compute values nobody reads) and only the stores and the
+            // error accumulation are predicated: no divergent region inside the unrolled body
+            const int row = r - 6;
+            const bool ok = col_out && row >= y0 && row < y1;
+            const int g = (row - a.row_base) * a.Nx + gx;
+            double e = fma(a.he[6], k7, fma(a.he[5], k6w[6], fma(a.he[4], k5w[6], fma(a.he[3], k4w[6],
+                           fma(a.he[2], k3w[6], a.he[0] * k1w[6])))));
+            double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
+            double qq = e * rcp_pos(sc);
+            acc = ok ? fma(qq, qq, acc) : acc;
+            st_if(a.ynew + g, un[6], ok);
+            st_if(a.k7 + g, k7, ok);
+#pragma unroll
+            for (int ee = 0; ee < NE; ee++) {
+                double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
+                                fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
+                st_if(a.phi[ee] + (g + phi_shift), ph, ok);
+            }
+        }
+#else
         {
             const int row = r - 6;
             if (col_out && row >= y0 && row < y1) {
@@ -233,6 +328,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
                 }
             }
         }
+#endif
         __syncthreads();
         // ---- shift windows by one row (pure renaming inside the unrolled body)
 #pragma unroll
