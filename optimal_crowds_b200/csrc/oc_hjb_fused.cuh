@@ -46,6 +46,9 @@ static_assert(UNROLL % PF == 0 && UNROLL % 2 == 0 && PD < PF, "ring / unroll geo
 #if !defined(OC_BRANCHY) && !defined(OC_BRANCHLESS)
 #define OC_BRANCHLESS 1
 #endif
+#if !defined(OC_VREGCONST) && !defined(OC_LDSCONST) && defined(OC_BRANCHLESS)
+#define OC_VREGCONST 3
+#endif
 // 2 CTAs (8 warps) per SM with 192 registers/thread beat 3 CTAs at 164: the row body is one long straight-line block
 // and the extra registers buy instruction-level parallelism across the six stage chains (measured 0.75 vs 0.70 of
 // the HBM peak, profiles/r1_fused_v4.md)
@@ -141,7 +144,7 @@ struct Smem {
     double ex[2][6][BX + 2];   // published stage-input rows (u2..u6, y_new), double buffered
     double pf[PF][3][BX];      // cp.async ring: y, k1, coef
     double red[BX / 32];
-#ifdef OC_LDSCONST
+#if defined(OC_LDSCONST) || defined(OC_VREGCONST)
     double cst[(1 + NE_MAX) * 6];  // h*E and the dense-output weights, read as broadcast LDS.128 (frees uniform registers)
 #endif
 };
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     const int phi_shift = (a.row_base - a.phi_row_base) * a.Nx;    // phi slices may start at another global row
 
     for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
-#ifdef OC_LDSCONST
+#if defined(OC_LDSCONST) || defined(OC_VREGCONST)
     if (tid < 6) {
         const int j = tid == 0 ? 0 : tid + 1;  // stages 1,3,4,5,6,7 (B[1] = E[1] = P[1] = 0)
         sm.cst[tid] = a.he[j];
@@ -212,6 +215,26 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     for (int q = 0; q < PD; q++) issue(r_begin + q, q);
     __syncthreads();
 
+#ifdef OC_VREGCONST
+    // The ~47 FP64 constants of the body do not fit the uniform register file (ptxas then spills uniform registers
+    // through MOV.SPILL / R2UR.FILL every row).  With 2 CTAs/SM there are spare vector registers: the dense-output
+    // weights of the first OC_VREGCONST samples (and h*E) are pinned there by making them opaque to the compiler.
+    constexpr int NV = NE < OC_VREGCONST ? NE : OC_VREGCONST;
+    double wv[NV > 0 ? NV : 1][6], hev[6];
+    // (read back from shared memory: a value ptxas could re-derive from the constant bank would not stay in a register)
+    __syncthreads();
+#pragma unroll
+    for (int ee = 0; ee < NV; ee++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) wv[ee][j] = sm.cst[6 * (ee + 1) + j];
+#ifdef OC_VREGCONST_E
+#pragma unroll
+    for (int j = 0; j < 6; j++) hev[j] = sm.cst[j];
+#else
+#pragma unroll
+    for (int j = 0; j < 6; j++) hev[j] = a.he[j == 0 ? 0 : j + 1];
+#endif
+#endif
     double acc = 0.0;
     // The row loop is unrolled by the ring depth: inside the unrolled body the ring slot of every window row, the
     // exchange buffer and the register holding each window entry are compile-time constants -- no address
@@ -282,6 +305,29 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
             for (int ee = 0; ee < NE; ee++) {
                 const double2 w01 = cs[3 * (ee + 1)], w23 = cs[3 * (ee + 1) + 1], w45 = cs[3 * (ee + 1) + 2];
                 double ph = fma(w45.y, k7, fma(w45.x, k6w[6], fma(w23.y, k5w[6], fma(w23.x, k4w[6], fma(w01.y, k3w[6], fma(w01.x, k1w[6], yw[6]))))));
+                st_if(a.phi[ee] + (g + phi_shift), ph, ok);
+            }
+        }
+#elif defined(OC_VREGCONST)
+        {
+            const int row = r - 6;
+            const bool ok = col_out && row >= y0 && row < y1;
+            const int g = (row - a.row_base) * a.Nx + gx;
+            double e = fma(hev[5], k7, fma(hev[4], k6w[6], fma(hev[3], k5w[6], fma(hev[2], k4w[6], fma(hev[1], k3w[6], hev[0] * k1w[6])))));
+            double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
+            double qq = e * rcp_pos(sc);
+            acc = ok ? fma(qq, qq, acc) : acc;
+            st_if(a.ynew + g, un[6], ok);
+            st_if(a.k7 + g, k7, ok);
+#pragma unroll
+            for (int ee = 0; ee < NE; ee++) {
+                double ph;
+                if (ee < NV)
+                    ph = fma(wv[ee][5], k7, fma(wv[ee][4], k6w[6], fma(wv[ee][3], k5w[6], fma(wv[ee][2], k4w[6],
+                             fma(wv[ee][1], k3w[6], fma(wv[ee][0], k1w[6], yw[6]))))));
+                else
+                    ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
+                             fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
                 st_if(a.phi[ee] + (g + phi_shift), ph, ok);
             }
         }
