@@ -52,12 +52,15 @@ long long oc_launch_count(int reset);
 int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length, double room_height,
                   const double *X, const double *Y, oc_ctx **out);
 void oc_ctx_destroy(oc_ctx *ctx);
+/* Integer tuning options of a context.  "gcfm_sweep_ctas": upper bound of the GCFM sweep kernel's grid (0 = fill the
+ * GPU, the default); ensembles set it so that the concurrent sweeps of many small crowds share the SMs.  Results do
+ * not depend on it. */
+int oc_ctx_set_int(oc_ctx *ctx, const char *key, int value);
 
 /* Host -> device copy of a caller-owned input array (e.g. the density `m` that
  * optimals.compute_optimal_velocity(t, m) receives as a numpy array, optimals.py:124) onto `stream`.
  * Page-locked `host` memory goes to the copy engine directly and must stay valid until `stream` has passed the
- * copy; pageable memory is staged through the context's pinned buffers (memcpy overlapped with DMA) and has been
- * read completely when the call returns. */
+ * copy; pageable memory is staged by the driver and has been read completely when the call returns. */
 int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream);
 
 /* ------------------------------------------------------------------ room rasteriser (K8)
@@ -142,7 +145,8 @@ int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const *d_V, const
 typedef struct {
     int n_virtual;   /* > 1: virtual bands in one process; otherwise the communicator of oc_dist_init is used */
     int own0, own1;  /* distributed mode: global rows [own0, own1) of this rank (= rank*rows .. (rank+1)*rows) */
-    int reserved;
+    int phi_extra_hi; /* distributed mode: 1 = d_phi slices are (rows+3, Nx): one more halo row above the band (global
+                         row own1+1), as the distributed GCFM sampler needs (oc_key.phi_row0 / phi_rows); 0 = (rows+2, Nx) */
 } oc_band_cfg;
 int oc_dist_unique_id(void *out128);
 int oc_dist_init(oc_ctx *ctx, const void *id128, int rank, int nranks);
@@ -175,6 +179,12 @@ typedef struct {
     double cos_fov, one_minus_cos_fov;
     double dx, dy, room_length, room_height;
     int Ny, Nx;
+    /* Distributed step (one room on several GPUs): the agents are replicated on every rank; a
+     * rank evaluates the field sample and the wall force only for the agents whose sampled node row lies in
+     * [own0, own1) -- its band of the row-decomposed field -- the per-agent terms are merged bit-exactly over the
+     * communicator of oc_dist_init, and every rank then runs the identical sequential sweep (a room's sweep is one
+     * dependency chain).  own0 = own1 = 0: single-GPU step, everything local. */
+    int own0, own1;
 } oc_gcfm_params;
 
 typedef struct {
@@ -193,6 +203,10 @@ typedef struct {
     double mu, lim;
     const double *doors;          /* host (n_doors,4): cx,cy,w,h of the box's targets (pedestrians.py:132-135) */
     int n_doors;
+    /* row-band storage of d_phi (distributed runs): every slice holds node rows [phi_row0, phi_row0 + phi_rows) only,
+     * as oc_hjb_solve_band writes them with phi_extra_hi = 1 (phi_row0 = own0 - 1, phi_rows = rows + 3).
+     * phi_rows = 0: full-grid slices (Ny rows). */
+    int phi_row0, phi_rows;
 } oc_key;
 
 /* Occupancy map used by the exact nearest-wall search (pedestrians.py:311-313): one byte per

@@ -18,16 +18,18 @@ def _window(coords, c, r):
     return max(lo, 0), min(hi, len(coords))
 
 
-def place_box(box, X1, Y1, place_ped, r_in=0.2):
+def place_box(box, X1, Y1, place_ped, r_in=0.2, rng=np.random):
     """Rejection-sample ``int(rho*w*h)`` positions inside ``box`` = [cx, cy, w, h, rho, ...]; returns xs, ys, v_des.
 
-    ``place_ped`` (Ny,Nx) is the occupancy mask shared by all boxes (simulations.py:110) and is updated in place."""
+    ``place_ped`` (Ny,Nx) is the occupancy mask shared by all boxes (simulations.py:110) and is updated in place.
+    ``rng``: the legacy generator to draw from -- the global ``np.random`` module like the reference, or a
+    ``np.random.RandomState(seed)`` (same stream as ``np.random.seed(seed)``) for ensemble members."""
     loc_N = int(box[4] * box[2] * box[3])                                   # simulations.py:122
     xs, ys = np.empty(loc_N), np.empty(loc_N)
     placed = 0
     while placed < loc_N:
-        x_in = np.random.uniform(box[0] - box[2] / 2, box[0] + box[2] / 2, 1)   # :130
-        y_in = np.random.uniform(box[1] - box[3] / 2, box[1] + box[3] / 2, 1)   # :131
+        x_in = rng.uniform(box[0] - box[2] / 2, box[0] + box[2] / 2, 1)   # :130
+        y_in = rng.uniform(box[1] - box[3] / 2, box[1] + box[3] / 2, 1)   # :131
         j0, j1 = _window(X1, x_in[0], r_in)
         i0, i1 = _window(Y1, y_in[0], r_in)
         near = np.sqrt((X1[None, j0:j1] - x_in) ** 2 + (Y1[i0:i1, None] - y_in) ** 2) < r_in
@@ -37,5 +39,5 @@ def place_box(box, X1, Y1, place_ped, r_in=0.2):
         sub[near] = 1                                                           # :135
         xs[placed], ys[placed] = x_in[0], y_in[0]
         placed += 1
-    v_des = np.random.normal(1.34, 0.26, size=loc_N)                           # :140
+    v_des = rng.normal(1.34, 0.26, size=loc_N)                           # :140
     return xs, ys, v_des

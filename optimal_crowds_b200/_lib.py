@@ -59,26 +59,26 @@ class HjbStats(C.Structure):
 
 
 class BandCfg(C.Structure):
-    _fields_ = [("n_virtual", C.c_int), ("own0", C.c_int), ("own1", C.c_int), ("reserved", C.c_int)]
+    _fields_ = [("n_virtual", C.c_int), ("own0", C.c_int), ("own1", C.c_int), ("phi_extra_hi", C.c_int)]
 
 
 class GcfmParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("dt", "dt2", "half_noise", "relaxation", "v_max", "cutoff", "a_min", "tau_a", "b_min", "b_max",
                  "eta", "eta_walls", "cos_fov", "one_minus_cos_fov", "dx", "dy", "room_length", "room_height")] + \
-               [("Ny", C.c_int), ("Nx", C.c_int)]
+               [("Ny", C.c_int), ("Nx", C.c_int), ("own0", C.c_int), ("own1", C.c_int)]
 
 
 class Key(C.Structure):
     _fields_ = [("d_V", C.c_void_p), ("d_wall_tiles", C.c_void_p), ("v_min", C.c_double), ("d_vx", C.c_void_p),
                 ("d_vy", C.c_void_p), ("nt_opt", C.c_int), ("n_slices", C.c_int), ("d_phi", C.c_void_p),
                 ("n_phi", C.c_int), ("pad_", C.c_int), ("mu", C.c_double), ("lim", C.c_double), ("doors", dp),
-                ("n_doors", C.c_int)]
+                ("n_doors", C.c_int), ("phi_row0", C.c_int), ("phi_rows", C.c_int)]
 
 
 _lib = None
 
-EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_rasterise",
+EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_ctx_set_int", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
@@ -100,6 +100,7 @@ def load():
     lib.oc_gcfm_last_ms.restype = C.c_double
     lib.oc_gcfm_last_ms.argtypes = [C.c_void_p]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
+    lib.oc_ctx_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.oc_ctx_destroy.restype = None
     lib.oc_ctx_destroy.argtypes = [C.c_void_p]
     lib.oc_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp,
@@ -188,6 +189,9 @@ class Context:
         self.h = h
         self.torch_device = torch.device("cuda", self.device)
 
+    def set_int(self, key: str, value: int):
+        check(load().oc_ctx_set_int(self.h, key.encode(), int(value)))
+
     def close(self):
         if getattr(self, "h", None):
             load().oc_ctx_destroy(self.h)
@@ -248,8 +252,9 @@ class Context:
         self.rank, self.nranks = int(rank), int(nranks)
 
     def hjb_solve_band(self, V, m, prm: HjbParams, T, nt, n_virtual=0, own=None, want_phi=True, want_vel=False,
-                       trace=False, out_phi=None):
-        """V, m: full-grid tensors (virtual bands) or this rank's band (distributed, after dist_init)."""
+                       trace=False, out_phi=None, phi_extra_hi=0):
+        """V, m: full-grid tensors (virtual bands) or this rank's band (distributed, after dist_init).
+        phi_extra_hi=1: phi slices hold rows+3 rows (one more halo row above the band, for the GCFM sampler)."""
         t_eval = np.linspace(T, 0, nt)
         if n_virtual and n_virtual > 1 or own is None:
             rows, prow, own0, own1 = self.Ny, self.Ny, 0, self.Ny
@@ -257,7 +262,7 @@ class Context:
         else:
             own0, own1 = own
             rows = own1 - own0
-            prow = rows + 2
+            prow = rows + 2 + int(phi_extra_hi)
             vshape = (max(nt - 1, 0), rows, self.Nx - 2)
         phi = out_phi if out_phi is not None else (self.empty(nt, prow, self.Nx) if want_phi else None)
         vx = vy = None
@@ -265,7 +270,7 @@ class Context:
             import torch
             vx = torch.zeros(vshape, dtype=torch.float64, device=self.torch_device)
             vy = torch.zeros(vshape, dtype=torch.float64, device=self.torch_device)
-        cfg = BandCfg(int(n_virtual or 0), int(own0), int(own1), 0)
+        cfg = BandCfg(int(n_virtual or 0), int(own0), int(own1), int(phi_extra_hi))
         st = HjbStats()
         cap = 1 << 16 if trace else 0
         th = np.empty(max(cap, 1)); te = np.empty(max(cap, 1))
@@ -371,7 +376,8 @@ class Context:
                           k["vy"].data_ptr() if k.get("vy") is not None else None, int(k["nt_opt"]),
                           int(k["vx"].shape[0]) if k.get("vx") is not None else 0,
                           phi.data_ptr() if phi is not None else None, int(phi.shape[0]) if phi is not None else 0, 0,
-                          float(k.get("mu", 5.0)), float(k.get("lim", 10e-3)), _hp(doors), len(doors))
+                          float(k.get("mu", 5.0)), float(k.get("lim", 10e-3)), _hp(doors), len(doors),
+                          int(k.get("phi_row0", 0)), int(k.get("phi_rows", 0)))
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 2)
         check(load().oc_gcfm_step_launch(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]),
@@ -430,6 +436,7 @@ def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: 
     p.cos_fov, p.one_minus_cos_fov = c, 1 - c
     p.dx = p.dy = cfg["grid_step"]
     p.room_length, p.room_height, p.Ny, p.Nx = room_length, room_height, Ny, Nx
+    p.own0 = p.own1 = 0   # single-GPU step; a row-decomposed run sets its band here
     return p
 
 

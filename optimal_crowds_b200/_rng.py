@@ -25,7 +25,9 @@ class StepRandomness:
     CKPT_BEFORE_END = (4096, 1024, 256, 64)
     MIN_N = 25000  # below this the draws take less time than the bookkeeping: no look-ahead
 
-    def __init__(self, lookahead: bool = True):
+    def __init__(self, lookahead: bool = True, rng=np.random):
+        # rng: the global ``np.random`` module (reference behaviour) or a ``np.random.RandomState`` of an ensemble member
+        self.rng = rng
         self.enabled = lookahead
         self._spec = None
         self.hits = self.misses = 0
@@ -33,33 +35,33 @@ class StepRandomness:
     def draw(self, N: int, n_active: int):
         """(perm, noise) of the step that starts now; the global generator ends where the reference's would."""
         sp, self._spec = self._spec, None
-        if sp is not None and sp["N"] == N and n_active <= sp["n_spec"] and _same_state(np.random.get_state(), sp["state0"]):
+        if sp is not None and sp["N"] == N and n_active <= sp["n_spec"] and _same_state(self.rng.get_state(), sp["state0"]):
             self.hits += 1
             count, state = max((c for c in sp["ckpt"] if c[0] <= n_active), key=lambda c: c[0])
-            np.random.set_state(state)
+            self.rng.set_state(state)
             if n_active > count:
-                np.random.normal(size=(n_active - count, 2))  # re-draws pairs count..n_active (already in Z)
+                self.rng.normal(size=(n_active - count, 2))  # re-draws pairs count..n_active (already in Z)
             return sp["perm"], sp["Z"][:n_active]
         self.misses += 1
-        perm = np.random.choice(np.arange(N), N, replace=False)
-        noise = np.random.normal(size=(n_active, 2)) if n_active else np.zeros((0, 2))
+        perm = self.rng.choice(np.arange(N), N, replace=False)
+        noise = self.rng.normal(size=(n_active, 2)) if n_active else np.zeros((0, 2))
         return perm, noise
 
     def lookahead(self, N: int, n_upper: int):
         """Pre-draw the next step (call while the GPU is busy).  Leaves the global generator state unchanged."""
         if not self.enabled or N < self.MIN_N:
             return
-        state0 = np.random.get_state()
-        perm = np.random.choice(np.arange(N), N, replace=False)
-        ckpt = [(0, np.random.get_state())]
+        state0 = self.rng.get_state()
+        perm = self.rng.choice(np.arange(N), N, replace=False)
+        ckpt = [(0, self.rng.get_state())]
         parts = []
         done = 0
         for back in self.CKPT_BEFORE_END + (0,):
             stop = n_upper - back
             if stop > done:
-                parts.append(np.random.normal(size=(stop - done, 2)))
+                parts.append(self.rng.normal(size=(stop - done, 2)))
                 done = stop
-                ckpt.append((done, np.random.get_state()))
+                ckpt.append((done, self.rng.get_state()))
         Z = np.concatenate(parts) if parts else np.zeros((0, 2))
-        np.random.set_state(state0)
+        self.rng.set_state(state0)
         self._spec = dict(N=N, n_spec=n_upper, state0=state0, perm=perm, Z=Z, ckpt=ckpt)

@@ -40,6 +40,8 @@ struct oc_ctx {
     double gcfm_last_ms = 0.0;
     void *gcfm_stream = nullptr;
     bool gcfm_pending = false;
+    int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
+    int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
     // batched (ensemble) HJB solve: per-room workspace, streams and events
     double *batch_ws = nullptr;
     size_t batch_ws_bytes = 0;
@@ -47,9 +49,9 @@ struct oc_ctx {
     size_t batch_pinned_n = 0;
     std::vector<cudaStream_t> batch_streams;
     std::vector<cudaEvent_t> batch_events;
-    void *up_stage[2] = {nullptr, nullptr};  // pinned staging buffers of oc_upload (pageable sources)
-    cudaEvent_t up_ev[2] = {nullptr, nullptr};
 };
+
+int oc_dist_allreduce_max_u64(oc_ctx *ctx, void *d_buf, size_t count, cudaStream_t st);  // oc_hjb_dist.cu
 
 namespace oc {
 void set_error(const char *fmt, ...);

@@ -40,6 +40,7 @@ struct KeyDev {
     int nt_opt, n_slices, door_off, n_doors, n_phi;
     double off_min;  // v_min * 10e3
     double mu, lim;
+    int phi_row0, phi_rows;  // node rows held by every phi slice (phi_rows = 0: the whole grid)
 };
 
 struct Ws {  // device workspace carved out of ctx->gcfm_ws
@@ -80,6 +81,16 @@ __device__ __forceinline__ double py_floordiv(double vx, double wx) {
     return copysign(0.0, vx / wx);
 }
 
+// node row whose band "owns" an agent in a row-decomposed run: the first of the (up to) two rows the sampler reads
+// (i0 + 1 in node indexing), clamped into the grid so that every position -- also one the sampler refuses -- has
+// exactly one owner.  The sampler then reads node rows i0 .. i0+3, i.e. owner-1 .. owner+2.
+__device__ __forceinline__ int sampler_owner_row(const oc_gcfm_params &p, double y) {
+    long long i0 = (y < p.room_height - p.dy) ? (long long)py_floordiv(y, p.dy) : (long long)(p.Ny - 3);
+    if (!(y == y)) i0 = 0;
+    i0 = i0 < -1 ? -1 : (i0 > p.Ny - 2 ? p.Ny - 2 : i0);
+    return (int)i0 + 1;
+}
+
 // optimals.py:212-250 -- returns 1 if the reference would raise IndexError / wrap a negative index
 __device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double x, double y, int t, double &ox,
                                double &oy) {
@@ -111,7 +122,10 @@ __device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double 
         // vx_opt[t] = vels(sol.y[:, nt_opt-1-t]) (optimals.py:200-204), evaluated at the two sampled nodes
         const int kd = k.nt_opt - 1 - t;
         if (kd < 0 || kd >= k.n_phi) return 1;
-        const double *ph = k.phi + (size_t)kd * p.Ny * p.Nx;
+        // slices hold the whole grid or (row-decomposed runs) node rows [phi_row0, phi_row0 + phi_rows)
+        const int rows = k.phi_rows ? k.phi_rows : p.Ny, row0 = k.phi_rows ? k.phi_row0 : 0;
+        if (i0 < row0 || i1 + 2 >= row0 + rows) return 1;  // not this band's agent (the caller only asks for its own)
+        const double *ph = k.phi + (size_t)kd * rows * p.Nx - (long long)row0 * p.Nx;
         const double i2x = 1.0 / (2 * p.dx), i2y = 1.0 / (2 * p.dy);
         {
             const double *c = ph + (size_t)(i0 + 1) * p.Nx + (j0 + 1);
@@ -385,6 +399,14 @@ __global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, W
     const int lane = threadIdx.x & 31;
     const KeyDev k = w.keys[key_id[i]];
     double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i];
+    if (p.own1 > p.own0) {
+        // row-decomposed run: another rank owns this agent -- leave all-zero bits for the bit-exact merge
+        const int orow = sampler_owner_row(p, yi);
+        if (orow < p.own0 || orow >= p.own1) {
+            if (lane == 0) { w.des_x[i] = 0.0; w.des_y[i] = 0.0; w.wfx[i] = 0.0; w.wfy[i] = 0.0; }
+            return;
+        }
+    }
     long long ind = wall_argmin_warp(X, Y, k.V, k.tiles, p.Ny, p.Nx, xi, yi, k.off_min);
     if (lane == 0) {
         double ux, uy;
@@ -411,7 +433,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
              uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
-             double inv_cs, int nbx, int nby) {
+             double inv_cs, int nbx, int nby, unsigned poll_ns) {
     __shared__ int s_c[SWEEP_WARPS][CAND_CAP];
     __shared__ int s_j[SWEEP_WARPS][LIST_CAP];
     __shared__ double s_fx[SWEEP_WARPS][LIST_CAP];
@@ -496,7 +518,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                     sj = si;
                 } else if (jr.y < r) {  // earlier in the sweep: needs j's NEW state
                     int f;
-                    while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(20);
+                    while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(poll_ns);
                     alive = (f & 1) != 0;
                     const double2 a = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j));
                     const double2 bb = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j) + 1);
@@ -724,7 +746,7 @@ extern "C" int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, d
     return OC_OK;
 }
 
-static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins, Ws &w, int **pinned) {
+static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins, Ws &w, int **pinned, cudaStream_t st) {
     size_t need = 0;
     auto al = [&](size_t b) { need += ((b + 255) / 256) * 256; };
     for (int q = 0; q < 8; q++) al(sizeof(double) * N);
@@ -745,10 +767,12 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
         ctx->gcfm_ws = nullptr;
         ctx->gcfm_ws_bytes = 0;
         OC_CUDA(cudaMalloc(&ctx->gcfm_ws, need));
-        OC_CUDA(cudaMemset(ctx->gcfm_ws, 0, need));  // done-flags start at 0; tags are never 0
+        // done-flags start at 0; tags are never 0.  On the step's own stream: a legacy-stream cudaMemset is not ordered
+        // against kernels of a non-blocking stream (ensembles step every member on its own stream)
+        OC_CUDA(cudaMemsetAsync(ctx->gcfm_ws, 0, need, st));
         ctx->gcfm_ws_bytes = need;
     } else if (ctx->gcfm_N != N || ctx->gcfm_nbins != nbins || ctx->gcfm_nkeys != n_keys || ctx->gcfm_ndoors != n_doors) {
-        OC_CUDA(cudaMemset(ctx->gcfm_ws, 0, ctx->gcfm_ws_bytes));  // layout changes: done-flags must restart at 0
+        OC_CUDA(cudaMemsetAsync(ctx->gcfm_ws, 0, ctx->gcfm_ws_bytes, st));  // layout changes: done-flags must restart at 0
     }
     ctx->gcfm_N = N; ctx->gcfm_nbins = nbins; ctx->gcfm_nkeys = n_keys; ctx->gcfm_ndoors = n_doors;
     char *p = (char *)ctx->gcfm_ws;
@@ -810,7 +834,7 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     for (int k = 0; k < n_keys; k++) n_doors += keys[k].n_doors;
     Ws w{};
     int *pinned = nullptr;
-    int rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned);
+    int rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned, st);
     if (rc) return rc;
     // upload keys, doors, perm, noise
     std::vector<KeyDev> hk(n_keys);
@@ -822,7 +846,8 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
         hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy,
                        keys[k].d_vx ? nullptr : keys[k].d_phi, keys[k].nt_opt, keys[k].d_vx ? keys[k].n_slices : 0, off,
                        keys[k].n_doors, (keys[k].d_vx || !keys[k].d_phi) ? 0 : keys[k].n_phi, keys[k].v_min * 10e3,
-                       keys[k].mu, keys[k].lim};
+                       keys[k].mu, keys[k].lim, keys[k].phi_row0, keys[k].phi_rows};
+        OC_ARG(keys[k].phi_rows >= 0 && (keys[k].phi_rows == 0 || !keys[k].d_vx), "row-band storage needs phi samples");
         for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
         off += keys[k].n_doors;
     }
@@ -843,13 +868,24 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     scatter_kernel<<<nb, 256, 0, st>>>(N, w);
     noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
     prepare_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(*prm, N, w, ctx->d_X, ctx->d_Y, d_vdes, d_key, simu_step);
+    if (prm->own1 > prm->own0 && ctx->nccl_comm && ctx->nranks > 1) {
+        // merge the per-agent terms over the ranks: des_x, des_y, wfx, wfy are carved back to back (padding is zero),
+        // every agent was written by exactly one rank and is all-zero bits elsewhere; the sampler-range flag likewise
+        const size_t words = (size_t)((w.wfy + N) - w.des_x);
+        if ((rc = oc_dist_allreduce_max_u64(ctx, w.des_x, words, st))) return rc;
+        if ((rc = oc_dist_allreduce_max_u64(ctx, w.counters, 4, st))) return rc;  // 8 ints
+    }
     int n_sm = 0;
     OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     int occ = 0;
     OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, 0));
     int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
+    // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
+    // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
+    // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
+    if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
     sweep_kernel<<<grid, SWEEP_WARPS * 32, 0, st>>>(*prm, N, w, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key,
-                                                    tag, inv_cs, nbx, nby);
+                                                    tag, inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns);
     exit_compact_kernel<<<1, 1024, 0, st>>>(N, w, pinned);
     oc::count_launch(7);
     OC_CUDA(cudaGetLastError());

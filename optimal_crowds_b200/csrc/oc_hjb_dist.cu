@@ -26,7 +26,7 @@ namespace {
 // ---- minimal NCCL binding, resolved at run time from the libnccl torch has already loaded ---------------
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclFloat64 = 8 };
+enum { ncclFloat64 = 8, ncclUint64 = 5, ncclMax = 2 };
 struct Nccl {
     void *h = nullptr;
     int (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -37,6 +37,7 @@ struct Nccl {
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load() {
         if (h) return true;
@@ -47,7 +48,7 @@ struct Nccl {
         if (!h) return false;
 #define SYM(f) *(void **)(&f) = dlsym(h, "nccl" #f); if (!f) return false;
         SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(GroupStart) SYM(GroupEnd) SYM(Send) SYM(Recv)
-        SYM(AllGather) SYM(GetErrorString)
+        SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
 #undef SYM
         return true;
     }
@@ -210,6 +211,15 @@ extern "C" int oc_dist_init(oc_ctx *ctx, const void *id128, int rank, int nranks
     return OC_OK;
 }
 
+// In-place element-wise maximum of `count` 64-bit words over all ranks.  The distributed GCFM step merges per-agent
+// terms that exactly one rank computed (the others hold all-zero bits), so the maximum of the bit patterns is a
+// bit-exact merge -- unlike a floating-point sum, which would turn -0.0 into +0.0.
+int oc_dist_allreduce_max_u64(oc_ctx *ctx, void *d_buf, size_t count, cudaStream_t st) {
+    if (!ctx->nccl_comm || ctx->nranks <= 1) return OC_OK;
+    OC_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclUint64, ncclMax, (ncclComm_t)ctx->nccl_comm, st));
+    return OC_OK;
+}
+
 extern "C" int oc_dist_finalize(oc_ctx *ctx) {
     if (ctx && ctx->nccl_comm) {
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
@@ -252,6 +262,10 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     const int rows_store = band_rows + 2 * HB;
     const size_t n_store = (size_t)rows_store * Nx, n_glob = (size_t)Ny * Nx;
     const bool want_v = d_vx && d_vy, want_out = d_phi || want_v;
+    // phi slices of a distributed band hold one halo row below and 1 + phi_extra_hi rows above the owned rows (the
+    // GCFM sampler of an agent owned by this band reads up to two rows past it, oc_gcfm.cu)
+    const int xhi = dist ? cfg->phi_extra_hi : 0;
+    OC_ARG(xhi == 0 || xhi == 1, "phi_extra_hi must be 0 or 1");
 
     // ---- workspace: per local band 5 arrays + partials (+ phi scratch)
     const size_t per_band = 5 * n_store + (size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64 +
@@ -291,7 +305,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
         b.V = d_V; b.m = d_m;
         b.io_row0 = dist ? b.v.own0 : 0;
         if (dist) {
-            b.phi_row_base = b.v.own0 - 1; b.phi_slice = (size_t)(band_rows + 2) * Nx;
+            b.phi_row_base = b.v.own0 - 1; b.phi_slice = (size_t)(band_rows + 2 + xhi) * Nx;
             b.v_row_base = b.v.own0; b.v_slice = (size_t)band_rows * (Nx - 2);
         } else {
             b.phi_row_base = 0; b.phi_slice = n_glob;
@@ -341,13 +355,13 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
         }
         for (int e = 0; e < phi_ne; e++) {  // slice storage: row 0 = own0-1 (halo), rows 1..band_rows owned, last = halo
             double *p = phi_ptrs[e];
-            if (rank > 0) {
-                OC_NCCL(g_nccl.Send(p + (size_t)1 * Nx, Nx, ncclFloat64, rank - 1, comm, st));
+            if (rank > 0) {  // my first 1 + xhi owned rows are the upper neighbour's high halo
+                OC_NCCL(g_nccl.Send(p + (size_t)1 * Nx, (size_t)(1 + xhi) * Nx, ncclFloat64, rank - 1, comm, st));
                 OC_NCCL(g_nccl.Recv(p, Nx, ncclFloat64, rank - 1, comm, st));
             }
             if (rank + 1 < nranks) {
                 OC_NCCL(g_nccl.Send(p + (size_t)band_rows * Nx, Nx, ncclFloat64, rank + 1, comm, st));
-                OC_NCCL(g_nccl.Recv(p + (size_t)(band_rows + 1) * Nx, Nx, ncclFloat64, rank + 1, comm, st));
+                OC_NCCL(g_nccl.Recv(p + (size_t)(band_rows + 1) * Nx, (size_t)(1 + xhi) * Nx, ncclFloat64, rank + 1, comm, st));
             }
         }
         if (!in_group) OC_NCCL(g_nccl.GroupEnd());
@@ -561,8 +575,14 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                     phis.push_back(d_phi ? d_phi + (size_t)kd * b.phi_slice : b.scratch + (size_t)e * b.phi_slice);
             }
         for (Band &b : bands) { std::swap(b.y, b.ynew); std::swap(b.f, b.fnew); }  // FSAL (rk.py:167-174)
-        // the halo rows of the new y, f travelled with the error sums; only phi rows (velocity output) are left
-        if (dist && !phis.empty() && (rc = exchange({}, (int)phis.size(), phis.data()))) return rc;
+        // the halo rows of the new y, f travelled with the error sums; only the halo rows of the emitted phi slices are
+        // left: needed by the velocity conversion below and, with phi_extra_hi, by the distributed GCFM sampler
+        if (dist && want_v && !phis.empty() && (rc = exchange({}, (int)phis.size(), phis.data()))) return rc;
+        if (dist && !want_v && xhi && d_phi) {
+            std::vector<double *> hp;
+            for (int e = 0; e < n_emit; e++) hp.push_back(d_phi + (size_t)(nt - 1 - (t_eval_i - 1 - e)) * bands[0].phi_slice);
+            if (!hp.empty() && (rc = exchange({}, (int)hp.size(), hp.data()))) return rc;
+        }
         if (want_v) {
             size_t pi = 0;
             for (int e = 0; e < n_emit; e++) {

@@ -1,0 +1,208 @@
+"""Ensembles of independent rooms / seeds (BASELINE.json configs[4]).
+
+With the reference an ensemble is a Python loop -- ``np.random.seed(s); simulations.simulation(room, T).run()`` once
+per member.  Members never interact, so here they are sharded one batch per GPU (member i belongs to rank
+i % world, no data-path collective) and, inside a batch, run concurrently on one GPU:
+
+  * every member is an ordinary ``simulations.simulation`` whose randomness comes from its own
+    ``np.random.RandomState(seed)`` -- the very stream ``np.random.seed(seed)`` gives the reference, so member i
+    reproduces the stand-alone run with that seed bit for bit (tests/test_gpu_ensemble.py);
+  * the HJB fields of all members of a wave are solved by ONE ``oc_hjb_solve_batch`` call: one RK45 controller and
+    one CUDA stream per member, the members' step kernels overlapping on the GPU;
+  * the GCFM steps of the members advance in lock-step: every member's sweep is launched on its own stream
+    (``oc_gcfm_step_launch``) before any is finished (``oc_gcfm_step_finish``), so the host's per-step work (RNG
+    draws, exit bookkeeping) of one member overlaps the other members' kernels;
+  * members are processed in waves sized to the GPU's memory (a 512^2 room with T = 20 s holds 2.1 GB of field
+    samples), and only the per-member results are kept.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+
+import numpy as np
+
+from . import _lib, simulations
+
+
+def shard(n_members: int, rank: int, world: int):
+    """member indices owned by `rank`: round-robin, so that every rank gets members of every cost class"""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside the world")
+    return list(range(rank, n_members, world))
+
+
+def field_bytes_per_member(Ny: int, Nx: int, T: float, dt: float, n_keys: int = 1, field_storage: str = "phi") -> int:
+    """device bytes one member holds: field samples (optimals.py:80-81 sizes them by round(T/dt)) + solver workspace"""
+    nt = round(T / dt)
+    n = Ny * Nx
+    field = nt * n * 8 if field_storage == "phi" else 2 * max(nt - 1, 0) * (Ny - 2) * (Nx - 2) * 8
+    return n_keys * (field + 2 * n * 8) + 6 * n * 8
+
+
+def plan_waves(members, bytes_per_member: int, budget_bytes: int, max_wave: int = 256):
+    """split the member list into waves that fit `budget_bytes` of device memory"""
+    per = max(1, min(max_wave, budget_bytes // max(bytes_per_member, 1)))
+    return [members[i:i + per] for i in range(0, len(members), per)]
+
+
+def gather_results(local: dict, group=None) -> dict:
+    """merge the per-rank {member index: result} dicts on every rank (the only exchange of an ensemble run)"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(local)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, local, group=group)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return dict(sorted(merged.items()))
+
+
+class ensemble:
+    """``ensemble(room, T, seeds)``: one member per seed of the same room; ``ensemble([room0, room1, ...], T, seeds)``:
+    one room per member (all rooms must give the same grid shape).  ``run()`` returns {member index: result} with
+    ``evac_time`` (simulation time when the run stopped), ``steps``, ``inside`` (agents left inside: 0 = evacuation
+    complete), ``exit_order`` (agent ids in exit order), ``exit_step`` (per agent, -1 = still inside),
+    ``times`` (per-agent clocks, as evac_times() returns them), ``final`` (N,4: x, y, vx, vy) and ``hjb`` (solver
+    statistics per target set)."""
+
+    def __init__(self, rooms, T, seeds, recompute=False, field_storage="phi", chunk_rows=0, rank=0, world=1,
+                 memory_budget=None, max_wave=256, record=False, verbose=False):
+        self.T, self.recompute, self.field_storage, self.chunk_rows = T, recompute, field_storage, int(chunk_rows)
+        self.seeds = list(seeds)
+        if isinstance(rooms, (list, tuple)):
+            if len(rooms) != len(self.seeds):
+                raise ValueError("one seed per room expected")
+            self.rooms = list(rooms)
+        else:
+            self.rooms = [rooms] * len(self.seeds)
+        self.rank, self.world = rank, world
+        self.mine = shard(len(self.seeds), rank, world)
+        self.memory_budget, self.max_wave = memory_budget, max_wave
+        self.record, self.verbose = record, verbose
+        self.min_sweep_ctas, self.sweep_ctas = 8, 0   # sweep grid per member: automatic share of the GPU, or fixed
+        self.results = {}
+        self.members = {}          # member index -> simulation (kept only when record=True)
+        self.stats = dict(hjb_ms=0.0, gcfm_ms=0.0, build_ms=0.0, agent_steps=0, cell_updates=0, waves=0, launch_ms=0.0,
+                          finish_ms=0.0)
+
+    # ---------------------------------------------------------------------------------------------
+    def _build(self, idx):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return simulations.simulation(self.rooms[idx], self.T, recompute=self.recompute, record=self.record,
+                                          field_storage=self.field_storage, fused=1, lookahead=False,
+                                          rng=np.random.RandomState(self.seeds[idx]), chunk_rows=self.chunk_rows)
+
+    def _solve_wave(self, sims):
+        """simulation._solve_all for every member of the wave in one batched call per target set"""
+        import torch
+        first = sims[0]
+        d_ms = None
+        if first.simu_step > 0:
+            d_ms = [s._density_device(s.sigma_convolution) for s in sims]
+        cells = 0
+        for k, key in enumerate(first.targets):
+            opts = [list(s.targets.values())[k] for s in sims]
+            nt = round((self.T - first.time) / first.dt)                    # optimals.py:140
+            if nt < 1:
+                raise ValueError("Values in `t_eval` are not within `t_span`.")
+            for o in opts:
+                if nt - 1 > o._n_slices:
+                    raise IndexError("re-solve asks for more slices than the field was allocated for")
+            prm = opts[0]._prm
+            vel = self.field_storage == "velocity"
+            res = first._ctx.hjb_solve_batch([o.d_V for o in opts], d_ms, prm, self.T, nt,
+                                             out_phi=None if vel else [o.d_phi for o in opts],
+                                             out_vx=[o.d_vx for o in opts] if vel else None,
+                                             out_vy=[o.d_vy for o in opts] if vel else None)
+            for o, r, s in zip(opts, res, sims):
+                o.t, o.nt_opt, o.last_stats = s.time, nt, r["stats"]
+                o._h_vx = o._h_vy = None
+                if r["stats"]["status"] == -1:
+                    raise IndexError("RK45 stopped early (required step size is less than spacing between numbers)")
+                cells += r["stats"]["nfev"] * o.Ny * o.Nx
+        torch.cuda.synchronize()
+        return cells
+
+    def _run_wave(self, wave):
+        import time
+        import torch
+        t0 = time.perf_counter()
+        sims = [self._build(i) for i in wave]
+        shape = {(s.Ny, s.Nx, tuple(s.targets)) for s in sims}
+        if len({sh[:2] for sh in shape}) != 1 or len({len(sh[2]) for sh in shape}) != 1:
+            raise ValueError("ensemble members must share the grid shape and the number of target sets")
+        streams = [torch.cuda.Stream() for _ in range(min(len(sims), 128))]
+        # the members' sweeps run concurrently: each gets its share of the GPU's resident-CTA slots
+        n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        ctas = self.sweep_ctas or max(self.min_sweep_ctas, (n_sm * 4) // len(streams))
+        for s in sims:
+            s._ctx.set_int("gcfm_sweep_ctas", ctas)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.stats["cell_updates"] += self._solve_wave(sims)
+        t2 = time.perf_counter()
+        live = list(range(len(sims)))
+        while live:
+            first = sims[live[0]]
+            if self.recompute and first.simu_step % first.recompute_step == 0 and first.simu_step > 0:
+                self.stats["cell_updates"] += self._solve_wave([sims[q] for q in live])
+            launched = []
+            tl0 = time.perf_counter()
+            for q in live:
+                s = sims[q]
+                if self.record:
+                    s.write_history(s.time)
+                self.stats["agent_steps"] += s.inside
+                with torch.cuda.stream(streams[q % len(streams)]):
+                    launched.append(s._step_launch(s.dt))
+            tl1 = time.perf_counter()
+            for q, l in zip(live, launched):
+                sims[q]._step_finish(l)
+            self.stats["launch_ms"] += (tl1 - tl0) * 1e3
+            self.stats["finish_ms"] += (time.perf_counter() - tl1) * 1e3
+            live = [q for q in live if (sims[q].inside > 0) and (sims[q].time < sims[q].T)]   # simulations.py:427
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        for i, s in zip(wave, sims):
+            s._sync_host()
+            self.results[i] = dict(seed=self.seeds[i], evac_time=s.time, steps=s.simu_step, inside=int(s.inside), N=s.N,
+                                   exit_order=np.array(s._exit_order, dtype=np.int64), exit_step=s._exit_step.copy(),
+                                   times=np.array(s._h_timev, dtype=float), final=np.array(s._h_now, dtype=float),
+                                   hjb={k: o.last_stats for k, o in s.targets.items()})
+            if self.record:
+                self.members[i] = s
+        self.stats["build_ms"] += (t1 - t0) * 1e3
+        self.stats["hjb_ms"] += (t2 - t1) * 1e3
+        self.stats["gcfm_ms"] += (t3 - t2) * 1e3
+        self.stats["waves"] += 1
+        if not self.record:
+            for s in sims:
+                for o in s.targets.values():
+                    o.d_phi = o.d_vx = o.d_vy = None
+                s._ctx.close()
+            del sims
+            torch.cuda.empty_cache()
+
+    def run(self, gather=True):
+        """run this rank's members wave by wave; with torch.distributed initialised and gather=True every rank
+        returns the merged results of all ranks"""
+        import torch
+        if not self.mine:
+            return gather_results({}) if gather else {}
+        probe = simulations._load_room(self.rooms[self.mine[0]])
+        cfg = simulations._load_config()
+        Ny, Nx = _lib.grid_shape(probe["room_length"], probe["room_height"], cfg["grid_step"])
+        n_keys = len({' or '.join(b[5:]) for b in probe["initial_boxes"].values()})
+        per = field_bytes_per_member(Ny, Nx, self.T, cfg["dt"], n_keys, self.field_storage)
+        budget = self.memory_budget
+        if budget is None:
+            free, _total = torch.cuda.mem_get_info()
+            budget = int(free * 0.8)
+        for wave in plan_waves(self.mine, per, budget, self.max_wave):
+            self._run_wave(wave)
+            if self.verbose:
+                print(f"[ensemble rank {self.rank}] wave of {len(wave)} members done "
+                      f"({len(self.results)}/{len(self.mine)})", flush=True)
+        return gather_results(self.results) if gather else dict(self.results)

@@ -37,7 +37,9 @@ def _load_room(room):
 
 
 class optimals:
-    def __init__(self, room, V, T, target, _ctx=None, _config=None, field_storage="velocity", fused=1):
+    def __init__(self, room, V, T, target, _ctx=None, _config=None, field_storage="velocity", fused=1, band=None):
+        """``band = (own0, own1)``: this process holds only node rows [own0, own1) of the field (one rank of a
+        row-decomposed run; the context must carry a communicator, dist.init_context)."""
         var_config = _config if _config is not None else _load_config()
         var_room = _load_room(room)
         self.room_length = var_room['room_length']
@@ -58,6 +60,9 @@ class optimals:
         self._prm = _lib.hjb_params(var_config, fused=fused)
         if field_storage not in ("velocity", "phi"):
             raise ValueError("field_storage must be 'velocity' or 'phi'")
+        self.band = tuple(band) if band is not None else None
+        if self.band is not None and field_storage != "phi":
+            raise ValueError("a row-decomposed field is stored as phi samples (field_storage='phi')")
         # 'velocity': (nt-1,Ny-2,Nx-2) x 2 slices exactly like the reference (optimals.py:80-81).
         # 'phi': the (nt,Ny,Nx) value-function samples only (half the memory, no conversion pass); the GCFM
         # sampler differentiates on the fly and vx_opt / vy_opt are produced on demand by the same kernel.
@@ -83,7 +88,9 @@ class optimals:
             self.d_phi = None
         else:
             self.d_vx = self.d_vy = None
-            self.d_phi = torch.empty((n_slices + 1, self.Ny, self.Nx), dtype=torch.float64, device=self.d_V.device)
+            # band: owned rows + one halo row below + two above (the sampler reads owner-1 .. owner+2)
+            rows = self.Ny if self.band is None else self.band[1] - self.band[0] + 3
+            self.d_phi = torch.empty((n_slices + 1, rows, self.Nx), dtype=torch.float64, device=self.d_V.device)
         self._h_vx = self._h_vy = None
         self._d_m = None
         self.phi_T = np.zeros((self.Ny, self.Nx), dtype=float).reshape(self.Nx * self.Ny) + 1  # optimals.py:83,93
@@ -104,6 +111,8 @@ class optimals:
         if self.d_vx is not None:
             self._h_vx, self._h_vy = self.d_vx.cpu().numpy(), self.d_vy.cpu().numpy()
             return
+        if self.band is not None:
+            raise NotImplementedError("vx_opt / vy_opt of a row-decomposed field: every rank holds only its band")
         # phi storage: vx_opt[s] = vels(sol.y[:, nt-1-s]) for s < nt-1 (optimals.py:200-204); later slices were
         # never written by the last solve (np.empty in the reference) and are left as zeros here
         vx = np.zeros((self._n_slices, self.Ny - 2, self.Nx - 2)); vy = np.zeros_like(vx)
@@ -124,8 +133,11 @@ class optimals:
 
     def field_key(self, doors):
         """descriptor of this target set for oc_gcfm_step"""
-        return dict(V=self.d_V, tiles=self.d_tiles, v_min=self.v_min, vx=self.d_vx, vy=self.d_vy, phi=self.d_phi,
-                    mu=self.mu, lim=self.lim, nt_opt=self.nt_opt, doors=doors)
+        key = dict(V=self.d_V, tiles=self.d_tiles, v_min=self.v_min, vx=self.d_vx, vy=self.d_vy, phi=self.d_phi,
+                   mu=self.mu, lim=self.lim, nt_opt=self.nt_opt, doors=doors)
+        if self.band is not None:
+            key.update(phi_row0=self.band[0] - 1, phi_rows=self.band[1] - self.band[0] + 3)
+        return key
 
     def V_host(self):
         return self.V if self.V is not None else self.d_V.cpu().numpy()
@@ -155,7 +167,11 @@ class optimals:
             d_m = m.reshape(self.Ny, self.Nx)
         if nt - 1 > self._n_slices:
             raise IndexError("re-solve asks for more slices than the field was allocated for")  # as numpy would
-        if self.field_storage == "velocity":
+        if self.band is not None:
+            own0, own1 = self.band
+            res = self._ctx.hjb_solve_band(self.d_V[own0:own1], None if d_m is None else d_m[own0:own1].contiguous(),
+                                           self._prm, self.T, nt, own=(own0, own1), out_phi=self.d_phi, phi_extra_hi=1)
+        elif self.field_storage == "velocity":
             res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_phi=False, want_vel=nt > 1,
                                       out_vx=self.d_vx, out_vy=self.d_vy)
         else:

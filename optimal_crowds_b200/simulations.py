@@ -24,10 +24,44 @@ from .optimals import _load_config, _load_room
 warnings.filterwarnings("ignore")  # simulations.py:15
 
 
+class _Frame(list):
+    """One history frame: a list whose LAST element (the density array) is materialised on first access."""
+
+    def __init__(self, agents, density_fn):
+        super().__init__(agents)
+        super().append(None)
+        self._density_fn = density_fn
+
+    def _fill(self):
+        if self._density_fn is not None:
+            fn, self._density_fn = self._density_fn, None
+            list.__setitem__(self, len(self) - 1, fn())
+
+    def __getitem__(self, i):
+        n = len(self)
+        if (len(range(*i.indices(n))[-1:]) and range(*i.indices(n))[-1] == n - 1) if isinstance(i, slice) \
+                else (i == -1 or i == n - 1):
+            self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+
 class simulation:
 
-    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1, lookahead=True):
+    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1, lookahead=True,
+                 rng=None, chunk_rows=0, band=False):
+        """``room, T, recompute`` as in the reference (simulations.py:20).  Extras, all defaulting to reference
+        behaviour: ``record`` (keep per-step host copies for traj/history), ``field_storage`` ('velocity' slices like
+        the reference or 'phi' samples, half the memory), ``rng`` (a ``np.random.RandomState``; default = numpy's
+        legacy global generator, which the reference uses), ``chunk_rows`` (fixes the HJB reduction order),
+        ``band`` (True: this process is one rank of a row-decomposed run under torch.distributed -- it solves and
+        stores only its band of rows of every HJB field, evaluates the field samples and wall forces of the agents
+        in its band, and runs the (replicated, deterministic) sweep; every rank must use the same seed)."""
         import torch
+        self._np_random = rng if rng is not None else np.random
         self.recompute = recompute
         var_config = _load_config()       # simulations.py:42
         var_room = _load_room(room)       # simulations.py:47
@@ -56,8 +90,15 @@ class simulation:
         self.history = {}
         self._record = record
         # host RNG draws of step k+1 overlap the GPU's step k (same stream as the reference, see _rng.py)
-        self._rng = _rng.StepRandomness(lookahead)
+        self._rng = _rng.StepRandomness(lookahead, self._np_random)
         self._gcfm_prm = _lib.gcfm_params(var_config, self.room_length, self.room_height, self.Ny, self.Nx)
+        self._band = None
+        if band:
+            from . import dist as _dist
+            self._band = _dist.init_context(self._ctx)          # (own0, own1) of this rank
+            self._gcfm_prm.own0, self._gcfm_prm.own1 = self._band
+            if field_storage != "phi":
+                raise ValueError("band=True stores the field as phi samples: pass field_storage='phi'")
         diag = float(np.hypot(self.room_length, self.room_height))
         if abs(self.pot) * 10e3 <= diag:
             raise NotImplementedError("wall search assumes |wall_potential|*10e3 exceeds the room diagonal")
@@ -83,9 +124,10 @@ class simulation:
                 V = self.create_potential(var_room, targets)
                 self.Vs[key] = V
                 self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config,
-                                                      field_storage=field_storage, fused=fused)
+                                                      field_storage=field_storage, fused=fused, band=self._band)
+                self.targets[key]._prm.chunk_rows = int(chunk_rows)
             box_count[key] = box_count.get(key, 0) + 1
-            xs, ys, v_des_all = _crowd.place_box(box, X1, Y1, self.place_ped, r_in)
+            xs, ys, v_des_all = _crowd.place_box(box, X1, Y1, self.place_ped, r_in, self._np_random)
             loc_N = len(xs)
             N += loc_N
             kid = list(self.targets).index(key)
@@ -177,10 +219,17 @@ class simulation:
     # ---- simulations.py:252-342 ----------------------------------------------------------------------
     def step(self, dt, verbose=False):
         """One GCFM step for every agent still inside, with the reference's sequential sweep semantics."""
+        self._step_finish(self._step_launch(dt), verbose)
+
+    def _step_launch(self, dt):
+        """first half of step(): draw this step's randomness and enqueue the sweep on the current CUDA stream
+        (ensembles launch every member before finishing any, so the members' kernels overlap)"""
         if dt != self.dt:
             prm = _lib.gcfm_params(dict(self._config, dt=dt), self.room_length, self.room_height, self.Ny, self.Nx)
+            prm.own0, prm.own1 = self._gcfm_prm.own0, self._gcfm_prm.own1
         else:
             prm = self._gcfm_prm
+        pending = None
         if self.N > 0:
             n_active = int(self._h_status.sum())
             # np.random.choice(np.arange(N), N, replace=False) (simulations.py:271) and one normal pair per active
@@ -189,6 +238,11 @@ class simulation:
             pending = self._ctx.gcfm_step_launch(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm,
                                                  noise, self.simu_step)
             self._rng.lookahead(self.N, n_active)   # next step's draws while the GPU sweeps
+        return dt, pending
+
+    def _step_finish(self, launched, verbose=False):
+        dt, pending = launched
+        if pending is not None:
             exits, rc = self._ctx.gcfm_step_finish(pending)
             if rc == _lib.OC_ERR_SAMPLER_RANGE:
                 raise IndexError("agent position outside the velocity field's index range "
@@ -271,14 +325,28 @@ class simulation:
 
     # ---- simulations.py:579-589 ----------------------------------------------------------------------
     def write_history(self, time):
+        """history[time] = [[pos, vel, target, v_des] per agent inside, ..., density] (simulations.py:579-589).
+        The reference splats the density (O(N Nx Ny) exps) on every step although only draw_history('density')
+        reads it; here the last element is computed on first access, from the positions stored in the frame."""
         frame = []
         now = self._h_now
         keys = list(self.targets)
-        for i in np.nonzero(self._h_status)[0]:
+        act = np.nonzero(self._h_status)[0]
+        for i in act:
             frame.append([np.array(now[i, :2], dtype=float), np.array(now[i, 2:], dtype=float),
                           keys[self._h_key[i]], self._h_vdes[i]])
-        frame.append(self.gaussian_density(self.sigma_convolution))
-        self.history[time] = frame
+        xy = np.array(now[act, :2], dtype=np.float64)
+        self.history[time] = _Frame(frame, lambda xy=xy: self._density_of(xy, self.sigma_convolution))
+
+    def _density_of(self, xy, sigma):
+        """density of the crowd at positions xy (n,2), all inside: same kernel, same summation order (agents inside,
+        in index order) as gaussian_density at the time the positions were recorded"""
+        import torch
+        n = len(xy)
+        x = self._ctx.to_device(np.ascontiguousarray(xy[:, 0])) if n else None
+        y = self._ctx.to_device(np.ascontiguousarray(xy[:, 1])) if n else None
+        st = torch.ones(n, dtype=torch.uint8, device=self._ctx.torch_device) if n else None
+        return self._ctx.density(x, y, st, sigma, self._d_Vglobal).cpu().numpy()
 
     # ---- plotting (visualisation only; needs matplotlib / seaborn) ---------------------------------------
     def _ellipse_axes(self, vel, v_des):

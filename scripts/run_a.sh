@@ -1,3 +1,4 @@
-for v in vw3 vw3e vw2; do OC_B200_LIB=$PWD/optimal_crowds_b200/variants/liboc_$v.so python scripts/perf_fused.py 2>&1 | tail -1; done
-python scripts/perf_fused.py 2>&1 | tail -1
-OC_B200_LIB=$PWD/optimal_crowds_b200/variants/liboc_vw3.so python -m pytest tests/test_gpu_hjb.py -m gpu -q -x 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/dist_gcfm_check.py > gpurun_out/dist_gcfm.log 2>&1
+grep -n "DIST_GCFM\|rank 0\|rank 1\|Error" gpurun_out/dist_gcfm.log | head -30
+OC_RECOMPUTE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/dist_gcfm_check.py > gpurun_out/dist_gcfm_rc.log 2>&1
+grep -n "DIST_GCFM\|rank 0\|rank 1\|Error" gpurun_out/dist_gcfm_rc.log | head -30

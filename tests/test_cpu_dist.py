@@ -96,3 +96,49 @@ def test_band_partition_rules():
         ocd.band_rows(100, 3)
     with pytest.raises(ValueError):
         ocd.band_rows(120, 4)   # 30 rows: not a multiple of 16
+
+
+def _ens_worker(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from optimal_crowds_b200 import ensemble
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        mine = ensemble.shard(7, rank, world)
+        local = {i: dict(seed=100 + i, evac_time=float(i) * 0.5, exit_order=np.arange(i)) for i in mine}
+        merged = ensemble.gather_results(local)
+        assert list(merged) == list(range(7))
+        assert all(merged[i]["seed"] == 100 + i and len(merged[i]["exit_order"]) == i for i in merged)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ensemble_shard_and_gather_gloo():
+    """ensembles shard by member (no data-path collective); the only exchange is the final gather of results"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ens_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_ensemble_planning():
+    from optimal_crowds_b200 import ensemble
+    assert ensemble.shard(10, 1, 4) == [1, 5, 9]
+    assert ensemble.shard(3, 3, 4) == []
+    with pytest.raises(ValueError):
+        ensemble.shard(3, 4, 4)
+    per = ensemble.field_bytes_per_member(512, 512, 20.0, 0.02)
+    assert 2.0e9 < per < 2.3e9                       # 1000 phi samples of a 512^2 room
+    waves = ensemble.plan_waves(list(range(128)), per, int(140e9))
+    assert sum(len(w) for w in waves) == 128 and max(len(w) for w in waves) <= 140e9 // per
+    assert ensemble.plan_waves([1, 2, 3], per, 10) == [[1], [2], [3]]     # never less than one member per wave

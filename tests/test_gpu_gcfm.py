@@ -302,3 +302,46 @@ def test_step_with_nobody_inside_and_single_agent(cfg):
             assert np.array_equal(dev[k].cpu().numpy(), st[k])
         left = left or len(ex) == 1
     ctx.close()
+
+
+def test_row_band_field_storage_and_ownership_change_no_bit(cfg):
+    """distributed-step building blocks on one GPU: (a) phi slices stored as a row band (phi_row0 / phi_rows, here
+    one band that covers the grid plus the halo rows) sample exactly like full-grid slices; (b) with an ownership
+    range the agents outside it get all-zero terms, the owned ones the same bits as the single-GPU step, so the
+    bit-wise maximum over bands (what oc_gcfm_step does over NCCL) reassembles the single-GPU step."""
+    import torch
+    from optimal_crowds_b200 import _lib
+    L, H, N, steps = 12.0, 9.0, 120, 6
+    rng = np.random.RandomState(3)
+    ctx = _lib.Context(L, H, 0.05)
+    Ny, Nx = ctx.Ny, ctx.Nx
+    prm = _lib.gcfm_params(cfg, L, H, Ny, Nx)
+    from oracle import cpu_oracle as co
+    doors = np.array([[L, H / 2, 0.6, 2.0]])
+    V = co.create_potential(ctx.X, ctx.Y, [[L / 3, H / 2, 0.4, H / 2]], [], [[2 * L / 3, H / 3, 0.5]], doors)
+    V[V < 0] = -100; V[V > 0] = 1
+    Vd = ctx.to_device(V)
+    tiles, vmin = ctx.wall_tiles(Vd)
+    nt = steps + 3
+    phi = ctx.hjb_solve(Vd, None, _lib.hjb_params(cfg, fused=1), nt * 0.02, nt, want_phi=True, want_vel=False)["phi"]
+    band = torch.zeros((nt, Ny + 3, Nx), dtype=torch.float64, device=phi.device)
+    band[:, 1:Ny + 1] = phi
+    full_key = dict(V=Vd, tiles=tiles, v_min=vmin, phi=phi, nt_opt=nt, doors=doors)
+    band_key = dict(full_key, phi=band, phi_row0=-1, phi_rows=Ny + 3)
+    pos = _random_crowd(rng, N, L, H)
+    st0 = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=rng.normal(0, 0.5, N), vy=rng.normal(0, 0.5, N),
+               time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    vd, kid = ctx.to_device(rng.normal(1.34, 0.26, N)), ctx.to_device(np.zeros(N, dtype=np.int32))
+    a = {k: ctx.to_device(v) for k, v in st0.items()}
+    b = {k: ctx.to_device(v) for k, v in st0.items()}
+    prm_own = _lib.gcfm_params(cfg, L, H, Ny, Nx)
+    prm_own.own0, prm_own.own1 = 0, Ny          # owns every row: no communicator needed
+    for s in range(steps):
+        perm = rng.permutation(N)
+        noise = rng.normal(size=(int(a["status"].cpu().sum()), 2))
+        ex_a, rc_a = ctx.gcfm_step(prm, a, vd, kid, [full_key], perm, noise, s)
+        ex_b, rc_b = ctx.gcfm_step(prm_own, b, vd, kid, [band_key], perm, noise, s)
+        assert rc_a == 0 and rc_b == 0 and np.array_equal(ex_a, ex_b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"{k} differs at step {s}"
+    ctx.close()

@@ -164,3 +164,24 @@ def test_stagewise_and_fused_shim_agree(in_repo_cwd):
     b, _ = _run("room_test", 3.0, False, 1, fused=1)
     for ta, tb in zip(a._track[:60], b._track[:60]):
         assert np.abs(ta - tb).max() < 1e-8
+
+
+def test_history_density_is_lazy_and_equal_to_the_eager_splat(in_repo_cwd):
+    """write_history (simulations.py:579-589) stores the density lazily: the array materialised later from the
+    frame's positions equals gaussian_density() evaluated at recording time, bit for bit."""
+    from optimal_crowds_b200 import simulations
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        simu = simulations.simulation("room_test", 1.0)
+        simu._solve_all()
+        eager = []
+        for _ in range(6):
+            simu.write_history(simu.time)
+            eager.append(simu.gaussian_density(simu.sigma_convolution))
+            simu.step(simu.dt)
+    for (t, frame), d in zip(simu.history.items(), eager):
+        assert list.__getitem__(frame, len(frame) - 1) is None      # nothing computed yet
+        assert len(frame) == simu.N + 1
+        pos, vel, target, v_des = frame[0]
+        assert pos.shape == (2,) and target == "door_1"
+        assert np.array_equal(frame[-1], d) and frame[-1].shape == (simu.Ny, simu.Nx)
