@@ -29,8 +29,9 @@ namespace {
 constexpr int WT = OC_WALL_TILE;
 constexpr double DISP_MARGIN = 1.0;  // max displacement per step assumed by the candidate search (checked)
 constexpr int SWEEP_WARPS = 4;       // warps per block in the sweep
-constexpr int LIST_CAP = 384;        // interacting neighbours per agent held in shared memory
-constexpr int CAND_CAP = 768;        // candidates (agents within cutoff + margin of the old position)
+constexpr int CAND_CAP = 512;        // candidates (agents within cutoff + margin of the old position) per agent
+constexpr int LIST_CAP = CAND_CAP;
+constexpr size_t SWEEP_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * (2 * sizeof(double) + 4 * sizeof(int));  // 64 KB
 
 struct KeyDev {
     const double *V;
@@ -422,25 +423,51 @@ __global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, W
     }
 }
 
+// ascending bitonic sort of a[0..n) (64-bit keys, n <= m2 = power of two, a[n..m2) is overwritten with padding) by one warp
+__device__ __forceinline__ void warp_sort_u64(unsigned long long *a, int n, int lane) {
+    int m2 = 1;
+    while (m2 < n) m2 <<= 1;
+    for (int t = n + lane; t < m2; t += 32) a[t] = ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= m2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = lane; t < m2; t += 32) {
+                const int u = t ^ jj;
+                if (u > t) {
+                    const unsigned long long x = a[t], y = a[u];
+                    if ((x > y) == ((t & k) == 0)) { a[t] = y; a[u] = x; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
 // K6: the sweep (simulations.py:271-332).  Per agent (one warp):
 //  A. gather the candidates -- agents whose OLD position is within cutoff + margin of i's old position -- from the
 //     cell list into shared memory (no waiting: only the immutable snapshot is read);
-//  B. 32 candidates at a time: a candidate EARLIER in the sweep must have finished (acquire on its done-flag,
-//     which also carries its inside/exited status), then its NEW packed state is read; a LATER one is still in
-//     its snapshot state.  Cutoff test and pair force (simulations.py:291-295);
-//  C. sort the interacting neighbours by agent index, add the forces left to right, advance the agent, publish.
+//  B. two sorts, still without waiting: the PROCESSING order (candidates later in the sweep first -- they are in
+//     their snapshot state -- then the earlier ones by ascending sweep rank, i.e. roughly in the order in which they
+//     will publish) and the SUMMATION order (ascending agent index, `for j in range(N)`, simulations.py:287);
+//  C. forces, 32 candidates at a time in processing order: an earlier candidate must have finished (acquire on its
+//     done-flag, which also carries its inside/exited status), then its NEW packed state is read.  Cutoff test and
+//     pair force (simulations.py:291-295) go to the candidate's slot, +0.0 if it does not interact (adding +0.0 to
+//     the running sum changes no bit: the sum starts at +0.0 and can never become -0.0);
+//  D. ascending-j sum, Euler step, exit test, publish.
+// The sweep is a chain of dependencies (an agent needs the new state of every earlier neighbour), so what matters is
+// the time from "my last dependency published" to "I publish": with this ordering it is ONE batch of pair forces plus
+// the sum, instead of all remaining batches plus the sort.
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
              uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
              double inv_cs, int nbx, int nby, unsigned poll_ns) {
-    __shared__ int s_c[SWEEP_WARPS][CAND_CAP];
-    __shared__ int s_j[SWEEP_WARPS][LIST_CAP];
-    __shared__ double s_fx[SWEEP_WARPS][LIST_CAP];
-    __shared__ double s_fy[SWEEP_WARPS][LIST_CAP];
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int *lc = s_c[wid], *lj = s_j[wid];
-    double *lfx = s_fx[wid], *lfy = s_fy[wid];
+    // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj, proc, ord (ints)
+    unsigned char *base = sweep_smem + (size_t)wid * CAND_CAP * (2 * sizeof(double) + 4 * sizeof(int));
+    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + CAND_CAP;
+    int *ckk = reinterpret_cast<int *>(lfy + CAND_CAP), *cj = ckk + CAND_CAP, *proc = cj + CAND_CAP, *ord = proc + CAND_CAP;
+    unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(lfx), *sort_b = reinterpret_cast<unsigned long long *>(lfy);
     const double reach = p.cutoff + DISP_MARGIN;
     const double reach2 = reach * reach;
     const int span = (int)ceil(reach * inv_cs);
@@ -457,7 +484,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
         // ---- A. candidates.  Each of the (2 span + 1) bin rows is one contiguous range of the cell list; lanes fetch the
         // range bounds in parallel, then the concatenated ranges are scanned 32 entries at a time.
-        int nc = 0;
+        int nc = 0, n_later = 0;
         const int b = w.agent_bin[i];
         const int bix = b % nbx, biy = b / nbx;
         const int by0 = max(biy - span, 0), nrows = min(biy + span, nby - 1) - by0 + 1;
@@ -475,8 +502,8 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         }
         const int total = __shfl_sync(0xffffffffu, my_off, 7);  // nrows <= 7
         my_off -= my_len;                                        // exclusive
-        for (int base = 0; base < total; base += 32) {
-            const int t = base + lane;
+        for (int base_t = 0; base_t < total; base_t += 32) {
+            const int t = base_t + lane;
             int kk = -1;
             for (int q = 0; q < nrows; q++) {
                 const int o = __shfl_sync(0xffffffffu, my_off, q), l = __shfl_sync(0xffffffffu, my_len, q),
@@ -484,39 +511,64 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 if (t >= o && t < o + l) kk = bq + (t - o);
             }
             bool keep = false;
+            int2 jr = make_int2(-1, 0);
             if (kk >= 0) {
                 const double2 pj = *reinterpret_cast<const double2 *>(w.cell_state + kk);  // (x, y)
                 const double ox = pj.x - xi, oy = pj.y - yi;
-                keep = (ox * ox + oy * oy < reach2);  // the agent itself is dropped in phase B (id test)
+                if (ox * ox + oy * oy < reach2) {
+                    jr = w.cell_jr[kk];
+                    keep = jr.x != i;  // j != i (simulations.py:291)
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const bool later = jr.y > r;
             if (keep) {
                 const int pos = nc + __popc(m & lt_mask);
-                if (pos < CAND_CAP) lc[pos] = kk;
+                if (pos < CAND_CAP) {
+                    ckk[pos] = kk;
+                    cj[pos] = jr.x;
+                    // processing key: later candidates first (key 0), earlier ones by ascending sweep rank
+                    sort_a[pos] = ((unsigned long long)(later ? 0u : (unsigned)jr.y + 1u) << 32) | (unsigned)pos;
+                    sort_b[pos] = ((unsigned long long)(unsigned)jr.x << 32) | (unsigned)pos;  // summation key: agent index
+                }
             }
             nc += __popc(m);
         }
-        if (nc > CAND_CAP) {
+        if (nc > CAND_CAP) {  // uniform across the warp
             if (lane == 0) atomicOr(&w.counters[1], 2);
+            // too many neighbours for the shared-memory lists: the step is refused (flag), the agent still advances
+            // with the first CAND_CAP candidates so that later agents do not wait forever
             nc = CAND_CAP;
         }
         __syncwarp();
-        // ---- B. forces
-        int cnt = 0;
-        for (int base = 0; base < nc; base += 32) {
-            const int c = base + lane;
-            bool hit = false;
+        // ---- B. processing order and summation order (no waiting yet)
+        if (nc > 1) {
+            warp_sort_u64(sort_a, nc, lane);
+            warp_sort_u64(sort_b, nc, lane);
+        }
+        for (int t0 = 0; t0 < nc; t0 += 32) {
+            const int t = t0 + lane;
+            bool is_later = false;
+            if (t < nc) {
+                const unsigned long long ka = sort_a[t];
+                proc[t] = (int)(unsigned)ka;
+                ord[t] = (int)(unsigned)sort_b[t];
+                is_later = (ka >> 32) == 0;  // key 0 <=> later in the sweep: no waiting
+            }
+            n_later += __popc(__ballot_sync(0xffffffffu, is_later));
+        }
+        __syncwarp();
+        // ---- C. forces in processing order
+        for (int base_c = 0; base_c < nc; base_c += 32) {
+            const int c = base_c + lane;
             double fx = 0.0, fy = 0.0;
-            int j = -1;
+            int slot = -1;
             if (c < nc) {
-                const int kk = lc[c];
-                const int2 jr = w.cell_jr[kk];
-                j = jr.x;
+                slot = proc[c];
+                const int kk = ckk[slot], j = cj[slot];
                 double4 sj;
-                bool alive = j != i;
-                if (!alive) {
-                    sj = si;
-                } else if (jr.y < r) {  // earlier in the sweep: needs j's NEW state
+                bool alive = true;
+                if (c >= n_later) {  // earlier in the sweep: needs j's NEW state
                     int f;
                     while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(poll_ns);
                     alive = (f & 1) != 0;
@@ -528,48 +580,20 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 }
                 if (alive) {
                     const double ddx = sj.x - xi, ddy = sj.y - yi;
-                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
+                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff)  // pedestrians.py:354, simulations.py:291
                         pair_force(p, ei, xi, yi, vxi, vyi, vd, sj.x, sj.y, sj.z, sj.w, fx, fy);
-                        hit = true;
-                    }
+                    else { fx = 0.0; fy = 0.0; }
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int pos = cnt + __popc(m & lt_mask);
-                if (pos < LIST_CAP) { lj[pos] = j; lfx[pos] = fx; lfy[pos] = fy; }
-            }
-            cnt += __popc(m);
+            __syncwarp();
+            if (slot >= 0) { lfx[slot] = fx; lfy[slot] = fy; }  // the sort buffers are dead: proc/ord were extracted
         }
-        if (cnt > LIST_CAP) {
-            if (lane == 0) atomicOr(&w.counters[1], 2);
-            cnt = LIST_CAP;
-        }
-        // ---- C. sort by agent index (bitonic, in shared memory), ascending-j sum (simulations.py:285-295)
-        int m2 = 1;
-        while (m2 < cnt) m2 <<= 1;
-        for (int t = cnt + lane; t < m2; t += 32) lj[t] = 0x7fffffff;
         __syncwarp();
-        for (int k = 2; k <= m2; k <<= 1)
-            for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                for (int t = lane; t < m2; t += 32) {
-                    const int u = t ^ jj;
-                    if (u > t) {
-                        const bool up = ((t & k) == 0);
-                        const int a = lj[t], bb = lj[u];
-                        if ((a > bb) == up) {
-                            lj[t] = bb; lj[u] = a;
-                            double q = lfx[t]; lfx[t] = lfx[u]; lfx[u] = q;
-                            q = lfy[t]; lfy[t] = lfy[u]; lfy[u] = q;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+        // ---- D. ascending-j sum (simulations.py:285-295)
         double acc = 0.0;
         if (lane < 2) {  // lane 0 -> x component, lane 1 -> y component
             const double *src = lane == 0 ? lfx : lfy;
-            for (int t = 0; t < cnt; t++) acc = acc + src[t];
+            for (int t = 0; t < nc; t++) acc = acc + src[ord[t]];
         }
         const double rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1);
         if (lane == 0) {
@@ -878,13 +902,18 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     int n_sm = 0;
     OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     int occ = 0;
-    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, 0));
+    static bool sweep_attr = false;
+    if (!sweep_attr) {
+        OC_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+        sweep_attr = true;
+    }
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, SWEEP_SMEM));
     int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
     // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
     // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
     // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
     if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
-    sweep_kernel<<<grid, SWEEP_WARPS * 32, 0, st>>>(*prm, N, w, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key,
+    sweep_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_SMEM, st>>>(*prm, N, w, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key,
                                                     tag, inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns);
     exit_compact_kernel<<<1, 1024, 0, st>>>(N, w, pinned);
     oc::count_launch(7);
