@@ -31,7 +31,9 @@ constexpr double DISP_MARGIN = 1.0;  // max displacement per step assumed by the
 constexpr int SWEEP_WARPS = 4;       // warps per block in the sweep
 constexpr int CAND_CAP = 512;        // candidates (agents within cutoff + margin of the old position) per agent
 constexpr int LIST_CAP = CAND_CAP;
-constexpr size_t SWEEP_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * (2 * sizeof(double) + 4 * sizeof(int));  // 64 KB
+constexpr size_t SWEEP_SLOT_BYTES = 2 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned short);  // 28 B
+constexpr size_t SWEEP_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * SWEEP_SLOT_BYTES;  // 56 KB: 4 CTAs (16 warps) per SM
+static_assert(CAND_CAP <= 65536, "slot indices are stored as 16-bit");
 
 struct KeyDev {
     const double *V;
@@ -463,10 +465,12 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
              double inv_cs, int nbx, int nby, unsigned poll_ns) {
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj, proc, ord (ints)
-    unsigned char *base = sweep_smem + (size_t)wid * CAND_CAP * (2 * sizeof(double) + 4 * sizeof(int));
+    // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj (ints), proc, ord
+    // (16-bit slot indices)
+    unsigned char *base = sweep_smem + (size_t)wid * CAND_CAP * SWEEP_SLOT_BYTES;
     double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + CAND_CAP;
-    int *ckk = reinterpret_cast<int *>(lfy + CAND_CAP), *cj = ckk + CAND_CAP, *proc = cj + CAND_CAP, *ord = proc + CAND_CAP;
+    int *ckk = reinterpret_cast<int *>(lfy + CAND_CAP), *cj = ckk + CAND_CAP;
+    unsigned short *proc = reinterpret_cast<unsigned short *>(cj + CAND_CAP), *ord = proc + CAND_CAP;
     unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(lfx), *sort_b = reinterpret_cast<unsigned long long *>(lfy);
     const double reach = p.cutoff + DISP_MARGIN;
     const double reach2 = reach * reach;
@@ -541,6 +545,19 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             nc = CAND_CAP;
         }
         __syncwarp();
+        // everything the final Euler step needs that does not depend on the neighbours is fetched now, so that no global
+        // load sits between "last dependency published" and "I publish"
+        double nz_x = 0.0, nz_y = 0.0, wf_x = 0.0, wf_y = 0.0, de_x = 0.0, de_y = 0.0, tim_i = 0.0;
+        int door_off = 0, n_doors = 0;
+        if (lane == 0) {
+            const int nz = w.nzidx[i];
+            nz_x = w.noise[2 * nz]; nz_y = w.noise[2 * nz + 1];
+            wf_x = w.wfx[i]; wf_y = w.wfy[i];
+            de_x = w.des_x[i]; de_y = w.des_y[i];
+            tim_i = tim[i];
+            const KeyDev *kp = w.keys + key_id[i];
+            door_off = kp->door_off; n_doors = kp->n_doors;
+        }
         // ---- B. processing order and summation order (no waiting yet)
         if (nc > 1) {
             warp_sort_u64(sort_a, nc, lane);
@@ -551,8 +568,8 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             bool is_later = false;
             if (t < nc) {
                 const unsigned long long ka = sort_a[t];
-                proc[t] = (int)(unsigned)ka;
-                ord[t] = (int)(unsigned)sort_b[t];
+                proc[t] = (unsigned short)ka;
+                ord[t] = (unsigned short)sort_b[t];
                 is_later = (ka >> 32) == 0;  // key 0 <=> later in the sweep: no waiting
             }
             n_later += __popc(__ballot_sync(0xffffffffu, is_later));
@@ -597,10 +614,9 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         }
         const double rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1);
         if (lane == 0) {
-            const int nz = w.nzidx[i];
-            double cx = vxi + p.half_noise * w.noise[2 * nz] + rx + w.wfx[i];  // simulations.py:303
-            double cy = vyi + p.half_noise * w.noise[2 * nz + 1] + ry + w.wfy[i];
-            double ax = (w.des_x[i] - cx) / p.relaxation, ay = (w.des_y[i] - cy) / p.relaxation;  // :307-308
+            double cx = vxi + p.half_noise * nz_x + rx + wf_x;  // simulations.py:303
+            double cy = vyi + p.half_noise * nz_y + ry + wf_y;
+            double ax = (de_x - cx) / p.relaxation, ay = (de_y - cy) / p.relaxation;  // :307-308
             double nx_ = xi + cx * p.dt + 0.5 * ax * p.dt2;  // :314-315
             double ny_ = yi + cy * p.dt + 0.5 * ay * p.dt2;
             double nvx = cx + ax * p.dt, nvy = cy + ay * p.dt;  // :316-317
@@ -612,15 +628,14 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             }
             if (!(fabs(nx_ - xi) <= DISP_MARGIN * 0.5) || !(fabs(ny_ - yi) <= DISP_MARGIN * 0.5))
                 atomicOr(&w.counters[1], 4);
-            const KeyDev k = w.keys[key_id[i]];
             bool out = false;
-            for (int d = 0; d < k.n_doors; d++) {  // pedestrians.py:132-136
-                const double *door = w.doors + 4 * (k.door_off + d);
+            for (int d = 0; d < n_doors; d++) {  // pedestrians.py:132-136
+                const double *door = w.doors + 4 * (door_off + d);
                 if (fabs(nx_ - door[0]) < door[2] * 0.5 && fabs(ny_ - door[1]) < door[3] * 0.5) out = true;
             }
             w.live4[i] = make_double4(nx_, ny_, nvx, nvy);
             x[i] = nx_; y[i] = ny_; vx[i] = nvx; vy[i] = nvy;
-            tim[i] = tim[i] + p.dt;  // pedestrians.py:191
+            tim[i] = tim_i + p.dt;  // pedestrians.py:191
             if (out) {
                 status[i] = 0;
                 w.exit_mark[r] = i + 1;  // simulations.py:331-332, ordered by sweep position
