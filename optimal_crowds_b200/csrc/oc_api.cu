@@ -86,6 +86,8 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->gcfm_ws);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
+    cudaFree(c->fr_ticket);
+    if (c->fr_result) cudaFreeHost(c->fr_result);
     cudaFree(c->batch_ws);
     if (c->batch_pinned) cudaFreeHost(c->batch_pinned);
     for (auto s : c->batch_streams) cudaStreamDestroy(s);

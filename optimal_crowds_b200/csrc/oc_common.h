@@ -42,6 +42,12 @@ struct oc_ctx {
     bool gcfm_pending = false;
     int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
     int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
+    // in-kernel final reduction of the fused step (oc_hjb_fused.cuh): ticket counters on the device, results in
+    // mapped page-locked host memory (slot b: value at [2b], sequence number at [2b+1])
+    unsigned *fr_ticket = nullptr;
+    double *fr_result = nullptr;
+    int fr_slots = 0;
+    unsigned long long fr_seq = 0;
     // batched (ensemble) HJB solve: per-room workspace, streams and events
     double *batch_ws = nullptr;
     size_t batch_ws_bytes = 0;

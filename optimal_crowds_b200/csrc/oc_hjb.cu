@@ -415,6 +415,52 @@ int ensure_ws(oc_ctx *ctx, size_t n, int nbx, int nby) {
     return OC_OK;
 }
 
+// in-kernel final reduction of the fused step: device ticket counters + mapped host result slots
+int ensure_final_reduce(oc_ctx *ctx, int slots) {
+    if (ctx->fr_slots >= slots) return OC_OK;
+    if (ctx->fr_ticket) cudaFree(ctx->fr_ticket);
+    if (ctx->fr_result) cudaFreeHost(ctx->fr_result);
+    ctx->fr_ticket = nullptr; ctx->fr_result = nullptr; ctx->fr_slots = 0;
+    OC_CUDA(cudaMalloc(&ctx->fr_ticket, sizeof(unsigned) * slots));
+    OC_CUDA(cudaMemset(ctx->fr_ticket, 0, sizeof(unsigned) * slots));
+    OC_CUDA(cudaHostAlloc(&ctx->fr_result, sizeof(double) * 2 * slots, cudaHostAllocMapped));
+    memset(ctx->fr_result, 0, sizeof(double) * 2 * slots);
+    OC_CUDA(cudaDeviceSynchronize());
+    ctx->fr_slots = slots;
+    return OC_OK;
+}
+void final_reduce_args(oc_ctx *ctx, int slot, fused::Args &fa) {
+    double *dev = nullptr;
+    cudaHostGetDevicePointer(&dev, ctx->fr_result, 0);
+    fa.ticket = ctx->fr_ticket + slot;
+    fa.result = dev + 2 * slot;
+    fa.result_seq = reinterpret_cast<unsigned long long *>(dev + 2 * slot + 1);
+    fa.seq = ++ctx->fr_seq;
+}
+inline bool final_ready(oc_ctx *ctx, int slot, unsigned long long seq, double *out) {
+    const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(ctx->fr_result + 2 * slot + 1);
+    if (*f != seq) return false;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *out = *reinterpret_cast<const volatile double *>(ctx->fr_result + 2 * slot);
+    return true;
+}
+// host side of the hand-over: spin on the sequence word the last CTA writes (a few microseconds after the kernel's
+// last store, instead of the copy + stream synchronisation round trip); the stream is queried from time to time so
+// that a failed launch cannot hang the host
+int wait_final(oc_ctx *ctx, int slot, unsigned long long seq, cudaStream_t st, double *out) {
+    for (unsigned long long spin = 1;; spin++) {
+        if (final_ready(ctx, slot, seq, out)) return OC_OK;
+        if ((spin & 0x3ffff) == 0) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaErrorNotReady) continue;
+            if (e == cudaSuccess && final_ready(ctx, slot, seq, out)) return OC_OK;
+            oc::set_error("fused RK45 step did not deliver its error sum: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return OC_ERR_CUDA;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int oc_hjb_rhs(oc_ctx *ctx, const double *d_phi, const double *d_V, const double *d_m,
@@ -555,6 +601,8 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
     int n_out = 0, status = 1;
     const double error_exponent = -1.0 / 5.0;
     const size_t n_int = (size_t)(s.Ny - 2) * (s.Nx - 2);
+    const bool final_in_kernel = use_fused && s.fused_gy <= fused::MAX_FINAL_ROWS;
+    if (final_in_kernel && (rc = ensure_final_reduce(ctx, 1))) return rc;
 
     while (status == 1) {
         if (t == t_bound) { status = 0; break; }  // base.py:193-198
@@ -614,9 +662,12 @@ extern "C" int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, c
                         fa.phi[ne] = d_phi ? d_phi + (size_t)kd * n : phi_scratch + (size_t)ne * n;
                     }
                 }
+                if (final_in_kernel) final_reduce_args(ctx, 0, fa);
                 if ((rc = s.launch_fused(ne, fa))) return rc;
                 stats->nfev += 6;
-                if ((rc = s.reduce_to_host(0, &se, s.fused_gx, s.fused_gy))) return rc;
+                if (final_in_kernel) {
+                    if ((rc = wait_final(ctx, 0, fa.seq, s.st, &se))) return rc;
+                } else if ((rc = s.reduce_to_host(0, &se, s.fused_gx, s.fused_gy))) return rc;
             } else {
             // rk_step (rk.py:61-69): K[0] = f already in place
             for (int sgi = 1; sgi < 6; sgi++) {
@@ -761,10 +812,12 @@ struct BatchRoom {
     double *rs_d = nullptr, *rs_h = nullptr;  // row-group sums (device / pinned host), 3 regions of `rs_stride`
     int rs_stride = 0;
     cudaEvent_t ev = nullptr;
+    unsigned long long wait_seq = 0;     // sequence number of the step attempt in flight (in-kernel final reduction)
     // controller state (rk.py:111-176, base.py:179-210, ivp.py:659-728)
     double t = 0, h_abs = 0, h = 0, t_new = 0, min_step = 0, h0 = 0, d1 = 0;
     bool rejected = false;
     int status = 1, t_eval_i = 0, n_out = 0, ia_lo = 0;
+    double step_sum = 0.0;               // error sum delivered by the last CTA of the attempt
     oc_hjb_stats st{};
 };
 
@@ -834,6 +887,11 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
     const double t_bound = 0.0, direction = (t_bound != T) ? (t_bound > T ? 1.0 : -1.0) : 1.0;
     const double error_exponent = -1.0 / 5.0;
     const bool want_v = d_vx && d_vy;
+    const bool final_in_kernel = fgy <= fused::MAX_FINAL_ROWS;
+    if (final_in_kernel) {
+        int frc = ensure_final_reduce(ctx, n_rooms);
+        if (frc) return frc;
+    }
     std::vector<BatchRoom> rooms(n_rooms);
     for (int b = 0; b < n_rooms; b++) {
         BatchRoom &r = rooms[b];
@@ -917,6 +975,7 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
                 // without a phi output the samples go to the room's scratch slices (velocities are derived on accept)
                 fa.phi[ne] = d_phi ? r.phi + (size_t)kd * n : r.phi + (size_t)((r.t_eval_i - 1 - ia) % fused::NE_MAX) * n;
             }
+            if (final_in_kernel) { final_reduce_args(ctx, (int)(&r - rooms.data()), fa); r.wait_seq = fa.seq; }
             int rc = s.launch_fused(ne, fa);
             if (rc) return rc;
             if (!d_phi && ia >= r.ia_lo) {
@@ -925,8 +984,10 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
             }
         } while (ia >= r.ia_lo);
         r.st.nfev += 6;
-        reduce_async(r, 0, fgx, fgy, 0);
-        cudaEventRecord(r.ev, s.st);
+        if (!final_in_kernel) {
+            reduce_async(r, 0, fgx, fgy, 0);
+            cudaEventRecord(r.ev, s.st);
+        }
         r.phase = BatchRoom::STEP;
         return OC_OK;
     };
@@ -982,7 +1043,7 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
             return start_step(r);
         }
         case BatchRoom::STEP: {  // rk.py:146-165
-            const double error_norm = std::sqrt(host_sum(r, fgy, 0)) / sqrt_n;
+            const double error_norm = std::sqrt(final_in_kernel ? r.step_sum : host_sum(r, fgy, 0)) / sqrt_n;
             if (!(error_norm < 1)) {
                 r.h_abs *= std::max(0.2, 0.9 * std::pow(error_norm, error_exponent));
                 r.rejected = true;
@@ -1022,13 +1083,34 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
         rc = advance(rooms[b]);
         if (rooms[b].phase == BatchRoom::DONE) live--;
     }
+    unsigned long long idle = 0;
     while (live > 0 && !rc) {
+        bool progressed = false;
         for (int b = 0; b < n_rooms && !rc; b++) {
             BatchRoom &r = rooms[b];
             if (r.phase == BatchRoom::DONE) continue;
-            OC_CUDA(cudaEventSynchronize(r.ev));
+            if (final_in_kernel && r.phase == BatchRoom::STEP) {
+                // the attempt's last CTA publishes the error sum in mapped host memory: no event, no copy
+                if (!final_ready(ctx, b, r.wait_seq, &r.step_sum)) continue;
+            } else {
+                cudaError_t e = cudaEventQuery(r.ev);
+                if (e == cudaErrorNotReady) continue;
+                OC_CUDA(e);
+            }
+            progressed = true;
             rc = advance(r);
             if (r.phase == BatchRoom::DONE) live--;
+        }
+        if (progressed) { idle = 0; continue; }
+        if ((++idle & 0x3ffff) == 0) {  // nothing became ready for a long time: make sure no launch has failed
+            for (int q = 0; q < n_streams && !rc; q++) {
+                cudaError_t e = cudaStreamQuery(ctx->batch_streams[q]);
+                if (e != cudaSuccess && e != cudaErrorNotReady) {
+                    oc::set_error("batched HJB solve: %s", cudaGetErrorString(e));
+                    cudaGetLastError();
+                    rc = OC_ERR_CUDA;
+                }
+            }
         }
     }
     // the caller's stream continues after every room stream

@@ -89,7 +89,17 @@ struct Args {
     // whose first row is global row `row_base` (halo rows from the neighbouring bands included); phi slices
     // start at global row `phi_row_base`.  Single GPU: row_base = phi_row_base = 0, own = [0, Ny).
     int row_base, own0, own1, phi_row_base;
+    // Final reduction inside the launch (single-GPU and batched solves): the CTA that finishes last adds the per-CTA
+    // partial sums in the library's fixed order (per chunk row: 256 strided accumulators, shuffle tree, 8 warp sums left
+    // to right; then the chunk rows top to bottom -- exactly rowgroup_sum_kernel + the host loop) and publishes the
+    // scalar in page-locked host memory, where the host polls for it: no reduction launch, no copy, no stream
+    // synchronisation per step attempt.  ticket == NULL: partial sums only (row-band solver: NCCL all-gather).
+    unsigned *ticket;
+    double *result;                 // mapped host memory: result[0] = sum
+    unsigned long long *result_seq; // mapped host memory: set to `seq` after result[0] is visible
+    unsigned long long seq;
 };
+constexpr int MAX_FINAL_ROWS = 2 * 6 * (BX + 2) - 8;  // chunk-row sums are staged in the (then idle) exchange buffer
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -403,6 +413,46 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
 #pragma unroll
         for (int i = 0; i < BX / 32; i++) s += sm.red[i];
         a.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+    if (a.ticket == nullptr) return;
+    // ---- last CTA: fixed-order final reduction (see Args)
+    __shared__ int is_last;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double *rows = &sm.ex[0][0][0];
+    const int ngx = gridDim.x, gy = gridDim.y, lane = tid & 31;
+    for (int row = tid >> 5; row < gy; row += BX / 32) {
+        // the 8 warps of rowgroup_sum_kernel's 256 threads, emulated by this warp: all loads first (independent, in
+        // flight together), then the 8 shuffle trees, then the left-to-right sum of the 8 warp totals
+        double v[8];
+#pragma unroll
+        for (int vw = 0; vw < 8; vw++) {
+            v[vw] = 0.0;
+            for (int i = vw * 32 + lane; i < ngx; i += 256) v[vw] += __ldcg(a.partial + (size_t)row * ngx + i);
+        }
+        double srow = 0.0;
+#pragma unroll
+        for (int vw = 0; vw < 8; vw++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[vw] += __shfl_down_sync(0xffffffffu, v[vw], o);
+            srow += v[vw];  // meaningful on lane 0
+        }
+        if (lane == 0) rows[row] = srow;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int r = 0; r < gy; r++) tot += rows[r];
+        *a.ticket = 0u;
+        *reinterpret_cast<volatile double *>(a.result) = tot;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(a.result_seq) = a.seq;
     }
 }
 

@@ -125,3 +125,38 @@ def test_step_randomness_lookahead_is_stream_exact():
     end = np.random.get_state()
     assert end[2] == end_ref[2] and np.array_equal(end[1], end_ref[1]) and end[3:] == end_ref[3:]
     assert sr.hits >= len(exits) - 3 and sr.misses >= 2          # first step + the step after the foreign draw
+
+
+def test_member_rng_is_the_seeded_global_stream():
+    """ensemble members draw from np.random.RandomState(seed): the very stream np.random.seed(seed) gives the
+    reference (crowd placement: simulations.py:130-140; per-step draws: :271,303)"""
+    from optimal_crowds_b200 import _crowd, _rng
+    X, Y = np.linspace(0, 10, 200), np.linspace(0, 6, 120)
+    box = [2.0, 3.0, 2.0, 3.0, 2.0, "door"]
+    np.random.seed(41)
+    a = _crowd.place_box(box, X, Y, np.zeros((120, 200)))
+    sr = _rng.StepRandomness(lookahead=False)
+    pa, za = sr.draw(12, 7)
+    rs = np.random.RandomState(41)
+    b = _crowd.place_box(box, X, Y, np.zeros((120, 200)), rng=rs)
+    pb, zb = _rng.StepRandomness(lookahead=False, rng=rs).draw(12, 7)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    assert np.array_equal(pa, pb) and np.array_equal(za, zb)
+    # and it equals the reference's literal calls
+    np.random.seed(41)
+    _crowd.place_box(box, X, Y, np.zeros((120, 200)))
+    assert np.array_equal(np.random.choice(np.arange(12), 12, replace=False), pa)
+    assert np.array_equal(np.array([np.random.normal(size=2) for _ in range(7)]), za)
+
+
+def test_history_frame_is_lazy():
+    from optimal_crowds_b200.simulations import _Frame
+    calls = []
+    f = _Frame([["p0", "v0", "door", 1.3], ["p1", "v1", "door", 1.2]], lambda: calls.append(1) or np.ones((3, 4)))
+    assert len(f) == 3 and f[0][2] == "door" and f[1][3] == 1.2 and not calls
+    assert [a[0] for a in f[:-1]] == ["p0", "p1"] and not calls        # agents only: nothing computed
+    assert f[-1].shape == (3, 4) and calls == [1]
+    assert f[2] is f[-1] and calls == [1]                              # computed once
+    g = _Frame([], lambda: np.zeros((2, 2)))
+    assert [type(x) for x in g] == [np.ndarray]                        # iteration materialises the density

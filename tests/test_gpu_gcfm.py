@@ -345,3 +345,53 @@ def test_row_band_field_storage_and_ownership_change_no_bit(cfg):
         for k in a:
             assert torch.equal(a[k], b[k]), f"{k} differs at step {s}"
     ctx.close()
+
+
+def test_sweep_result_is_independent_of_the_schedule(cfg):
+    """size-independent property at 20k agents (no CPU oracle in reach): the concurrent sweep must give the same bits
+    whatever the number of resident warps -- a grid of 2 CTAs (almost sequential), 37 CTAs and the full GPU -- because
+    the dependency protocol, not the schedule, defines the result."""
+    import torch
+    from optimal_crowds_b200 import _lib
+    from oracle import cpu_oracle as co
+    L, H, N, steps = 120.0, 90.0, 20000, 4
+    rng = np.random.RandomState(8)
+    outs = []
+    for ctas in (2, 37, 0):
+        rng = np.random.RandomState(8)
+        ctx = _lib.Context(L, H, 0.05)
+        ctx.set_int("gcfm_sweep_ctas", ctas)
+        Ny, Nx = ctx.Ny, ctx.Nx
+        prm = _lib.gcfm_params(cfg, L, H, Ny, Nx)
+        doors = np.array([[L, H / 2, 0.6, 6.0], [0.0, H / 2, 0.6, 6.0]])
+        Vd = ctx.rasterise([[L / 2, H / 2, 0.4, H / 2]], [], [[L / 3, H / 3, 1.5], [2 * L / 3, 2 * H / 3, 1.5]], doors,
+                           remap=True)
+        tiles, vmin = ctx.wall_tiles(Vd)
+        nsl = steps + 2
+        gx = torch.linspace(-1, 1, Nx - 2, device="cuda", dtype=torch.float64)
+        vx = gx[None, None, :].expand(nsl, Ny - 2, Nx - 2).contiguous()
+        vy = torch.zeros_like(vx)
+        key = dict(V=Vd, tiles=tiles, v_min=vmin, vx=vx, vy=vy, nt_opt=nsl + 1, doors=doors)
+        # a dense crowd: 20000 agents on a jittered lattice of 0.55 m pitch (3.3 ped/m^2, long dependency chains)
+        side = int(np.ceil(np.sqrt(N)))
+        gxp, gyp = np.meshgrid(np.arange(side), np.arange(side))
+        pos = np.column_stack([gxp.ravel()[:N] * 0.55 + 10.0, gyp.ravel()[:N] * 0.55 + 5.0]) + rng.uniform(-0.1, 0.1, (N, 2))
+        st = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=rng.normal(0, 0.5, N), vy=rng.normal(0, 0.5, N),
+                  time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+        dev = {k: ctx.to_device(v) for k, v in st.items()}
+        vd, kid = ctx.to_device(rng.normal(1.34, 0.26, N)), ctx.to_device(np.zeros(N, dtype=np.int32))
+        exits = []
+        for s in range(steps):
+            perm = rng.permutation(N)
+            noise = rng.normal(size=(int(dev["status"].sum().item()), 2))
+            ex, rc = ctx.gcfm_step(prm, dev, vd, kid, [key], perm, noise, s)
+            assert rc == 0
+            exits.append(ex)
+        outs.append(({k: v.clone() for k, v in dev.items()}, exits))
+        ctx.close()
+    for other, ex in outs[1:]:
+        for k in outs[0][0]:
+            assert torch.equal(outs[0][0][k], other[k]), k
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0][1], ex))
+    moved = (outs[0][0]["x"].cpu().numpy() - pos[:, 0])
+    assert np.abs(moved).max() > 1e-3

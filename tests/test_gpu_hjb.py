@@ -294,3 +294,48 @@ def test_batched_solve_is_bitwise_the_single_solves(store, cfg, torch_mod):
             assert torch_mod.equal(batch[b]["phi"], one["phi"])
             np.testing.assert_allclose(batch[b]["phi"].cpu().numpy().reshape(nt, -1), phi_ref, rtol=RTOL)
     ctx.close()
+
+
+def test_full_size_band_properties(cfg, torch_mod):
+    """BASELINE configs[3] band size (16384 x 2048), where the CPU oracle is out of reach: size-independent properties.
+    (1) the stage-fused kernel and the stage-wise kernels (independent code paths) agree to 1e-10 with identical
+    controller decisions; (2) a room that is mirror-symmetric in x gives a mirror-symmetric value function up to the
+    rounding of the (left/right asymmetric) summation order, 1e-11 -- any wrong tile, halo or mirror index would show
+    as an O(1) difference; (3) two virtual row bands reproduce the undecomposed solve bit for bit."""
+    from optimal_crowds_b200 import _lib
+    Ny, Nx, T = 2048, 16384, 0.24
+    nt = round(T / 0.02)
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    ctx = _lib.Context(L, H, 0.05)
+    t = torch_mod
+    ix = t.arange(Nx, device="cuda"); iy = t.arange(Ny, device="cuda")
+    V = t.zeros((Ny, Nx), dtype=t.float64, device="cuda")
+    # cylinders on a 160-node lattice and square doors on a 1280-node lattice, built from index arithmetic so that
+    # column j and column Nx-1-j are exact mirror images
+    jx = t.minimum(ix, Nx - 1 - ix)
+    cx = (jx % 160) - 80; cy = (iy % 160) - 80
+    V[(cy[:, None] ** 2 + cx[None, :] ** 2) < 100] = -100.0
+    dx_ = ((jx % 1280) - 640).abs() < 20; dy_ = ((iy % 1280) - 640).abs() < 20
+    V[dy_[:, None] & dx_[None, :]] = 1.0
+    V[0, :] = -100; V[-1, :] = -100; V[:, 0] = -100; V[:, -1] = -100
+    assert t.equal(V, V.flip(1))
+    phi = ctx.empty(nt, Ny, Nx)
+    a = ctx.hjb_solve(V, None, _lib.hjb_params(cfg, fused=1, chunk_rows=256), T, nt, want_vel=False, out_phi=phi, trace=True)
+    assert a["stats"]["status"] == 0 and a["stats"]["n_out"] == nt
+    # (2) mirror symmetry of every sample
+    asym = ((phi - phi.flip(2)).abs() / phi.abs()).max().item()
+    assert asym < 1e-11, asym
+    # (1) stage-wise path
+    phi2 = ctx.empty(nt, Ny, Nx)
+    b = ctx.hjb_solve(V, None, _lib.hjb_params(cfg, fused=0), T, nt, want_vel=False, out_phi=phi2, trace=True)
+    assert b["stats"]["nfev"] == a["stats"]["nfev"]
+    np.testing.assert_allclose(a["trace_h"], b["trace_h"], rtol=1e-11)
+    rel = ((phi - phi2).abs() / phi2.abs()).max().item()
+    assert rel < RTOL, rel
+    del phi2
+    # (3) virtual bands
+    one = ctx.hjb_solve_band(V, None, _lib.hjb_params(cfg, fused=1, chunk_rows=256), T, nt, n_virtual=1, trace=True)
+    two = ctx.hjb_solve_band(V, None, _lib.hjb_params(cfg, fused=1, chunk_rows=256), T, nt, n_virtual=2, trace=True)
+    assert np.array_equal(one["trace_h"], two["trace_h"]) and t.equal(one["phi"], two["phi"])
+    assert np.abs(one["trace_h"] - a["trace_h"]).max() < 1e-12
+    ctx.close()
