@@ -210,7 +210,8 @@ typedef struct {
 } oc_key;
 
 /* Occupancy map used by the exact nearest-wall search (pedestrians.py:311-313): one byte per
- * OC_WALL_TILE x OC_WALL_TILE block of nodes, 1 if the block holds a node with V < 0.
+ * OC_WALL_TILE x OC_WALL_TILE block of nodes = 1 + ring distance (in tiles, capped) to the nearest block that holds
+ * a node with V < 0 (1 = the block itself holds one); the content is private to the library.
  * d_tiles: device buffer of oc_wall_tiles_bytes(ctx) bytes, caller-owned.  Synchronises `stream`. */
 #define OC_WALL_TILE 16
 long long oc_wall_tiles_bytes(oc_ctx *ctx);

@@ -231,7 +231,10 @@ __device__ long long wall_argmin_warp(const double *__restrict__ X, const double
     double best = INFINITY;
     long long best_i = (long long)Ny * Nx;
     const int kmax = max(max(tcx, ntx - 1 - tcx), max(tcy, nty - 1 - tcy));
-    for (int k = 0; k <= kmax; k++) {
+    // tiles[t] = 1 + (ring distance, in tiles, from t to the nearest tile holding a wall node, capped at RING_CAP):
+    // the rings below that distance are known to be empty and are skipped (no memory round trips for them)
+    const int k0 = min((int)tiles[tcy * ntx + tcx] - 1, kmax);
+    for (int k = max(k0, 0); k <= kmax; k++) {
         const int ty_lo = tcy - k, ty_hi = tcy + k, tx_lo = tcx - k, tx_hi = tcx + k;
         // ring k = border of the (2k+1)^2 tile square.  The occupancy bytes of 32 ring tiles are fetched at once
         // (one lane each) and only the occupied ones are scanned: the ring costs one memory round trip instead
@@ -248,7 +251,7 @@ __device__ long long wall_argmin_warp(const double *__restrict__ X, const double
                 else if (r < 2 * side + (side - 2)) { tx = tx_lo; ty = ty_lo + 1 + (r - 2 * side); }
                 else { tx = tx_hi; ty = ty_lo + 1 + (r - 2 * side - (side - 2)); }
             }
-            const bool occ = tx >= 0 && tx < ntx && ty >= 0 && ty < nty && tiles[ty * ntx + tx] != 0;
+            const bool occ = tx >= 0 && tx < ntx && ty >= 0 && ty < nty && tiles[ty * ntx + tx] == 1;
             unsigned todo = __ballot_sync(0xffffffffu, occ);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -315,6 +318,31 @@ __global__ void tiles_kernel(const double *__restrict__ V, int Ny, int Nx, uint8
         tiles[w] = (uint8_t)any;
         vmin_out[w] = vm;
     }
+}
+
+// ring distance (Chebyshev, in tiles, capped) from every tile to the nearest occupied tile; out = 1 + distance
+constexpr int RING_CAP = 64;
+__global__ void tile_ring_kernel(const uint8_t *__restrict__ occ, int ntx, int nty, uint8_t *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntx * nty) return;
+    const int ty = t / ntx, tx = t % ntx;
+    int d = RING_CAP;
+    for (int k = 0; k < RING_CAP && d == RING_CAP; k++) {
+        bool hit = false;
+        for (int q = -k; q <= k && !hit; q++) {
+            const int xs = tx + q, ys = ty + q;
+            if (xs >= 0 && xs < ntx) {
+                if (ty - k >= 0 && occ[(ty - k) * ntx + xs]) hit = true;
+                if (ty + k < nty && occ[(ty + k) * ntx + xs]) hit = true;
+            }
+            if (ys >= 0 && ys < nty) {
+                if (tx - k >= 0 && occ[ys * ntx + tx - k]) hit = true;
+                if (tx + k < ntx && occ[ys * ntx + tx + k]) hit = true;
+            }
+        }
+        if (hit) d = k;
+    }
+    out[t] = (uint8_t)(1 + d);
 }
 
 // rank = inverse permutation; snapshot; bin histogram
@@ -771,9 +799,12 @@ extern "C" int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, d
     cudaStream_t st = (cudaStream_t)stream;
     int nt = (int)oc_wall_tiles_bytes(ctx);
     double *d_vm = nullptr;
-    OC_CUDA(cudaMalloc(&d_vm, sizeof(double) * nt));
-    tiles_kernel<<<(nt * 32 + 127) / 128, 128, 0, st>>>(d_V, ctx->Ny, ctx->Nx, d_tiles, d_vm);
-    oc::count_launch();
+    OC_CUDA(cudaMalloc(&d_vm, sizeof(double) * nt + nt));
+    uint8_t *d_occ = reinterpret_cast<uint8_t *>(d_vm + nt);
+    const int ntx = (ctx->Nx + WT - 1) / WT, nty = (ctx->Ny + WT - 1) / WT;
+    tiles_kernel<<<(nt * 32 + 127) / 128, 128, 0, st>>>(d_V, ctx->Ny, ctx->Nx, d_occ, d_vm);
+    tile_ring_kernel<<<(nt + 127) / 128, 128, 0, st>>>(d_occ, ntx, nty, d_tiles);
+    oc::count_launch(2);
     std::vector<double> h(nt);
     cudaError_t e = cudaMemcpyAsync(h.data(), d_vm, sizeof(double) * nt, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -1,1 +1,2 @@
-timeout 500 python -m pytest tests/test_gpu_hjb.py::test_full_size_band_properties tests/test_gpu_gcfm.py::test_sweep_result_is_independent_of_the_schedule -m gpu -q -x --timeout 240 2>&1 | tail -12
+timeout 500 python -m pytest tests/test_gpu_gcfm.py tests/test_gpu_simulation.py -m gpu -q -x --timeout 200 2>&1 | tail -3
+timeout 200 python scripts/perf_gcfm.py 2>&1 | tail -4
