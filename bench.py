@@ -477,7 +477,7 @@ def main():
     dom = 0  # RK stage kernels
     achieved = cls_bytes[dom] / (cls_ms[dom] * 1e-3) / 1e9 if cls_ms[dom] > 0 else 0.0
     roof = {"bound": "hbm", "kernel": "hjb_stage_kernel<N,MODE> (RK45 stage: combination + stencil [+ y_new, error])"
-            if not args.fused else "hjb_fused_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            if not args.fused else "fused::hjb_fused_kernel<NE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
             else "fallback (B200_PROFILING.md)", "traffic": None,
             "launches": int(cls_n[dom]), "avg_launch_ms": float(cls_ms[dom] / max(cls_n[dom], 1)),
