@@ -301,8 +301,11 @@ def run_dist(args, world, rank, local_rank):
                 "config": {"workload": f"slalom (BASELINE configs[3]) cylinder field, {nx}x{Ny} grid "
                                        f"({nx}x{ny} band per GPU; N=8 is the 16384^2 / 100k-agent config), T={args.T} "
                                        f"(nt={nt} slices), {args.agents * world} agents",
-                           "parallelism": f"row bands over {world} GPUs, NCCL halo exchange (6 rows of y,f per accepted "
-                                          "step) + all-gather of per-chunk error sums per attempt",
+                           "parallelism": (f"row bands over {world} GPUs; halo rows (6 of y_new, f_new per side) and the "
+                                           "per-chunk error sums are exchanged INSIDE the step launch as NVLink peer "
+                                           "stores (CUDA IPC), NCCL only at solve start") if getattr(ctx, "peer_memory", False)
+                           else (f"row bands over {world} GPUs, NCCL halo exchange (6 rows of y,f per accepted "
+                                 "step) + all-gather of per-chunk error sums per attempt"),
                            "l2": "inputs larger than L2 (each field 268 MB > 126 MB)",
                            "formulation": "stage-fused RK45 step (40 B/cell/attempt + 8 B/cell/emitted phi slice)",
                            "field_storage": "phi", "nfev_per_solve": nfev_total // K},

@@ -151,6 +151,17 @@ typedef struct {
 int oc_dist_unique_id(void *out128);
 int oc_dist_init(oc_ctx *ctx, const void *id128, int rank, int nranks);
 int oc_dist_finalize(oc_ctx *ctx);
+/* NVLink peer-memory mode of the distributed row-band solve (optional; all ranks on one NVSwitch box, <= 8).
+ * After oc_dist_init every rank calls oc_dist_p2p_export(ctx, rows, handle) -- it allocates the band's time-stepping
+ * arrays for bands of `rows` rows in one block and returns its 64-byte CUDA IPC handle -- the ranks exchange the
+ * handles (e.g. torch.distributed.all_gather_object) and call oc_dist_p2p_import(ctx, handles /(n x 64 bytes, rank
+ * order)/, n).  From then on oc_hjb_solve_band does the per-attempt halo exchange and the error-norm all-gather INSIDE
+ * the stage-fused step launch, as peer stores over NVLink, instead of an NCCL group after it; results are bit-identical.
+ * Every rank must call oc_hjb_solve_band the same number of times. */
+int oc_dist_p2p_export(oc_ctx *ctx, int band_rows, void *handle_out64);
+int oc_dist_p2p_import(oc_ctx *ctx, const void *handles, int n);
+int oc_dist_p2p_enabled(oc_ctx *ctx);
+int oc_dist_p2p_disable(oc_ctx *ctx);   /* back to the NCCL exchange (collective decision of the caller) */
 int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const double *d_V, const double *d_m,
                       const oc_hjb_params *prm, double T, const double *t_eval, int nt, double *d_phi, double *d_vx,
                       double *d_vy, oc_hjb_stats *stats, double *trace_h, double *trace_err, int trace_cap,

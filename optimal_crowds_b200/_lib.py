@@ -81,7 +81,7 @@ _lib = None
 EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create", "oc_ctx_destroy", "oc_ctx_set_int", "oc_rasterise",
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
-           "oc_dist_finalize", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
+           "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
            "oc_gcfm_step_finish"]
 
 
@@ -122,6 +122,10 @@ def load():
     lib.oc_dist_unique_id.argtypes = [C.c_void_p]
     lib.oc_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.oc_dist_finalize.argtypes = [C.c_void_p]
+    lib.oc_dist_p2p_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.oc_dist_p2p_import.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.oc_dist_p2p_enabled.argtypes = [C.c_void_p]
+    lib.oc_dist_p2p_disable.argtypes = [C.c_void_p]
     lib.oc_hjb_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p,
                                C.c_void_p]
     lib.oc_hjb_vels.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(HjbParams), C.c_void_p, C.c_void_p, C.c_void_p]
@@ -250,6 +254,24 @@ class Context:
         buf = C.create_string_buffer(bytes(id_bytes), 128)
         check(load().oc_dist_init(self.h, buf, int(rank), int(nranks)))
         self.rank, self.nranks = int(rank), int(nranks)
+
+    def p2p_export(self, band_rows: int) -> bytes:
+        """allocate this rank's peer-memory band arrays and return their 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        check(load().oc_dist_p2p_export(self.h, int(band_rows), buf))
+        return buf.raw
+
+    def p2p_import(self, handles):
+        """map the band arrays of all ranks (handles in rank order); the row-band solve then exchanges halos and
+        error sums inside the step launch over NVLink peer memory"""
+        blob = b"".join(bytes(h) for h in handles)
+        check(load().oc_dist_p2p_import(self.h, C.create_string_buffer(blob, len(blob)), len(handles)))
+
+    def p2p_enabled(self) -> bool:
+        return bool(load().oc_dist_p2p_enabled(self.h))
+
+    def p2p_disable(self):
+        load().oc_dist_p2p_disable(self.h)
 
     def hjb_solve_band(self, V, m, prm: HjbParams, T, nt, n_virtual=0, own=None, want_phi=True, want_vel=False,
                        trace=False, out_phi=None, phi_extra_hi=0):

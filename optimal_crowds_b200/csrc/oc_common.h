@@ -48,6 +48,13 @@ struct oc_ctx {
     double *fr_result = nullptr;
     int fr_slots = 0;
     unsigned long long fr_seq = 0;
+    // row-band solve over NVLink peer memory (oc_dist_p2p_*): y, y_new, f, f_new of this rank's band + the inboxes live
+    // in ONE cudaMalloc block that the other ranks map through CUDA IPC
+    void *p2p_buf = nullptr;
+    size_t p2p_bytes = 0, p2p_n_store = 0;
+    void *p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_on = false;
+    unsigned long long p2p_seq = 0;
     // batched (ensemble) HJB solve: per-room workspace, streams and events
     double *batch_ws = nullptr;
     size_t batch_ws_bytes = 0;

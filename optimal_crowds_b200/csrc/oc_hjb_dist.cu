@@ -18,6 +18,7 @@
 
 #include "oc_common.h"
 #include "oc_hjb_fused.cuh"
+#include "oc_hjb_final.h"
 #include "oc_rk45.h"
 #include "oc_vels.h"
 
@@ -220,7 +221,72 @@ int oc_dist_allreduce_max_u64(oc_ctx *ctx, void *d_buf, size_t count, cudaStream
     return OC_OK;
 }
 
+// ---- NVLink peer-memory mode --------------------------------------------------------------------------------
+// One cudaMalloc block per rank holds the four time-stepping arrays of its band (y, y_new, f, f_new: rows_store x Nx
+// each) and the inboxes of the cross-GPU error-sum exchange.  The block is exported through CUDA IPC; every rank maps
+// the blocks of all ranks (same layout everywhere, so a peer address is peer_base + local offset).
+static size_t p2p_inbox_doubles() { return (size_t)2 * fused::P2P_MAX_RANKS * fused::P2P_INBOX_STRIDE; }
+
+extern "C" int oc_dist_p2p_export(oc_ctx *ctx, int band_rows, void *handle_out64) {
+    OC_ARG(ctx && handle_out64 && band_rows > 0, "bad arguments");
+    OC_ARG(ctx->nranks >= 1 && ctx->nranks <= fused::P2P_MAX_RANKS, "peer-memory mode supports up to 8 ranks");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    const size_t n_store = (size_t)(band_rows + 2 * HB) * ctx->Nx;
+    const size_t bytes = (4 * n_store + p2p_inbox_doubles()) * sizeof(double);
+    if (ctx->p2p_buf) { cudaFree(ctx->p2p_buf); ctx->p2p_buf = nullptr; }
+    ctx->p2p_on = false;
+    if (cudaMalloc(&ctx->p2p_buf, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        oc::set_error("cannot allocate %zu bytes for the peer-memory band arrays", bytes);
+        return OC_ERR_NOMEM;
+    }
+    OC_CUDA(cudaMemset(ctx->p2p_buf, 0, bytes));
+    OC_CUDA(cudaDeviceSynchronize());
+    ctx->p2p_bytes = bytes;
+    ctx->p2p_n_store = n_store;
+    cudaIpcMemHandle_t h;
+    OC_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_buf));
+    memcpy(handle_out64, &h, sizeof(h));
+    return OC_OK;
+}
+
+extern "C" int oc_dist_p2p_import(oc_ctx *ctx, const void *handles, int n) {
+    OC_ARG(ctx && handles && ctx->p2p_buf && n == ctx->nranks, "export first; one handle per rank expected");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    for (int q = 0; q < n; q++) {
+        if (q == ctx->rank) { ctx->p2p_peer[q] = ctx->p2p_buf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)q * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            oc::set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+            return OC_ERR_CUDA;
+        }
+        ctx->p2p_peer[q] = p;
+    }
+    ctx->p2p_on = true;
+    ctx->p2p_seq = 0;
+    return OC_OK;
+}
+
+extern "C" int oc_dist_p2p_enabled(oc_ctx *ctx) { return ctx && ctx->p2p_on ? 1 : 0; }
+extern "C" int oc_dist_p2p_disable(oc_ctx *ctx) {
+    if (ctx) ctx->p2p_on = false;  // back to the NCCL exchange (the mapped blocks are released by oc_dist_finalize)
+    return OC_OK;
+}
+
 extern "C" int oc_dist_finalize(oc_ctx *ctx) {
+    if (ctx && ctx->p2p_buf) {
+        cudaSetDevice(ctx->device);
+        for (int q = 0; q < ctx->nranks && q < 8; q++)
+            if (q != ctx->rank && ctx->p2p_peer[q]) cudaIpcCloseMemHandle(ctx->p2p_peer[q]);
+        cudaFree(ctx->p2p_buf);
+        ctx->p2p_buf = nullptr;
+        ctx->p2p_on = false;
+    }
     if (ctx && ctx->nccl_comm) {
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
@@ -261,12 +327,17 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     const int gy_f = (band_rows + rc_rows - 1) / rc_rows, gy_t = (band_rows + TYS - 1) / TYS;
     const int rows_store = band_rows + 2 * HB;
     const size_t n_store = (size_t)rows_store * Nx, n_glob = (size_t)Ny * Nx;
+    int rc0 = 0;
     const bool want_v = d_vx && d_vy, want_out = d_phi || want_v;
     // phi slices of a distributed band hold one halo row below and 1 + phi_extra_hi rows above the owned rows (the
     // GCFM sampler of an agent owned by this band reads up to two rows past it, oc_gcfm.cu)
     const int xhi = dist ? cfg->phi_extra_hi : 0;
     OC_ARG(xhi == 0 || xhi == 1, "phi_extra_hi must be 0 or 1");
 
+    // peer-memory mode: the band arrays live in the IPC-exported block, halos and error sums travel inside the step launch
+    const bool use_p2p = dist && nranks > 1 && ctx->p2p_on && ctx->p2p_n_store == n_store && gy_f <= fused::P2P_INBOX_STRIDE - 2 &&
+                         gy_f <= fused::MAX_FINAL_ROWS && !prm->forced_h;
+    if (use_p2p && (rc0 = ocfinal::ensure(ctx, 1))) return rc0;
     // ---- workspace: per local band 5 arrays + partials (+ phi scratch)
     const size_t per_band = 5 * n_store + (size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64 +
                             ((want_v && !d_phi) ? (size_t)fused::NE_MAX * (band_rows + 2) * Nx : 0);
@@ -300,6 +371,10 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
         b.rows_store = rows_store;
         b.coef = wsp; b.y = wsp + n_store; b.ynew = wsp + 2 * n_store; b.f = wsp + 3 * n_store; b.fnew = wsp + 4 * n_store;
         wsp += 5 * n_store;
+        if (use_p2p) {
+            double *pb = (double *)ctx->p2p_buf;
+            b.y = pb; b.ynew = pb + n_store; b.f = pb + 2 * n_store; b.fnew = pb + 3 * n_store;
+        }
         b.partial = wsp; wsp += (size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64;
         b.gy_fused = gy_f; b.gy_tiles = gy_t;
         b.V = d_V; b.m = d_m;
@@ -446,29 +521,37 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     }
     stats->h0 = h_abs;
 
-    static bool attr_done[fused::NE_MAX + 1] = {};
+    static bool attr_done[2][fused::NE_MAX + 1] = {};
     auto launch_fused = [&](int ne, const fused::Args &fa, dim3 grid) -> int {
-#define CASE(NE)                                                                                                  \
-    case NE:                                                                                                      \
-        if (!attr_done[NE]) {                                                                                     \
-            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)sizeof(fused::Smem)));                                              \
-            attr_done[NE] = true;                                                                                 \
-        }                                                                                                         \
-        fused::hjb_fused_kernel<NE><<<grid, fused::BX, sizeof(fused::Smem), st>>>(fa);                            \
+#define CASE(NE)                                                                                                         \
+    case NE:                                                                                                             \
+        if (!attr_done[use_p2p][NE]) {                                                                                   \
+            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)sizeof(fused::Smem)));                                                     \
+            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)sizeof(fused::Smem)));                                                     \
+            attr_done[use_p2p][NE] = true;                                                                               \
+        }                                                                                                                \
+        if (use_p2p) fused::hjb_fused_kernel<NE, true><<<grid, fused::BX, sizeof(fused::Smem), st>>>(fa);                 \
+        else fused::hjb_fused_kernel<NE, false><<<grid, fused::BX, sizeof(fused::Smem), st>>>(fa);                       \
         break;
         switch (ne) { CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) }
 #undef CASE
         launches++;
         return OC_OK;
     };
+    // peer addresses: same layout in every rank's block
+    auto peer_of = [&](int q, const double *mine) -> double * {
+        return (double *)ctx->p2p_peer[q] + (mine - (const double *)ctx->p2p_buf);
+    };
 
     int t_eval_i = nt, n_out = 0, status = 1;
+    unsigned long long p2p_wait_seq = 0;
     const double error_exponent = -1.0 / 5.0;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;  // one pair per attempt, read after the final synchronisation
     double step_ms = 0.0;
     int step_launches = 0;
-    if (prm->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
 
     while (status == 1) {
         if (t == t_bound) { status = 0; break; }
@@ -526,7 +609,26 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                         fa.phi[e] = d_phi ? d_phi + (size_t)kd * b.phi_slice
                                           : b.scratch + (size_t)((done + e) % fused::NE_MAX) * b.phi_slice;
                     }
-                    if (prm->profile && q == 0 && done == 0) cudaEventRecord(pe0, st);
+                    if (use_p2p) {
+                        ocfinal::set_args(ctx, 0, ++ctx->p2p_seq, fa);
+                        p2p_wait_seq = fa.seq;
+                        fa.nranks = nranks; fa.my_rank = rank;
+                        for (int r2 = 0; r2 < nranks; r2++)
+                            fa.peer_inbox[r2] = (double *)ctx->p2p_peer[r2] + 4 * n_store;
+                        if (rank > 0) {
+                            fa.peer_ynew[0] = peer_of(rank - 1, b.ynew); fa.peer_k7[0] = peer_of(rank - 1, b.fnew);
+                            fa.peer_row_base[0] = b.v.row_base - band_rows;
+                        }
+                        if (rank + 1 < nranks) {
+                            fa.peer_ynew[1] = peer_of(rank + 1, b.ynew); fa.peer_k7[1] = peer_of(rank + 1, b.fnew);
+                            fa.peer_row_base[1] = b.v.row_base + band_rows;
+                        }
+                    }
+                    if (prm->profile && q == 0 && done == 0) {
+                        cudaEventCreate(&pe0); cudaEventCreate(&pe1);
+                        prof.emplace_back(pe0, pe1);
+                        cudaEventRecord(pe0, st);
+                    }
                     if ((rc = launch_fused(ne, fa, dim3(gx_f, gy_f)))) return rc;
                     if (prm->profile && q == nb_local - 1 && done == 0) {
                         cudaEventRecord(pe1, st);
@@ -536,13 +638,11 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
             } while (done < n_emit && !(want_v && !d_phi));  // scratch holds one batch only (see below)
             stats->nfev += 6;
             double se;
-            if ((rc = reduce(2 * nb_t, gx_f, gy_f, &se, true))) return rc;
-            if (prm->profile) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, pe0, pe1);
-                step_ms += ms;
-                step_launches += nb_local;
-            }
+            if (use_p2p) {
+                // halos and the gathered error sums arrived inside the launch; the last CTA hands over the total
+                if ((rc = ocfinal::wait(ctx, 0, p2p_wait_seq, st, &se))) return rc;
+            } else if ((rc = reduce(2 * nb_t, gx_f, gy_f, &se, true))) return rc;
+            if (prm->profile) step_launches += nb_local;
             const double error_norm = std::sqrt(se) / sqrt_n;
             if (trace_h && ntr < trace_cap) { trace_h[ntr] = h; trace_err[ntr] = error_norm; }
             ntr++;
@@ -608,7 +708,12 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     OC_CUDA(cudaGetLastError());
     float ms = 0;
     OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    if (pe0) { cudaEventDestroy(pe0); cudaEventDestroy(pe1); }
+    for (auto &pr : prof) {
+        float pms = 0;
+        if (cudaEventElapsedTime(&pms, pr.first, pr.second) == cudaSuccess) step_ms += pms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    cudaGetLastError();
     stats->gpu_ms = ms;
     stats->status = status;
     stats->n_out = n_out;

@@ -73,6 +73,9 @@ inline int plan_chunk_rows(int Nx, int rows, int n_sm, int copies, int must_divi
     return rc;
 }
 
+constexpr int P2P_MAX_RANKS = 8;    // one NVSwitch box
+constexpr int P2P_INBOX_STRIDE = 64; // doubles per (parity, rank) inbox slot: <= 62 chunk-row sums + the sequence number
+
 struct Args {
     const double *y, *k1, *coef;
     double *ynew, *k7, *partial;
@@ -98,6 +101,17 @@ struct Args {
     double *result;                 // mapped host memory: result[0] = sum
     unsigned long long *result_seq; // mapped host memory: set to `seq` after result[0] is visible
     unsigned long long seq;
+    // Row-band solve over NVLink peer memory (template parameter P2P; oc_hjb_dist.cu): the halo exchange and the
+    // error-norm all-gather are part of this launch.  (a) A thread that stores a row of y_new / f_new lying within
+    // HY rows of a band edge stores it a second time, straight into the neighbouring GPU's halo rows.  (b) The last
+    // CTA writes this band's chunk-row sums into the inbox of every rank (peer stores, then a system fence, then the
+    // sequence number), waits for the inboxes of all ranks, adds the sums in global chunk order and hands the total to
+    // the host.  A rank that has seen every rank's sequence number also knows that every rank's kernel -- and with it
+    // every halo store aimed at this rank -- has completed.
+    double *peer_ynew[2], *peer_k7[2];  // [0]: rank-1 (rows above), [1]: rank+1; NULL at the ends of the grid
+    int peer_row_base[2];               // global row of storage row 0 of the neighbour's arrays
+    int nranks, my_rank;
+    double *peer_inbox[P2P_MAX_RANKS];  // inbox of rank q as seen from this GPU; [my_rank] is the local one
 };
 constexpr int MAX_FINAL_ROWS = 2 * 6 * (BX + 2) - 8;  // chunk-row sums are staged in the (then idle) exchange buffer
 
@@ -161,7 +175,7 @@ struct Smem {
 
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-template <int NE>
+template <int NE, bool P2P = false>
 __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -329,6 +343,15 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
             acc = ok ? fma(qq, qq, acc) : acc;
             st_if(a.ynew + g, un[6], ok);
             st_if(a.k7 + g, k7, ok);
+            if (P2P) {  // rows within HY of a band edge also go to the neighbour's halo rows (NVLink peer stores)
+                const bool up = ok && row < a.own0 + HY && a.peer_ynew[0] != nullptr;
+                const bool dn = ok && row >= a.own1 - HY && a.peer_ynew[1] != nullptr;
+                const int gu = (row - a.peer_row_base[0]) * a.Nx + gx, gd = (row - a.peer_row_base[1]) * a.Nx + gx;
+                st_if(a.peer_ynew[0] + gu, un[6], up);
+                st_if(a.peer_k7[0] + gu, k7, up);
+                st_if(a.peer_ynew[1] + gd, un[6], dn);
+                st_if(a.peer_k7[1] + gd, k7, dn);
+            }
 #pragma unroll
             for (int ee = 0; ee < NE; ee++) {
                 double ph;
@@ -418,7 +441,8 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     // ---- last CTA: fixed-order final reduction (see Args)
     __shared__ int is_last;
     if (tid == 0) {
-        __threadfence();
+        if (P2P) __threadfence_system();  // this CTA's peer stores are ordered before its ticket
+        else __threadfence();
         const unsigned t = atomicAdd(a.ticket, 1u);
         is_last = (t == gridDim.x * gridDim.y - 1);
     }
@@ -446,6 +470,33 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         if (lane == 0) rows[row] = srow;
     }
     __syncthreads();
+    if (P2P) {
+        // all-gather of the chunk-row sums through the ranks' inboxes (double buffered by the parity of seq)
+        const int par = (int)(a.seq & 1ull);
+        if (tid < a.nranks) {
+            double *dst = a.peer_inbox[tid] + (size_t)(par * P2P_MAX_RANKS + a.my_rank) * P2P_INBOX_STRIDE;
+            for (int r = 0; r < gy; r++) *reinterpret_cast<volatile double *>(dst + r) = rows[r];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(dst + P2P_INBOX_STRIDE - 1) = a.seq;
+            const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(
+                a.peer_inbox[a.my_rank] + (size_t)(par * P2P_MAX_RANKS + tid) * P2P_INBOX_STRIDE + P2P_INBOX_STRIDE - 1);
+            while (*flag != a.seq) __nanosleep(100);
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int q = 0; q < a.nranks; q++) {  // global chunk order: ranks top to bottom, chunk rows top to bottom
+                const volatile double *src = a.peer_inbox[a.my_rank] + (size_t)(par * P2P_MAX_RANKS + q) * P2P_INBOX_STRIDE;
+                for (int r = 0; r < gy; r++) tot += src[r];
+            }
+            *a.ticket = 0u;
+            *reinterpret_cast<volatile double *>(a.result) = tot;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(a.result_seq) = a.seq;
+        }
+        return;
+    }
     if (tid == 0) {
         double tot = 0.0;
         for (int r = 0; r < gy; r++) tot += rows[r];

@@ -40,8 +40,47 @@ def share_unique_id(make_id=nccl_unique_id) -> bytes:
     return box[0]
 
 
-def init_context(ctx, make_id=nccl_unique_id):
-    """create the library's communicator for `ctx` on every rank of the default process group"""
+def share_ipc_handles(mine: bytes):
+    """every rank contributes its 64-byte CUDA IPC handle and gets the handles of all ranks, in rank order"""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, bytes(mine))
+    return out
+
+
+def enable_peer_memory(ctx, all_agree=None) -> bool:
+    """NVLink peer-memory mode of the row-band solve (halo exchange and error-norm all-gather inside the step launch).
+    Collective: every rank calls it.  All or nothing: if one rank cannot export or map the band arrays (or OC_P2P=0),
+    every rank stays on the NCCL exchange and False is returned."""
+    import os
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    want = os.environ.get("OC_P2P", "1") != "0" and 1 < world <= 8
+    mine = b""
+    if want:
+        try:
+            mine = ctx.p2p_export(band_rows(ctx.Ny, world))
+        except Exception:
+            mine = b""
+    handles = share_ipc_handles(mine)
+    ok = all(len(h) == 64 for h in handles)
+    if ok:
+        try:
+            ctx.p2p_import(handles)
+        except Exception:
+            ok = False
+    votes = [None] * world
+    dist.all_gather_object(votes, bool(ok))
+    ok = all(votes) if all_agree is None else all_agree(votes)
+    if not ok:
+        ctx.p2p_disable()
+    return ok
+
+
+def init_context(ctx, make_id=nccl_unique_id, peer_memory=True):
+    """create the library's communicator for `ctx` on every rank of the default process group (and, on one NVSwitch box,
+    map the ranks' band arrays into each other for the peer-memory exchange)"""
     import torch.distributed as dist
     ctx.dist_init(share_unique_id(make_id), dist.get_rank(), dist.get_world_size())
+    ctx.peer_memory = enable_peer_memory(ctx) if peer_memory else False
     return band_of(dist.get_rank(), ctx.Ny, dist.get_world_size())

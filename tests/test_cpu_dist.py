@@ -142,3 +142,63 @@ def test_ensemble_planning():
     waves = ensemble.plan_waves(list(range(128)), per, int(140e9))
     assert sum(len(w) for w in waves) == 128 and max(len(w) for w in waves) <= 140e9 // per
     assert ensemble.plan_waves([1, 2, 3], per, 10) == [[1], [2], [3]]     # never less than one member per wave
+
+
+class _FakeCtx:
+    """stands in for _lib.Context in the peer-memory hand-shake (no GPU here)"""
+
+    def __init__(self, rank, fail_export_on=None, fail_import_on=None):
+        self.rank, self.Ny = rank, 64
+        self.fail_export_on, self.fail_import_on = fail_export_on, fail_import_on
+        self.imported, self.disabled = None, False
+
+    def p2p_export(self, rows):
+        if self.rank == self.fail_export_on:
+            raise RuntimeError("no IPC here")
+        return bytes([self.rank]) * 64
+
+    def p2p_import(self, handles):
+        if self.rank == self.fail_import_on:
+            raise RuntimeError("cannot map peer")
+        self.imported = list(handles)
+
+    def p2p_disable(self):
+        self.disabled = True
+
+
+def _p2p_worker(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from optimal_crowds_b200 import dist as ocd
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        a = _FakeCtx(rank)
+        assert ocd.enable_peer_memory(a) is True and not a.disabled
+        assert a.imported == [bytes([0]) * 64, bytes([1]) * 64]          # every rank's handle, in rank order
+        b = _FakeCtx(rank, fail_export_on=1)
+        assert ocd.enable_peer_memory(b) is False and b.disabled         # all or nothing: both ranks fall back to NCCL
+        c = _FakeCtx(rank, fail_import_on=0)
+        assert ocd.enable_peer_memory(c) is False and c.disabled
+        os.environ["OC_P2P"] = "0"
+        d = _FakeCtx(rank)
+        assert ocd.enable_peer_memory(d) is False and d.imported is None
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        os.environ.pop("OC_P2P", None)
+        dist.destroy_process_group()
+
+
+def test_peer_memory_handshake_is_all_or_nothing_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
