@@ -317,7 +317,10 @@ def run_dist(args, world, rank, local_rank):
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "traffic": ncu_traffic(True)[0], "traffic_source": ncu_traffic(True)[1],
                              "launches": int(step_n), "avg_launch_ms": step_ms_max / max(step_n, 1),
-                             "share_of_step": step_ms_max / ms_max},
+                             "share_of_step": step_ms_max / ms_max,
+                             "note": ("the launch contains the halo exchange and the cross-GPU error-sum all-gather: its "
+                                      "duration includes waiting for the slowest rank") if getattr(ctx, "peer_memory", False)
+                             else "halo exchange and all-gather run as an NCCL group after the launch"},
                 "cpu_baseline": None,
                 "gcfm": {"metric": "gcfm_agent_steps_per_s", "value": world * agent_steps / float(gt[1].item()),
                          "unit": "agent-steps/s", "e2e_value": world * agent_steps / float(gt[0].item()),
