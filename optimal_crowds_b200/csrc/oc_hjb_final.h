@@ -41,8 +41,13 @@ inline bool ready(oc_ctx *ctx, int slot, unsigned long long seq, double *out) {
 // spin on the sequence word the last CTA writes (a few microseconds after the kernel's last store, instead of the copy +
 // stream synchronisation round trip); the stream is queried from time to time so that a failed launch cannot hang the host
 inline int wait(oc_ctx *ctx, int slot, unsigned long long seq, cudaStream_t st, double *out) {
+    const volatile unsigned long long *f = reinterpret_cast<const volatile unsigned long long *>(ctx->fr_result + 2 * slot + 1);
     for (unsigned long long spin = 1;; spin++) {
         if (ready(ctx, slot, seq, out)) return OC_OK;
+        if (*f == (seq | (1ull << 63))) {  // peer-memory mode: another rank never delivered its error sums
+            oc::set_error("row-band solve: a peer rank did not arrive within the time-out");
+            return OC_ERR_NCCL;
+        }
         if ((spin & 0x3ffff) == 0) {
             cudaError_t e = cudaStreamQuery(st);
             if (e == cudaErrorNotReady) continue;

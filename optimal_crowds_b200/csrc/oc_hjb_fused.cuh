@@ -480,11 +480,19 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
             *reinterpret_cast<volatile unsigned long long *>(dst + P2P_INBOX_STRIDE - 1) = a.seq;
             const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(
                 a.peer_inbox[a.my_rank] + (size_t)(par * P2P_MAX_RANKS + tid) * P2P_INBOX_STRIDE + P2P_INBOX_STRIDE - 1);
-            while (*flag != a.seq) __nanosleep(100);
+            // bounded wait (>= 8 s): a rank that died must not leave the others spinning in a kernel for ever
+            long long it = 0;
+            while (*flag != a.seq) {
+                if (++it > 40000000ll) { is_last = 2; break; }
+                __nanosleep(200);
+            }
             __threadfence_system();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && is_last == 2) {  // peer time-out: tell the host (sequence number with the top bit set)
+            *a.ticket = 0u;
+            *reinterpret_cast<volatile unsigned long long *>(a.result_seq) = a.seq | (1ull << 63);
+        } else if (tid == 0) {
             double tot = 0.0;
             for (int q = 0; q < a.nranks; q++) {  // global chunk order: ranks top to bottom, chunk rows top to bottom
                 const volatile double *src = a.peer_inbox[a.my_rank] + (size_t)(par * P2P_MAX_RANKS + q) * P2P_INBOX_STRIDE;

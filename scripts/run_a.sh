@@ -1,2 +1,4 @@
-timeout 700 python -m pytest tests -m gpu -q --timeout 240 > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+N=$1
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 150 $TR --master-port 29533 scripts/dist_check.py > gpurun_out/dist_check_p2p_n$N.log 2>&1; grep -n "DIST_CHECK" gpurun_out/dist_check_p2p_n$N.log | head -3
+timeout 120 python -m pytest tests/test_gpu_hjb.py -m gpu -q -x --timeout 100 2>&1 | tail -2
