@@ -257,3 +257,8 @@ if __name__ == "__main__":
     run_golden("run_room_test_T30", "room_test", 30.0)
     run_golden("run_room_test_T4", "room_test", 4.0)
     run_golden("run_exit_opposite_T4_recompute", "exit_opposite", 4.0, recompute=True)
+    # down-scaled BASELINE configs[2] (metro station: 4 boxes / 4 target sets, wall with holes, pillars) and configs[3]
+    # (slalom cylinder field); the full-size rooms are generated by optimal_crowds_b200/synthetic.py
+    hjb_golden("hjb_metro_station_T1", "metro_station", 1.0)
+    run_golden("run_metro_station_T3", "metro_station", 3.0)
+    run_golden("run_slalom_T4", "slalom", 4.0, seed=3)

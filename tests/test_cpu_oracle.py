@@ -1,6 +1,7 @@
 """CPU tests: the oracle (oracle/*.c) against the golden vectors produced by the UNMODIFIED reference
 (oracle/make_goldens.py).  This is what pins the oracle; the GPU tests then compare CUDA with the oracle."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -28,7 +29,8 @@ def test_elementary_functions_within_2ulp_of_numpy():
     assert co.math_fn("exp", np.array([800.0]))[0] == np.inf and co.math_fn("exp", np.array([-800.0]))[0] == 0.0
 
 
-@pytest.mark.parametrize("name", ["hjb_room_test_T3", "hjb_small_T2_density", "hjb_exit_opposite_T1"])
+@pytest.mark.parametrize("name", ["hjb_room_test_T3", "hjb_small_T2_density", "hjb_exit_opposite_T1",
+                                  "hjb_metro_station_T1"])
 def test_hjb_oracle_vs_reference(name):
     g = golden(name)
     T = float(g["T"])
@@ -144,3 +146,53 @@ def test_gcfm_teacher_forced_vs_reference(name, cfg):
         assert np.array_equal(out[:, 4], a[:, 4])  # exits bit-exact
         n_exits += len(ex)
     assert n_exits == int((g["before"][0][:, 4].sum() - g["inside"][-1])) or name == "gcfm_dense"
+
+
+@pytest.mark.parametrize("name,room_name,seed,horizon", [("run_metro_station_T3", "metro_station", 0, 60),
+                                                         ("run_slalom_T4", "slalom", 3, 60)])
+def test_whole_run_restatement_vs_reference_run(name, room_name, seed, horizon, cfg):
+    """O2 against O1 over a free run (down-scaled BASELINE configs[2] and [3]: 4 boxes with 4 target sets, two of them
+    multi-target, a wall pierced by holes, pillars / a cylinder field): crowd placement with the reference's RNG
+    stream, one oracle HJB solve per target set, sequential sweeps -- trajectories within 1e-8 of the reference's
+    over the first 60 steps (SURVEY section 0 #4: chaos separates any two implementations later)."""
+    from optimal_crowds_b200 import _crowd
+    from conftest import REPO, room_grid
+    g = golden(name)
+    room = json.loads(str(g["room"]))
+    assert room == json.load(open(os.path.join(REPO, "rooms", room_name + ".json")))
+    T = float(g["T"])
+    L, H, Ny, Nx, X, Y = room_grid(room)
+    P = co.gcfm_params(cfg, L, H, Ny, Nx)
+    np.random.seed(seed)
+    place = np.zeros((Ny, Nx))
+    keys, kdata, xs, ys, vd, kid = [], [], [], [], [], []
+    nt = round(T / cfg["dt"])
+    for box in room["initial_boxes"].values():
+        tg = box[5:]
+        key = " or ".join(tg)
+        if key not in keys:
+            doors = [room["targets"][t] for t in tg]
+            V = co.create_potential(X, Y, list(room["walls"].values()), list(room["holes"].values()),
+                                    list(room["cylinders"].values()), doors)
+            V[V < 0] = -100; V[V > 0] = 1
+            phi, st, _, _ = co.hjb_solve(V, None, T, nt)
+            assert st["status"] == 0
+            vx, vy = co.fill_field(phi, Ny, Nx)
+            keys.append(key)
+            kdata.append(co.KeyData(V, vx, vy, nt, doors))
+        a, b, c = _crowd.place_box(box, X, Y, place)
+        xs.append(a); ys.append(b); vd.append(c); kid.append(np.full(len(a), keys.index(key), dtype=np.int32))
+    xs, ys, vd, kid = map(np.concatenate, (xs, ys, vd, kid))
+    traj = g["traj"]
+    N = len(xs)
+    assert N == traj.shape[0] and np.array_equal(vd, g["v_des"])
+    assert np.array_equal(np.column_stack([xs, ys]), traj[:, 0, :2])          # identical initial crowd
+    st = dict(x=xs.copy(), y=ys.copy(), vx=np.zeros(N), vy=np.zeros(N), time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    for s in range(horizon):
+        perm = np.random.choice(np.arange(N), N, replace=False)
+        noise = np.random.normal(size=(int(st["status"].sum()), 2))
+        ex, bad, _ = co.gcfm_step(P, st, vd, kid, kdata, X, Y, perm, noise, s)
+        assert bad == 0
+        act = st["status"] == 1
+        ref = traj[:, s + 1]
+        assert np.abs(np.column_stack([st["x"], st["y"], st["vx"], st["vy"]])[act] - ref[act]).max() < 1e-8, f"step {s}"

@@ -38,7 +38,8 @@ FUSED = pytest.mark.parametrize("fused", [0, 1], ids=["stagewise", "fused"])
 
 
 @FUSED
-@pytest.mark.parametrize("name", ["hjb_room_test_T3", "hjb_small_T2_density", "hjb_exit_opposite_T1"])
+@pytest.mark.parametrize("name", ["hjb_room_test_T3", "hjb_small_T2_density", "hjb_exit_opposite_T1",
+                                  "hjb_metro_station_T1"])
 def test_solve_matches_reference_golden(name, fused, cfg, torch_mod):
     from optimal_crowds_b200 import _lib
     g = golden(name)

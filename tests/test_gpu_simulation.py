@@ -185,3 +185,25 @@ def test_history_density_is_lazy_and_equal_to_the_eager_splat(in_repo_cwd):
         pos, vel, target, v_des = frame[0]
         assert pos.shape == (2,) and target == "door_1"
         assert np.array_equal(frame[-1], d) and frame[-1].shape == (simu.Ny, simu.Nx)
+
+
+@pytest.mark.parametrize("name,room,T,seed", [("run_metro_station_T3", "metro_station", 3.0, 0),
+                                              ("run_slalom_T4", "slalom", 4.0, 3)])
+def test_multi_key_and_cylinder_field_runs_vs_reference(name, room, T, seed, in_repo_cwd):
+    """down-scaled BASELINE configs[2] (4 boxes / 4 target sets, two of them multi-target, wall with holes, pillars) and
+    configs[3] (cylinder field): same crowd, same number of steps, trajectories within 1e-8 of the reference's over
+    the first 60 steps, through the drop-in API."""
+    g = golden(name)
+    simu, log = _run(room, T, False, seed)
+    traj = g["traj"]
+    N = traj.shape[0]
+    assert simu.N == N and simu.simu_step == int(g["simu_step"]) and np.array_equal(simu._h_vdes, g["v_des"])
+    assert len(simu.targets) == (4 if room == "metro_station" else 1)
+    horizon = 60
+    for i in range(N):
+        t = np.array(simu.agents[i].traj)
+        v = np.array(simu.agents[i].vels)
+        n = min(horizon + 1, len(t))
+        assert np.abs(t[:n] - traj[i, :n, :2]).max() < 1e-8
+        assert np.abs(v[:n] - traj[i, :n, 2:]).max() < 1e-8
+    assert log.count("Optimal trajectories have been learnt for") == len(simu.targets)
