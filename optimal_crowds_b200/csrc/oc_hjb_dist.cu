@@ -610,7 +610,9 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                                           : b.scratch + (size_t)((done + e) % fused::NE_MAX) * b.phi_slice;
                     }
                     if (use_p2p) {
-                        ocfinal::set_args(ctx, 0, ++ctx->p2p_seq, fa);
+                        // sequence numbers of this mode carry bit 62, so a value left in the result slot by a
+                        // single-GPU solve on the same context (its own counter) can never look like an answer
+                        ocfinal::set_args(ctx, 0, (1ull << 62) | ++ctx->p2p_seq, fa);
                         p2p_wait_seq = fa.seq;
                         fa.nranks = nranks; fa.my_rank = rank;
                         for (int r2 = 0; r2 < nranks; r2++)
