@@ -43,7 +43,3 @@ def room_grid(room, step=0.05):
     L, H = room["room_length"], room["room_height"]
     Nx, Ny = int(L // step + 1), int(H // step + 1)
     return L, H, Ny, Nx, np.linspace(0, L, Nx), np.linspace(0, H, Ny)
-
-
-def pytest_sessionfinish(session, exitstatus):
-    np.seterr(all="warn")
