@@ -341,31 +341,15 @@ struct Solver {
         fused_rc = forced_rc > 0 ? forced_rc : fused::plan_chunk_rows(Nx, Ny, n_sm, 1, 0);
         fused_gy = (Ny + fused_rc - 1) / fused_rc;
     }
-    template <int NE>
-    int launch_fused_ne(const fused::Args &a) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(fused::Smem)));
-            attr_done = true;
-        }
+    fused::MapCache maps;  // TMA descriptors of this solve's arrays
+    int launch_fused(int ne, fused::Args &a) {
+        fused::set_tensor_maps(a, Ny, &maps);
         dim3 grid(fused_gx, fused_gy);
-        begin(0, 8.0 * (double)n * (5 + NE));  // y, f, coef in; y_new, f_new, NE phi slices out
-        fused::hjb_fused_kernel<NE><<<grid, fused::BX, sizeof(fused::Smem), st>>>(a);
+        begin(0, 8.0 * (double)n * (5 + ne));  // y, f, coef in; y_new, f_new, NE phi slices out
+        OC_CUDA(fused::launch<false>(ne, a, grid, st));
         end();
         launches++;
         return OC_OK;
-    }
-    int launch_fused(int ne, const fused::Args &a) {
-        switch (ne) {
-            case 0: return launch_fused_ne<0>(a);
-            case 1: return launch_fused_ne<1>(a);
-            case 2: return launch_fused_ne<2>(a);
-            case 3: return launch_fused_ne<3>(a);
-            case 4: return launch_fused_ne<4>(a);
-            case 5: return launch_fused_ne<5>(a);
-            default: return launch_fused_ne<6>(a);
-        }
     }
     // sum over tile rows of per-tile partials located at partial+off; host-visible after sync
     int reduce_to_host(size_t off, double *out, int gx = -1, int gy = -1) {
@@ -805,8 +789,9 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
     const int fgy = (Ny + frc - 1) / frc;
     // per room: coef, y, y_new, f, f_new (+ NE_MAX phi slices when only velocities are kept) ; partial sums
     const bool need_scratch = !d_phi;
-    const size_t np = std::max((size_t)2 * nbx * nby, (size_t)fgx * fgy) + 8;
-    const int rs_stride = std::max(nby, fgy) + 8;
+    // (even numbers of doubles: every room's arrays stay 16-byte aligned for the TMA descriptors)
+    const size_t np = ((std::max((size_t)2 * nbx * nby, (size_t)fgx * fgy) + 8) + 1) & ~(size_t)1;
+    const int rs_stride = ((std::max(nby, fgy) + 8) + 1) & ~1;
     const size_t per_room = (5 + (need_scratch ? fused::NE_MAX : 0)) * n + np + 3 * (size_t)rs_stride;
     const size_t need = per_room * n_rooms * sizeof(double);
     if (ctx->batch_ws_bytes < need) {

@@ -339,9 +339,10 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
                          gy_f <= fused::MAX_FINAL_ROWS && !prm->forced_h;
     if (use_p2p && (rc0 = ocfinal::ensure(ctx, 1))) return rc0;
     // ---- workspace: per local band 5 arrays + partials (+ phi scratch)
-    const size_t per_band = 5 * n_store + (size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64 +
-                            ((want_v && !d_phi) ? (size_t)fused::NE_MAX * (band_rows + 2) * Nx : 0);
-    const int seg = std::max(gy_f, gy_t);  // row sums per band
+    // (every piece is an even number of doubles: the band arrays stay 16-byte aligned for the TMA descriptors)
+    const size_t n_partial = (((size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64) + 1) & ~(size_t)1;
+    const size_t per_band = 5 * n_store + n_partial + ((want_v && !d_phi) ? (size_t)fused::NE_MAX * (band_rows + 2) * Nx : 0);
+    const int seg = (std::max(gy_f, gy_t) + 1) & ~1;  // row sums per band
     const size_t need = (per_band * nb_local + (size_t)2 * seg * nbands + 64) * sizeof(double);
     if (ctx->dist_ws_bytes < need) {
         if (ctx->dist_ws) cudaFree(ctx->dist_ws);
@@ -375,7 +376,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
             double *pb = (double *)ctx->p2p_buf;
             b.y = pb; b.ynew = pb + n_store; b.f = pb + 2 * n_store; b.fnew = pb + 3 * n_store;
         }
-        b.partial = wsp; wsp += (size_t)2 * gx_t * gy_t + (size_t)gx_f * gy_f + 64;
+        b.partial = wsp; wsp += n_partial;
         b.gy_fused = gy_f; b.gy_tiles = gy_t;
         b.V = d_V; b.m = d_m;
         b.io_row0 = dist ? b.v.own0 : 0;
@@ -521,22 +522,10 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     }
     stats->h0 = h_abs;
 
-    static bool attr_done[2][fused::NE_MAX + 1] = {};
-    auto launch_fused = [&](int ne, const fused::Args &fa, dim3 grid) -> int {
-#define CASE(NE)                                                                                                         \
-    case NE:                                                                                                             \
-        if (!attr_done[use_p2p][NE]) {                                                                                   \
-            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)sizeof(fused::Smem)));                                                     \
-            OC_CUDA(cudaFuncSetAttribute(fused::hjb_fused_kernel<NE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         (int)sizeof(fused::Smem)));                                                     \
-            attr_done[use_p2p][NE] = true;                                                                               \
-        }                                                                                                                \
-        if (use_p2p) fused::hjb_fused_kernel<NE, true><<<grid, fused::BX, sizeof(fused::Smem), st>>>(fa);                 \
-        else fused::hjb_fused_kernel<NE, false><<<grid, fused::BX, sizeof(fused::Smem), st>>>(fa);                       \
-        break;
-        switch (ne) { CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) }
-#undef CASE
+    fused::MapCache maps;  // TMA descriptors of the band arrays
+    auto launch_fused = [&](int ne, fused::Args &fa, dim3 grid) -> int {
+        fused::set_tensor_maps(fa, rows_store, &maps);
+        OC_CUDA(use_p2p ? fused::launch<true>(ne, fa, grid, st) : fused::launch<false>(ne, fa, grid, st));
         launches++;
         return OC_OK;
     };

@@ -6,20 +6,35 @@
 // phi slices once: 40 B/cell/attempt + 8 B/cell/emitted slice instead of the 312 B/cell/attempt of the
 // stage-wise formulation.
 //
-// Scheme ("2.5-D" streaming): a CTA owns BX = 256 consecutive columns and marches down a chunk of rows.
+// Scheme ("2.5-D" streaming): a CTA owns BX = 128 consecutive columns and marches down a chunk of rows.
 // Thread t owns ONE column; all RK state of that column lives in its registers as short row windows.
-// At iteration r the CTA loads row r (stage 1 input), and stage s = 2..7 evaluates the stencil on row
+// At iteration r the CTA receives row r (stage 1 input), and stage s = 2..7 evaluates the stencil on row
 // r-(s-1), i.e. every stage lags one row behind the previous one, so the 3-row stencil windows of all
-// six stage inputs are register-resident.  Only the left/right neighbours cross threads: each stage
-// input row is published once to a double-buffered shared-memory line (one __syncthreads per row).
-// Rows of y, f, coef are staged ahead of use through an 8-deep cp.async ring in shared memory.
+// six stage inputs are register-resident.  Only the left/right neighbours cross threads: the stage
+// input rows are published once per row to a double-buffered shared-memory line, two stages per 16-byte
+// element (3 STS.128 + 6 LDS.128 per thread and row; one __syncthreads per row).
+// Rows of y, f, coef are staged ahead of use in shared memory by the TMA unit: tiles of GR = 6 rows x 128 columns,
+// one `cp.async.bulk.tensor.2d` per field and row group, issued by one elected thread while the previous group is
+// being consumed (double buffered, completion tracked by one mbarrier per buffer; SASS: UTMALDG + SYNCS).  Columns
+// outside the grid are zero-filled by the TMA unit and never read: the mirror ghost columns are read from the
+// mirrored position inside the staged row.  Row groups that reach across the top or bottom edge of the grid (mirror
+// ghost rows: a different, descending source row each) are staged row by row with 1-D bulk copies (UBLKCP) on the
+// same mbarrier.  Grids with an odd number of columns (rows not 16-byte aligned) take the per-thread `cp.async`
+// (LDGSTS) variant of the same kernel (template parameter BULK = false).
 // Six stencil applications consume HALO = 6 columns per side (8 allocated for 64-byte aligned rows) and
-// 6 rows above/below the chunk, which are recomputed redundantly (about 7 % + 5 % extra work).
+// 6 rows above/below the chunk, which are recomputed redundantly.
 //
 // Arithmetic: FP64, FMA contraction allowed.  The stage combination is evaluated as
-// y + (h a_s1) k_1 + (h a_s2) k_2 + ... with premultiplied coefficients; it differs from scipy's
-// (sum_j a_sj k_j) * h by rounding only (parity bar 1e-10, observed ~1e-13).
+// y + (h a_s1) k_1 + (h a_s2) k_2 + ... with premultiplied coefficients, and the RHS (optimals.py:154-162)
+// as  A_w * (N + S + W + E) + d_w * C  with A_w = A, d_w = -(4 A + coef) in the room and A_w = d_w = 0 in
+// walls; both differ from the reference's evaluation order by rounding only (parity bar 1e-10, observed
+// ~1e-13).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
 
 namespace fused {
 
@@ -36,22 +51,20 @@ constexpr int BX = OC_BX;           // threads per CTA = columns per tile incl. 
 constexpr int HX = 8;               // halo columns per side (6 needed)
 constexpr int VX = BX - 2 * HX;     // valid output columns per tile (112)
 constexpr int HY = 6;               // halo rows per side
-constexpr int PF = OC_PF;           // cp.async ring depth (rows): rows r .. r+PD
-constexpr int PD = OC_PD;           // prefetch distance (rows in flight)
-constexpr int UNROLL = 12;          // rows per unrolled loop body (multiple of PF and of 2)
-static_assert(UNROLL % PF == 0 && UNROLL % 2 == 0 && PD < PF, "ring / unroll geometry");
+constexpr int PF = OC_PF;           // LDGSTS variant: staging ring depth (rows): rows r .. r+PD
+constexpr int PD = OC_PD;           // LDGSTS variant: prefetch distance (rows in flight)
+constexpr int GR = 6;               // TMA variant: rows per staged tile (row group)
+constexpr int NG = 2;               // TMA variant: tile buffers (one in use, one in flight)
+constexpr int UNROLL = 12;          // rows per unrolled loop body (multiple of PF, of NG*GR and of 2)
+static_assert(UNROLL % PF == 0 && UNROLL % 2 == 0 && PD < PF && UNROLL == NG * GR && PF == GR, "ring / unroll geometry");
 #ifndef OC_CTAS
 #define OC_CTAS 2
 #endif
-#if !defined(OC_BRANCHY) && !defined(OC_BRANCHLESS)
-#define OC_BRANCHLESS 1
-#endif
-#if !defined(OC_VREGCONST) && !defined(OC_LDSCONST) && defined(OC_BRANCHLESS)
+#ifndef OC_VREGCONST
 #define OC_VREGCONST 3
 #endif
-// 2 CTAs (8 warps) per SM with 192 registers/thread beat 3 CTAs at 164: the row body is one long straight-line block
-// and the extra registers buy instruction-level parallelism across the six stage chains (measured 0.75 vs 0.70 of
-// the HBM peak, profiles/r1_fused_v4.md)
+// 2 CTAs (8 warps) per SM with ~216 registers/thread beat 3 CTAs at 164: the row body is one long straight-line block
+// and the extra registers buy instruction-level parallelism across the six stage chains (profiles/r1_fused_v4.md)
 constexpr int CTAS_PER_SM = OC_CTAS;
 constexpr int NE_MAX = 6;           // dense-output samples per launch
 
@@ -76,7 +89,10 @@ inline int plan_chunk_rows(int Nx, int rows, int n_sm, int copies, int must_divi
 constexpr int P2P_MAX_RANKS = 8;    // one NVSwitch box
 constexpr int P2P_INBOX_STRIDE = 64; // doubles per (parity, rank) inbox slot: <= 62 chunk-row sums + the sequence number
 
-struct Args {
+struct alignas(64) Args {
+    // TMA descriptors of y, k1, coef as 2-D (storage rows, Nx) FP64 tensors with a (GR, BX) box; valid when tma != 0
+    CUtensorMap tm_y, tm_k1, tm_coef;
+    int tma;
     const double *y, *k1, *coef;
     double *ynew, *k7, *partial;
     double *phi[NE_MAX];
@@ -115,10 +131,7 @@ struct Args {
 };
 constexpr int MAX_FINAL_ROWS = 2 * 6 * (BX + 2) - 8;  // chunk-row sums are staged in the (then idle) exchange buffer
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
+// ---- per-thread cp.async (LDGSTS) staging: the BULK = false variant
 // predicated forms: the unrolled row body has no divergent region (a branch around the loads / stores makes ptxas save
 // and restore the uniform registers that hold the RK coefficients on both sides of it)
 __device__ __forceinline__ void cp_async8_if(void *smem, const void *gmem, bool ok) {
@@ -133,25 +146,72 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- bulk-async (TMA) staging: the BULK = true variant
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// one row segment global -> shared; completion (bytes) is signalled on `bar`.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// one (GR x BX) tile global -> shared through a tensor map; out-of-range elements are zero-filled
+__device__ __forceinline__ void tma_g2s_2d(unsigned smem, const CUtensorMap *map, int cx, int cy, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(cx), "r"(cy), "r"(bar) : "memory");
+}
+// true on exactly one lane of a converged warp (uniform predicate: the region it guards is issued once per warp)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(unsigned smem, const void *gmem, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OC_WAITU_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OC_DONEU_%=;\n"
+        "bra OC_WAITU_%=;\n"
+        "OC_DONEU_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OC_DONE_%=;\n"
+        "bra OC_WAIT_%=;\n"
+        "OC_DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 // optimals.py:154-162.  Mirror ghosts (:149-152) need no special case here: rows/columns outside the grid
 // are LOADED from their mirror image (row -j -> row j, row Ny-1+j -> Ny-1-j), the stencil commutes with
 // that reflection, so every stage input is automatically even about the boundary and the value the
 // reference reads from its ghost cell (ghost(-1) = value(1)) is exactly what sits in the halo.
 // The newest row `dn` of the stage input is produced in the same iteration, so the evaluation is split
 // into a part that does not depend on it (`pre`) and one FMA that does: the serial chain through the six
-// stages of one row iteration is 2 FMAs per stage.
-__device__ __forceinline__ double rhs_pre(double up, double lf, double rt, double C, double cf, double A) {
-    double S = (up + lf) + fma(-4.0, C, rt);
-    return fma(A, S, -(cf * C));
+// stages of one row iteration is 2 FMAs per stage, with no select on it (walls: A_w = d_w = 0).
+__device__ __forceinline__ double rhs_pre(double up, double lf, double rt, double C, double Aw, double dw) {
+    return fma(Aw, (up + lf) + rt, dw * C);
 }
-__device__ __forceinline__ double rhs_fin(double pre, double dn, double cf, double A) {
-    double r = fma(A, dn, pre);
-#ifdef OC_WALLINT
-    return (__double2hiint(cf) == 0x7ff80000) ? 0.0 : r;  // wall marker written by prep_kernel (integer pipe)
-#else
-    return (cf != cf) ? 0.0 : r;  // wall: optimals.py:162
-#endif
-}
+__device__ __forceinline__ double rhs_fin(double pre, double dn, double Aw) { return fma(Aw, dn, pre); }
 
 // 1/x for finite x > 0 (the error scale is >= atol): hardware seed + two Newton steps (~1e-16), no slow path
 __device__ __forceinline__ double rcp_pos(double x) {
@@ -164,104 +224,125 @@ __device__ __forceinline__ double rcp_pos(double x) {
     return r;
 }
 
-struct Smem {
-    double ex[2][6][BX + 2];   // published stage-input rows (u2..u6, y_new), double buffered
-    double pf[PF][3][BX];      // cp.async ring: y, k1, coef
+struct __align__(128) Smem {
+    double pf[NG][3][GR][BX];  // staged rows of y, k1, coef: NG tiles (TMA) / one ring of PF = GR row slots (LDGSTS)
+    double2 ex[2][3][BX + 2];  // published stage-input rows, double buffered: (u2,u3), (u4,u5), (u6,y_new)
+    double cst[(1 + NE_MAX) * 6];  // h*E and the dense-output weights (made opaque to the compiler, see below)
     double red[BX / 32];
-#if defined(OC_LDSCONST) || defined(OC_VREGCONST)
-    double cst[(1 + NE_MAX) * 6];  // h*E and the dense-output weights, read as broadcast LDS.128 (frees uniform registers)
-#endif
+    unsigned long long full[NG];   // one mbarrier per tile buffer (TMA)
 };
+static_assert(sizeof(double2) * 2 * 3 * (BX + 2) >= sizeof(double) * MAX_FINAL_ROWS, "final reduction staging");
 
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-template <int NE, bool P2P = false>
-__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int NE, bool P2P = false, bool BULK = true>
+__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid_constant__ Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    const int gx = blockIdx.x * VX - HX + tid;
-    const int gxm = min(max(mirror(gx, a.Nx), 0), a.Nx - 1);  // column this thread loads (clamped far outside)
+    const int x0 = blockIdx.x * VX - HX;                            // global column of tile position 0
+    const int gx = x0 + tid;
+    const int c0 = max(x0, 0), c1 = min(x0 + BX, a.Nx);             // columns of the grid this tile covers
+    const int gxm = min(max(mirror(gx, a.Nx), c0), c1 - 1);         // column this thread's state comes from
+    const int lt = BULK ? gxm - x0 : tid;                           // its position in the staged row
     const int y0 = a.own0 + blockIdx.y * a.RC;
     const int y1 = min(y0 + a.RC, a.own1);
     const bool col_out = tid >= HX && tid < BX - HX && gx < a.Nx;  // columns this thread stores
     const int phi_shift = (a.row_base - a.phi_row_base) * a.Nx;    // phi slices may start at another global row
 
-    for (int i = tid; i < 2 * 6 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = 0.0;
-#if defined(OC_LDSCONST) || defined(OC_VREGCONST)
+    for (int i = tid; i < 2 * 3 * (BX + 2); i += BX) (&sm.ex[0][0][0])[i] = make_double2(0.0, 0.0);
     if (tid < 6) {
         const int j = tid == 0 ? 0 : tid + 1;  // stages 1,3,4,5,6,7 (B[1] = E[1] = P[1] = 0)
         sm.cst[tid] = a.he[j];
 #pragma unroll
         for (int ee = 0; ee < NE; ee++) sm.cst[6 * (ee + 1) + tid] = a.w[ee][j];
     }
-#endif
+    if (BULK && tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NG; s++) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // shared-memory window addresses, computed once (opaque: ptxas would otherwise re-derive them from SR_CgaCtaId at every use)
+    unsigned sm_pf = (unsigned)__cvta_generic_to_shared(&sm.pf[0][0][0][0]);
+    unsigned sm_full = (unsigned)__cvta_generic_to_shared(&sm.full[0]);
+    asm volatile("" : "+r"(sm_pf), "+r"(sm_full));
 
     // windows, indexed by lag (row r - lag)
     // all windows are registers.  Shared memory is the bottleneck resource of this kernel (every LDS.64 of a
     // warp costs 2 cycles of the SM's 128 B/cycle), so each loaded value is read from the ring exactly once.
-    double yw[7], k1w[7], cw[7], k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
+    double yw[7], k1w[7], Aw[7], dw[7], k2w[5], k3w[7], k4w[7], k5w[7], k6w[7];
     double u2[3], u3[4], u4[5], u5[6], u6[7], un[8];
 #pragma unroll
-    for (int i = 0; i < 7; i++) { yw[i] = 0; k1w[i] = 0; cw[i] = 0; k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
+    for (int i = 0; i < 7; i++) { yw[i] = 0; k1w[i] = 0; Aw[i] = 0; dw[i] = 0; k3w[i] = 0; k4w[i] = 0; k5w[i] = 0; k6w[i] = 0; }
 #pragma unroll
     for (int i = 0; i < 5; i++) k2w[i] = 0;
     u2[0] = u2[1] = u2[2] = 0; u3[1] = u3[2] = u3[3] = 0; u4[2] = u4[3] = u4[4] = 0;
     u5[3] = u5[4] = u5[5] = 0; u6[4] = u6[5] = u6[6] = 0; un[5] = un[6] = un[7] = 0;
 
     const int r_begin = y0 - HY, r_end = y1 + HY;  // rows loaded: [r_begin, r_end)
+    const unsigned row_bytes = (unsigned)(c1 - c0) * 8u;
     // ring slot of row `row` = (row - r_begin) mod PF, tracked incrementally (PF is not a power of two)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+    constexpr unsigned TILE_BYTES = 3u * GR * BX * 8u, FIELD_BYTES = GR * BX * 8u, ROW_BYTES = BX * 8u;
+    // TMA variant: stage the row group that starts at row `ga` into tile buffer `slot` (one elected thread)
+    auto issue_group = [&](int ga, int slot) {
+        if (warp == 0 && ga < r_end && elect_one()) {
+            const unsigned bar = sm_full + 8u * slot, dst = sm_pf + TILE_BYTES * slot;
+            if (ga >= 0 && ga + GR <= a.Ny) {
+                mbar_expect_tx_u32(bar, TILE_BYTES);
+                tma_g2s_2d(dst, &a.tm_y, x0, ga - a.row_base, bar);
+                tma_g2s_2d(dst + FIELD_BYTES, &a.tm_k1, x0, ga - a.row_base, bar);
+                tma_g2s_2d(dst + 2u * FIELD_BYTES, &a.tm_coef, x0, ga - a.row_base, bar);
+            } else {  // the group reaches across the top / bottom edge of the grid: mirror ghost rows, one source row each
+                mbar_expect_tx_u32(bar, 3u * GR * row_bytes);
+#pragma unroll 1
+                for (int j = 0; j < GR; j++) {
+                    const int rm = min(max(mirror(ga + j, a.Ny), 0), a.Ny - 1);
+                    const int g = (rm - a.row_base) * a.Nx + c0;  // element offsets fit 32 bits (one field < 2^31 elements)
+                    const unsigned d = dst + ROW_BYTES * j + 8u * (c0 - x0);
+                    bulk_g2s_u32(d, a.y + g, row_bytes, bar);
+                    bulk_g2s_u32(d + FIELD_BYTES, a.k1 + g, row_bytes, bar);
+                    bulk_g2s_u32(d + 2u * FIELD_BYTES, a.coef + g, row_bytes, bar);
+                }
+            }
+        }
+    };
+    // LDGSTS variant: ring slot of row `row` = (row - r_begin) mod PF
     auto issue = [&](int row, int slot) {
-#ifdef OC_BRANCHLESS
-        {
-            const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
-            const int g = (rm - a.row_base) * a.Nx + gxm;
-            const bool ok = row < r_end;
-            cp_async8_if(&sm.pf[slot][0][tid], a.y + g, ok);
-            cp_async8_if(&sm.pf[slot][1][tid], a.k1 + g, ok);
-            cp_async8_if(&sm.pf[slot][2][tid], a.coef + g, ok);
-        }
-        if (false) {
-#else
-        if (row < r_end) {
-#endif
-            // element offsets fit 32 bits (one field < 2^31 elements); one IMAD instead of 64-bit multiplies
-            const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
-            const int g = (rm - a.row_base) * a.Nx + gxm;
-            cp_async8(&sm.pf[slot][0][tid], a.y + g);
-            cp_async8(&sm.pf[slot][1][tid], a.k1 + g);
-            cp_async8(&sm.pf[slot][2][tid], a.coef + g);
-        }
+        const int rm = min(max(mirror(row, a.Ny), 0), a.Ny - 1);
+        const int g = (rm - a.row_base) * a.Nx + gxm;
+        const bool ok = row < r_end;
+        cp_async8_if(&sm.pf[0][0][slot][tid], a.y + g, ok);
+        cp_async8_if(&sm.pf[0][1][slot][tid], a.k1 + g, ok);
+        cp_async8_if(&sm.pf[0][2][slot][tid], a.coef + g, ok);
         cp_async_commit();  // one group per iteration, possibly empty
     };
 
+    if (BULK) issue_group(r_begin, 0);
+    else {
 #pragma unroll 1
-    for (int q = 0; q < PD; q++) issue(r_begin + q, q);
-    __syncthreads();
+        for (int q = 0; q < PD; q++) issue(r_begin + q, q);
+    }
 
-#ifdef OC_VREGCONST
     // The ~47 FP64 constants of the body do not fit the uniform register file (ptxas then spills uniform registers
     // through MOV.SPILL / R2UR.FILL every row).  With 2 CTAs/SM there are spare vector registers: the dense-output
-    // weights of the first OC_VREGCONST samples (and h*E) are pinned there by making them opaque to the compiler.
+    // weights of the first OC_VREGCONST samples (and h*E) are pinned there by making them opaque to the compiler
+    // (read back from shared memory: a value ptxas could re-derive from the constant bank would not stay in a register).
     constexpr int NV = NE < OC_VREGCONST ? NE : OC_VREGCONST;
     double wv[NV > 0 ? NV : 1][6], hev[6];
-    // (read back from shared memory: a value ptxas could re-derive from the constant bank would not stay in a register)
-    __syncthreads();
 #pragma unroll
     for (int ee = 0; ee < NV; ee++)
 #pragma unroll
         for (int j = 0; j < 6; j++) wv[ee][j] = sm.cst[6 * (ee + 1) + j];
-#ifdef OC_VREGCONST_E
-#pragma unroll
-    for (int j = 0; j < 6; j++) hev[j] = sm.cst[j];
-#else
 #pragma unroll
     for (int j = 0; j < 6; j++) hev[j] = a.he[j == 0 ? 0 : j + 1];
-#endif
-#endif
+    const double dwall = -4.0 * a.A;  // d_w = -(4A + coef)
+
     double acc = 0.0;
-    // The row loop is unrolled by the ring depth: inside the unrolled body the ring slot of every window row, the
-    // exchange buffer and the register holding each window entry are compile-time constants -- no address
+    unsigned ph_base = 0;  // mbarrier phase of the tile buffers during this unrolled body
+    // The row loop is unrolled by (a multiple of) the ring depth: inside the unrolled body the ring slot of every row,
+    // the exchange buffer and the register holding each window entry are compile-time constants -- no address
     // arithmetic and no register moves for the shifting windows.
 #pragma unroll 1
     for (int rb = r_begin; rb < r_end; rb += UNROLL) {
@@ -272,20 +353,44 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         // unrolled body is one straight-line block and the window shifts below are pure register renaming
         const int s0 = uu % PF;      // ring slot of row r: (r - r_begin) mod PF
         const int buf = uu & 1;
-        issue(r + PD, (s0 + PD) % PF);
-        cp_async_wait<PD>();
-        yw[0] = sm.pf[s0][0][tid];
-        k1w[0] = sm.pf[s0][1][tid];
-        cw[0] = sm.pf[s0][2][tid];
-        const double *exp_ = &sm.ex[buf ^ 1][0][tid];  // previous iteration's rows: [s*(BX+2)] left, [+2] right
-        double *exc = &sm.ex[buf][0][tid + 1];
+        const int gi = uu / GR, gj = uu % GR;  // TMA variant: tile buffer and row inside the tile
+        if (BULK) {
+            if (gj == 0) {
+                // the other buffer was released by the barrier that ended the previous group: refill it, then make sure
+                // this group's tile (in flight since the previous group started) has landed
+                issue_group(r + GR, gi ^ 1);
+                if (r < r_end) mbar_wait_u32(sm_full + 8u * gi, ph_base);
+            }
+        } else {
+            issue(r + PD, (s0 + PD) % PF);
+            cp_async_wait<PD>();
+        }
+        const double *ring = BULK ? &sm.pf[gi][0][gj][lt] : &sm.pf[0][0][s0][lt];
+        yw[0] = ring[0];
+        k1w[0] = ring[GR * BX];
+        {
+            const double cf = ring[2 * GR * BX];
+            const bool wall = cf != cf;             // wall marker written by prep_kernel (optimals.py:162)
+            Aw[0] = wall ? 0.0 : a.A;
+            dw[0] = wall ? 0.0 : dwall - cf;
+        }
+        const double2 *exp_ = &sm.ex[buf ^ 1][0][tid];  // previous iteration's rows: [p*(BX+2)] left, [+2] right
+        double2 *exc = &sm.ex[buf][0][tid + 1];
+#ifdef OC_ABL_NOEX  // ablation (wrong results): no neighbour exchange
+        const double2 l23 = make_double2(u2[1], u3[2]), r23 = l23, l45 = make_double2(u4[3], u5[4]), r45 = l45,
+                      l6n = make_double2(u6[5], un[6]), r6n = l6n;
+#else
+        const double2 l23 = exp_[0], r23 = exp_[2];
+        const double2 l45 = exp_[BX + 2], r45 = exp_[BX + 2 + 2];
+        const double2 l6n = exp_[2 * (BX + 2)], r6n = exp_[2 * (BX + 2) + 2];
+#endif
         // parts of the six stencils that do not depend on this iteration's new rows
-        const double p2 = rhs_pre(u2[2], exp_[0 * (BX + 2)], exp_[0 * (BX + 2) + 2], u2[1], cw[1], a.A);
-        const double p3 = rhs_pre(u3[3], exp_[1 * (BX + 2)], exp_[1 * (BX + 2) + 2], u3[2], cw[2], a.A);
-        const double p4 = rhs_pre(u4[4], exp_[2 * (BX + 2)], exp_[2 * (BX + 2) + 2], u4[3], cw[3], a.A);
-        const double p5 = rhs_pre(u5[5], exp_[3 * (BX + 2)], exp_[3 * (BX + 2) + 2], u5[4], cw[4], a.A);
-        const double p6 = rhs_pre(u6[6], exp_[4 * (BX + 2)], exp_[4 * (BX + 2) + 2], u6[5], cw[5], a.A);
-        const double p7 = rhs_pre(un[7], exp_[5 * (BX + 2)], exp_[5 * (BX + 2) + 2], un[6], cw[6], a.A);
+        const double p2 = rhs_pre(u2[2], l23.x, r23.x, u2[1], Aw[1], dw[1]);
+        const double p3 = rhs_pre(u3[3], l23.y, r23.y, u3[2], Aw[2], dw[2]);
+        const double p4 = rhs_pre(u4[4], l45.x, r45.x, u4[3], Aw[3], dw[3]);
+        const double p5 = rhs_pre(u5[5], l45.y, r45.y, u5[4], Aw[4], dw[4]);
+        const double p6 = rhs_pre(u6[6], l6n.x, r6n.x, u6[5], Aw[5], dw[5]);
+        const double p7 = rhs_pre(un[7], l6n.y, r6n.y, un[6], Aw[6], dw[6]);
         // stage-input partial sums that do not depend on this iteration's new k's (rk.py:63-64, premultiplied by h)
         const double q3 = fma(a.ha3[0], k1w[1], yw[1]);
         const double q4 = fma(a.ha4[1], k2w[2], fma(a.ha4[0], k1w[2], yw[2]));
@@ -294,49 +399,48 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         const double qn = fma(a.hb[4], k5w[5], fma(a.hb[3], k4w[5], fma(a.hb[2], k3w[5], fma(a.hb[0], k1w[5], yw[5]))));
         // ---- the serial chain of this row iteration
         u2[0] = fma(a.ha21, k1w[0], yw[0]);            // stage 2 input on row r
-        k2w[1] = rhs_fin(p2, u2[0], cw[1], a.A);       // k2 on row r-1
+#ifdef OC_CHAIN1
+        // one FMA per stage on the chain: k_s = (A_w h a) k_{s-1} + (A_w q + p); the stage input itself is off the chain
+        k2w[1] = rhs_fin(p2, u2[0], Aw[1]);            // k2 on row r-1
+        k3w[2] = fma(Aw[2] * a.ha3[1], k2w[1], fma(Aw[2], q3, p3));
+        k4w[3] = fma(Aw[3] * a.ha4[2], k3w[2], fma(Aw[3], q4, p4));
+        k5w[4] = fma(Aw[4] * a.ha5[3], k4w[3], fma(Aw[4], q5, p5));
+        k6w[5] = fma(Aw[5] * a.ha6[4], k5w[4], fma(Aw[5], q6, p6));
         u3[1] = fma(a.ha3[1], k2w[1], q3);
-        k3w[2] = rhs_fin(p3, u3[1], cw[2], a.A);       // k3 on row r-2
         u4[2] = fma(a.ha4[2], k3w[2], q4);
-        k4w[3] = rhs_fin(p4, u4[2], cw[3], a.A);       // k4 on row r-3
         u5[3] = fma(a.ha5[3], k4w[3], q5);
-        k5w[4] = rhs_fin(p5, u5[3], cw[4], a.A);       // k5 on row r-4
         u6[4] = fma(a.ha6[4], k5w[4], q6);
-        k6w[5] = rhs_fin(p6, u6[4], cw[5], a.A);       // k6 on row r-5
         un[5] = fma(a.hb[5], k6w[5], qn);              // y_new on row r-5 (rk.py:66; B[1] = 0)
-        const double k7 = rhs_fin(p7, un[5], cw[6], a.A);  // k7 = f(y_new) on row r-6
-        exc[0 * (BX + 2)] = u2[0];
-        exc[1 * (BX + 2)] = u3[1];
-        exc[2 * (BX + 2)] = u4[2];
-        exc[3 * (BX + 2)] = u5[3];
-        exc[4 * (BX + 2)] = u6[4];
-        exc[5 * (BX + 2)] = un[5];
-        // ---- outputs on row r-6
-#if defined(OC_LDSCONST)
+        const double k7 = fma(Aw[6] * a.hb[5], k6w[5], fma(Aw[6], qn, p7));  // k7 = f(y_new) on row r-6
+#else
+        k2w[1] = rhs_fin(p2, u2[0], Aw[1]);            // k2 on row r-1
+        u3[1] = fma(a.ha3[1], k2w[1], q3);
+        k3w[2] = rhs_fin(p3, u3[1], Aw[2]);            // k3 on row r-2
+        u4[2] = fma(a.ha4[2], k3w[2], q4);
+        k4w[3] = rhs_fin(p4, u4[2], Aw[3]);            // k4 on row r-3
+        u5[3] = fma(a.ha5[3], k4w[3], q5);
+        k5w[4] = rhs_fin(p5, u5[3], Aw[4]);            // k5 on row r-4
+        u6[4] = fma(a.ha6[4], k5w[4], q6);
+        k6w[5] = rhs_fin(p6, u6[4], Aw[5]);            // k6 on row r-5
+        un[5] = fma(a.hb[5], k6w[5], qn);              // y_new on row r-5 (rk.py:66; B[1] = 0)
+        const double k7 = rhs_fin(p7, un[5], Aw[6]);   // k7 = f(y_new) on row r-6
+#endif
+#ifndef OC_ABL_NOEX
+        exc[0] = make_double2(u2[0], u3[1]);
+        exc[BX + 2] = make_double2(u4[2], u5[3]);
+        exc[2 * (BX + 2)] = make_double2(u6[4], un[5]);
+#endif
+        // ---- outputs on row r-6.  The arithmetic is unconditional (halo threads compute values nobody reads) and only
+        // the stores and the error accumulation are predicated: no divergent region inside the unrolled body
         {
             const int row = r - 6;
+#ifdef OC_ABL_NOSTORE  // ablation (wrong results): nothing is stored
+            const bool ok = col_out && row >= y0 && row < y1 && a.Nx < 0;
+#else
             const bool ok = col_out && row >= y0 && row < y1;
+#endif
             const int g = (row - a.row_base) * a.Nx + gx;
-            const double2 *cs = reinterpret_cast<const double2 *>(sm.cst);
-            const double2 e01 = cs[0], e23 = cs[1], e45 = cs[2];
-            double e = fma(e45.y, k7, fma(e45.x, k6w[6], fma(e23.y, k5w[6], fma(e23.x, k4w[6], fma(e01.y, k3w[6], e01.x * k1w[6])))));
-            double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
-            double qq = e * rcp_pos(sc);
-            acc = ok ? fma(qq, qq, acc) : acc;
-            st_if(a.ynew + g, un[6], ok);
-            st_if(a.k7 + g, k7, ok);
-#pragma unroll
-            for (int ee = 0; ee < NE; ee++) {
-                const double2 w01 = cs[3 * (ee + 1)], w23 = cs[3 * (ee + 1) + 1], w45 = cs[3 * (ee + 1) + 2];
-                double ph = fma(w45.y, k7, fma(w45.x, k6w[6], fma(w23.y, k5w[6], fma(w23.x, k4w[6], fma(w01.y, k3w[6], fma(w01.x, k1w[6], yw[6]))))));
-                st_if(a.phi[ee] + (g + phi_shift), ph, ok);
-            }
-        }
-#elif defined(OC_VREGCONST)
-        {
-            const int row = r - 6;
-            const bool ok = col_out && row >= y0 && row < y1;
-            const int g = (row - a.row_base) * a.Nx + gx;
+            // rk.py:106,146-147: err = h * K.E ; scale = atol + max(|y|,|y_new|) * rtol
             double e = fma(hev[5], k7, fma(hev[4], k6w[6], fma(hev[3], k5w[6], fma(hev[2], k4w[6], fma(hev[1], k3w[6], hev[0] * k1w[6])))));
             double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
             double qq = e * rcp_pos(sc);
@@ -354,7 +458,11 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
             }
 #pragma unroll
             for (int ee = 0; ee < NE; ee++) {
+                // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
                 double ph;
+#ifdef OC_ABL_NOPHI  // ablation (wrong results): no dense-output arithmetic
+                if (true) ph = k7; else
+#endif
                 if (ee < NV)
                     ph = fma(wv[ee][5], k7, fma(wv[ee][4], k6w[6], fma(wv[ee][3], k5w[6], fma(wv[ee][2], k4w[6],
                              fma(wv[ee][1], k3w[6], fma(wv[ee][0], k1w[6], yw[6]))))));
@@ -364,54 +472,12 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
                 st_if(a.phi[ee] + (g + phi_shift), ph, ok);
             }
         }
-#elif defined(OC_BRANCHLESS)
-        {
-            // the arithmetic is unconditional (halo threads compute values nobody reads) and only the stores and the
-            // error accumulation are predicated: no divergent region inside the unrolled body
-            const int row = r - 6;
-            const bool ok = col_out && row >= y0 && row < y1;
-            const int g = (row - a.row_base) * a.Nx + gx;
-            double e = fma(a.he[6], k7, fma(a.he[5], k6w[6], fma(a.he[4], k5w[6], fma(a.he[3], k4w[6],
-                           fma(a.he[2], k3w[6], a.he[0] * k1w[6])))));
-            double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
-            double qq = e * rcp_pos(sc);
-            acc = ok ? fma(qq, qq, acc) : acc;
-            st_if(a.ynew + g, un[6], ok);
-            st_if(a.k7 + g, k7, ok);
-#pragma unroll
-            for (int ee = 0; ee < NE; ee++) {
-                double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
-                                fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
-                st_if(a.phi[ee] + (g + phi_shift), ph, ok);
-            }
-        }
-#else
-        {
-            const int row = r - 6;
-            if (col_out && row >= y0 && row < y1) {
-                const int g = (row - a.row_base) * a.Nx + gx;
-                a.ynew[g] = un[6];
-                a.k7[g] = k7;
-                // rk.py:106,146-147: err = h * K.E ; scale = atol + max(|y|,|y_new|) * rtol
-                double e = fma(a.he[6], k7, fma(a.he[5], k6w[6], fma(a.he[4], k5w[6], fma(a.he[3], k4w[6],
-                               fma(a.he[2], k3w[6], a.he[0] * k1w[6])))));
-                double sc = fma(fmax(fabs(yw[6]), fabs(un[6])), a.rtol, a.atol);
-                double qq = e * rcp_pos(sc);
-                acc = fma(qq, qq, acc);
-#pragma unroll
-                for (int ee = 0; ee < NE; ee++) {
-                    // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
-                    double ph = fma(a.w[ee][6], k7, fma(a.w[ee][5], k6w[6], fma(a.w[ee][4], k5w[6],
-                                    fma(a.w[ee][3], k4w[6], fma(a.w[ee][2], k3w[6], fma(a.w[ee][0], k1w[6], yw[6]))))));
-                    a.phi[ee][g + phi_shift] = ph;
-                }
-            }
-        }
-#endif
+#ifndef OC_ABL_NOSYNC
         __syncthreads();
+#endif
         // ---- shift windows by one row (pure renaming inside the unrolled body)
 #pragma unroll
-        for (int l = 6; l > 0; l--) { yw[l] = yw[l - 1]; k1w[l] = k1w[l - 1]; cw[l] = cw[l - 1]; }
+        for (int l = 6; l > 0; l--) { yw[l] = yw[l - 1]; k1w[l] = k1w[l - 1]; Aw[l] = Aw[l - 1]; dw[l] = dw[l - 1]; }
         k2w[4] = k2w[3]; k2w[3] = k2w[2]; k2w[2] = k2w[1];
         k3w[6] = k3w[5]; k3w[5] = k3w[4]; k3w[4] = k3w[3]; k3w[3] = k3w[2];
         k4w[6] = k4w[5]; k4w[5] = k4w[4]; k4w[4] = k4w[3];
@@ -424,8 +490,9 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         u6[6] = u6[5]; u6[5] = u6[4];
         un[7] = un[6]; un[6] = un[5];
       }
+      ph_base ^= 1u;  // every tile buffer is used once per unrolled body
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
     // fixed-order CTA reduction of the error partial sum
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -449,7 +516,7 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    double *rows = &sm.ex[0][0][0];
+    double *rows = reinterpret_cast<double *>(&sm.ex[0][0][0]);
     const int ngx = gridDim.x, gy = gridDim.y, lane = tid & 31;
     for (int row = tid >> 5; row < gy; row += BX / 32) {
         // the 8 warps of rowgroup_sum_kernel's 256 threads, emulated by this warp: all loads first (independent, in
@@ -513,6 +580,88 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const Args a
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(a.result_seq) = a.seq;
     }
+}
+
+// Launch of one step attempt.  BULK staging needs 16-byte aligned rows: an even number of columns and 16-byte aligned
+// field pointers (phi slices are only stored to, with 8-byte stores).
+inline bool bulk_ok(const Args &a) {
+#ifdef OC_NO_BULK
+    return false;
+#else
+    return a.tma != 0 && (a.Nx % 2 == 0) && (((uintptr_t)a.y | (uintptr_t)a.k1 | (uintptr_t)a.coef) % 16 == 0);
+#endif
+}
+
+// Host side of the TMA staging: descriptor of one field stored as (rows, Nx) FP64 with a (GR, BX) box.  The encoder is
+// a driver entry point (no link-time dependency on libcuda).  Returns false when the field cannot be described
+// (odd Nx: row pitch not a multiple of 16 bytes) -- the solver then launches the LDGSTS variant.
+inline bool make_tensor_map(CUtensorMap *tm, const double *base, int rows, int Nx) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode || Nx % 2 != 0 || ((uintptr_t)base % 16) != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)Nx, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)Nx * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)BX, (cuuint32_t)GR};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// descriptors of the three fields an attempt reads (storage of `rows` rows each); sets a.tma.  A solve alternates between
+// a handful of arrays (y / y_new, f / f_new, coef): the encoded descriptors are kept in a small per-solve cache.
+struct MapCache {
+    static constexpr int CAP = 8;
+    const double *base[CAP];
+    int rows[CAP], n = 0;
+    CUtensorMap tm[CAP];
+    bool get(const double *b, int r, int Nx, CUtensorMap *out) {
+        for (int i = 0; i < n; i++)
+            if (base[i] == b && rows[i] == r) { *out = tm[i]; return true; }
+        CUtensorMap t;
+        if (!make_tensor_map(&t, b, r, Nx)) return false;
+        if (n < CAP) { base[n] = b; rows[n] = r; tm[n] = t; n++; }
+        *out = t;
+        return true;
+    }
+};
+inline void set_tensor_maps(Args &a, int rows, MapCache *cache = nullptr) {
+    MapCache local;
+    MapCache &c = cache ? *cache : local;
+    a.tma = c.get(a.y, rows, a.Nx, &a.tm_y) && c.get(a.k1, rows, a.Nx, &a.tm_k1) && c.get(a.coef, rows, a.Nx, &a.tm_coef);
+}
+template <int NE, bool P2P, bool BULK>
+inline cudaError_t launch_one(const Args &a, dim3 grid, cudaStream_t st) {
+    if (sizeof(Smem) > 48 * 1024) {  // per device, cheap: set on every launch (only deep rings need it)
+        cudaError_t e = cudaFuncSetAttribute(hjb_fused_kernel<NE, P2P, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+    }
+    hjb_fused_kernel<NE, P2P, BULK><<<grid, BX, sizeof(Smem), st>>>(a);
+    return cudaSuccess;
+}
+template <bool P2P>
+inline cudaError_t launch(int ne, const Args &a, dim3 grid, cudaStream_t st) {
+    const bool bulk = bulk_ok(a);
+#define OC_FUSED_CASE(NE) \
+    case NE: return bulk ? launch_one<NE, P2P, true>(a, grid, st) : launch_one<NE, P2P, false>(a, grid, st);
+    switch (ne) {
+        OC_FUSED_CASE(0) OC_FUSED_CASE(1) OC_FUSED_CASE(2) OC_FUSED_CASE(3) OC_FUSED_CASE(4) OC_FUSED_CASE(5)
+        default: return bulk ? launch_one<6, P2P, true>(a, grid, st) : launch_one<6, P2P, false>(a, grid, st);
+    }
+#undef OC_FUSED_CASE
 }
 
 }  // namespace fused
