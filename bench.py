@@ -198,199 +198,157 @@ def run_reference_arm(args):
     return 0
 
 
-# ----------------------------------------------------------------------------------------------- GPU arm, N > 1
-def run_dist(args, world, rank, local_rank):
-    """N > 1: the 16384 x (2048 N) slalom room row-decomposed over N GPUs (one band per rank): NCCL halo exchange of
-    6 rows of y and f per accepted step + one all-gather of the per-chunk error sums per attempt."""
+# ----------------------------------------------------------------------------------------------- GPU arm
+FP64_INST_PER_PAIR = 1130.0   # FP64-pipe warp instructions per lane of one pair_force call, measured with ncu
+                              # (profiles/r2_gcfm_pair_fp64.md: sm__inst_executed_pipe_fp64 of pair_probe_kernel / pairs)
+
+
+def pin_numa(local_rank):
+    """bind this process to the CPUs of the NUMA node its GPU hangs off (pinned host buffers are then allocated next to
+    the GPU's PCIe root: 8 ranks uploading at once do not cross the socket interconnect)"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
+
+
+def smooth_density(nx, rows, row0):
+    """synthetic crowd density m >= 0 of the band starting at global row row0: smooth bumps, 0 <= m <= 1 (the live density
+    of simulations.py:432-435 has the same range)"""
+    x = np.arange(nx, dtype=np.float64) * 0.05
+    y = (row0 + np.arange(rows, dtype=np.float64)) * 0.05
+    return 0.5 * (1.0 + np.sin(2 * np.pi * x / 97.0)[None, :] * np.cos(2 * np.pi * y / 61.0)[:, None])
+
+
+def parity_block(world, rank, note):
+    """untimed multi-GPU parity, through the same code path the timed region used (peer-memory step kernel):
+    (1) HJB: a reduced room (2048 x 256 N nodes, smooth random density > 0, a wall straddling every band edge) solved by
+        the N ranks == the virtual-band solve of the whole grid done locally on every GPU, bit for bit (phi samples,
+        step sizes, error norms); the single-GPU tests tie the virtual-band solve to the oracle;
+    (2) GCFM: simulation(room, T, band=True) == simulation(room, T) on one GPU, bit for bit, incl. the exit order, on a
+        room where agents leave in every band."""
     import contextlib, io
     import torch
     import torch.distributed as dist
     from optimal_crowds_b200 import _lib, dist as ocd, simulations, synthetic
+    with open(os.path.join(REPO, "optimal_crowds_b200", "config.json")) as f:
+        cfg = json.load(f)
+    out = {}
+    # ---- (1)
+    Nx, rows, T = 2048, 256, 0.6
+    Ny = rows * world
+    L, H = (Nx - 1) * 0.05 + 0.025, (Ny - 1) * 0.05 + 0.025
+    rng = np.random.RandomState(11)
+    V = np.zeros((Ny, Nx)); V[0] = V[-1] = -100; V[:, 0] = V[:, -1] = -100
+    for b in range(1, world):
+        V[b * rows - 8: b * rows + 8, 100:1500] = -100       # walls straddling every band edge
+        V[b * rows - 3: b * rows + 3, 1700:1760] = 1.0        # and a target cut by it
+    V[Ny // 2 - 10: Ny // 2 + 10, -1] = 1.0; V[0, 20:40] = 1.0
+    m = 0.2 + 0.8 * rng.uniform(0, 1, (Ny, Nx))
+    m = 0.25 * (m + np.roll(m, 1, 0) + np.roll(m, 1, 1) + np.roll(m, -1, 0))
+    nt = round(T / 0.02)
+    ctx = _lib.Context(L, H, 0.05)
+    own0, own1 = ocd.init_context(ctx)
+    prm = _lib.hjb_params(cfg, fused=1, chunk_rows=32)
+    res = ctx.hjb_solve_band(ctx.to_device(V[own0:own1]), ctx.to_device(m[own0:own1]), prm, T, nt, own=(own0, own1),
+                             trace=True)
+    ctx2 = _lib.Context(L, H, 0.05)
+    ref = ctx2.hjb_solve_band(ctx2.to_device(V), ctx2.to_device(m), prm, T, nt, n_virtual=world, trace=True)
+    ok = np.array_equal(res["trace_h"], ref["trace_h"]) and np.array_equal(res["trace_err"], ref["trace_err"])
+    ok = ok and torch.equal(res["phi"][:, 1:-1], ref["phi"][:, own0:own1])
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["hjb_bitwise"] = bool(flag.item() == 1)
+    out["hjb_case"] = (f"{Nx}x{Ny} nodes, T={T}, {len(res['trace_h'])} attempts, peer-memory exchange: "
+                       f"{bool(getattr(ctx, 'peer_memory', False))}")
+    del res, ref
+    ctx.close(); ctx2.close()
+    # ---- (2)
+    room = synthetic.parity_room(2048, 256 * world, world)
+
+    def run(band):
+        np.random.seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            simu = simulations.simulation(room, 1.2, record=False, chunk_rows=32, band=band)
+            simu._solve_all()
+            for _ in range(58):
+                simu.step(simu.dt)
+        return simu
+
+    a, b = run(True), run(False)
+    ok_state = np.array_equal(a._h_now, b._h_now) and np.array_equal(a._h_timev, b._h_timev) and a.inside == b.inside
+    ok_order = a._exit_order == b._exit_order and len(a._exit_order) > 0
+    own = a._band
+    exits_by_band = np.bincount(np.clip((a._h_now[a._exit_order, 1] / 0.05).astype(int) // (256), 0, world - 1),
+                                minlength=world) if a._exit_order else np.zeros(world, dtype=int)
+    flag = torch.tensor([1 if ok_state else 0, 1 if ok_order else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["gcfm_bitwise"] = bool(flag[0].item() == 1)
+    out["gcfm_exit_order"] = bool(flag[1].item() == 1)
+    out["gcfm_case"] = (f"{a.N} agents, 58 steps, {len(a._exit_order)} exits (per band: {exits_by_band.tolist()}), "
+                        f"band rows {own}")
+    note(f"parity: {out}")
+    return out
+
+
+def run_slalom(args, world, rank, local_rank):
+    """BASELINE configs[3] through the drop-in API: simulations.simulation(room, T) on one GPU, and
+    simulations.simulation(room, T, band=True) under torchrun -- the same room row-decomposed over N GPUs."""
+    import contextlib, io
+    import torch
+    import torch.distributed as dist
+    from optimal_crowds_b200 import _lib, simulations, synthetic
     W, K = max(args.warmup, 0), args.steps
     nx, ny = args.nx, args.band_ny
     Ny = ny * world
-    room = synthetic.slalom_room(nx, Ny, agents=args.agents * world)
-    with open(os.path.join(REPO, "optimal_crowds_b200", "config.json")) as f:
-        cfg = json.load(f)
-    ctx = _lib.Context(room["room_length"], room["room_height"], cfg["grid_step"])
-    assert (ctx.Ny, ctx.Nx) == (Ny, nx)
-    own0, own1 = ocd.init_context(ctx)
-    V = ctx.rasterise_band([], [], list(room["cylinders"].values()), list(room["targets"].values()), own0, ny,
-                           remap=True, wall_value=cfg["hjb_params"]["wall_potential"],
-                           target_value=cfg["hjb_params"]["target_potential"])
-    nt = round(args.T / cfg["dt"])
-    prm = _lib.hjb_params(cfg, fused=1, profile=1)
-    phi = ctx.empty(nt, ny + 2, nx)
-    m_host = torch.zeros((ny, nx), dtype=torch.float64).pin_memory()
-    m_dev = m_host.to("cuda")
-    cells = nx * Ny
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    def solve(m):
-        return ctx.hjb_solve_band(V, m, prm, args.T, nt, own=(own0, own1), out_phi=phi)["stats"]
-
-    for _ in range(W):
-        st = solve(m_dev)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    _lib.launch_count(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nfev_total, step_ms, step_n = 0, 0.0, 0
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        st = solve(m_dev)
-        nfev_total += st["nfev"]; step_ms += st["cls_ms"][0]; step_n += st["cls_launches"][0]
-    ev1.record()
-    barrier()
-    launches = _lib.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ev0.elapsed_time(ev1), step_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, step_ms_max = float(t[0].item()), float(t[1].item())
-    value = nfev_total * cells / (ms_max * 1e-3) / 1e9
-    # e2e: density band as pinned host memory -> H2D inside the timed region, checksum read back
-    for _ in range(max(min(W, 2), 1)):
-        solve(m_host.to("cuda", non_blocking=True))
-        float(phi[nt - 1, 1:-1].sum().item())
-    barrier()
-    t0 = time.perf_counter()
-    nfev_e2e = 0
-    for _ in range(K):
-        st = solve(m_host.to("cuda", non_blocking=True))
-        nfev_e2e += st["nfev"]
-        chk = float(phi[nt - 1, 1:-1].sum().item())
-    barrier()
-    t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = nfev_e2e * cells / (float(t.item()) * 1e-3) / 1e9
-    del phi
-    torch.cuda.empty_cache()
-    # GCFM: one independent band-sized crowd per GPU (a room's sweep is one dependency chain: replicas, SURVEY 8e)
-    np.random.seed(1000 + rank)
-    with contextlib.redirect_stdout(io.StringIO()):
-        simu = simulations.simulation(synthetic.slalom_room(nx, ny, agents=args.agents), args.T, recompute=False,
-                                      record=False, field_storage="phi", fused=1)
-        simu._solve_all()
-    for _ in range(3):
-        simu.step(simu.dt)
-    barrier()
-    g0 = time.perf_counter()
-    agent_steps, dev_ms = 0, 0.0
-    for _ in range(args.gcfm_steps):
-        agent_steps += int(simu._h_status.sum())
-        simu.step(simu.dt)
-        dev_ms += simu._ctx.gcfm_last_ms()
-    barrier()
-    gt = torch.tensor([time.perf_counter() - g0, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
-    dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        attempts = (nfev_total - 2 * K) // 6
-        band_cells = nx * ny
-        alg_bytes = 40.0 * band_cells * attempts + 8.0 * band_cells * nt * K
-        achieved = alg_bytes / (step_ms_max * 1e-3) / 1e9 if step_ms_max > 0 else 0.0
-        line = {"metric": "hjb_gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
-                "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"slalom (BASELINE configs[3]) cylinder field, {nx}x{Ny} grid "
-                                       f"({nx}x{ny} band per GPU; N=8 is the 16384^2 / 100k-agent config), T={args.T} "
-                                       f"(nt={nt} slices), {args.agents * world} agents",
-                           "parallelism": (f"row bands over {world} GPUs; halo rows (6 of y_new, f_new per side) and the "
-                                           "per-chunk error sums are exchanged INSIDE the step launch as NVLink peer "
-                                           "stores (CUDA IPC), NCCL only at solve start") if getattr(ctx, "peer_memory", False)
-                           else (f"row bands over {world} GPUs, NCCL halo exchange (6 rows of y,f per accepted "
-                                 "step) + all-gather of per-chunk error sums per attempt"),
-                           "l2": "inputs larger than L2 (each field 268 MB > 126 MB)",
-                           "formulation": "stage-fused RK45 step (40 B/cell/attempt + 8 B/cell/emitted phi slice)",
-                           "field_storage": "phi", "nfev_per_solve": nfev_total // K},
-                "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m_host.numel() * 8),
-                        "d2h_bytes_per_step": 8, "checksum": chk,
-                        "api": "oc_hjb_solve_band with the density band as a pinned host array + checksum read"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "fused::hjb_fused_kernel<NE>", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                             "traffic": ncu_traffic(True)[0], "traffic_source": ncu_traffic(True)[1],
-                             "launches": int(step_n), "avg_launch_ms": step_ms_max / max(step_n, 1),
-                             "share_of_step": step_ms_max / ms_max,
-                             "note": ("the launch contains the halo exchange and the cross-GPU error-sum all-gather: its "
-                                      "duration includes waiting for the slowest rank") if getattr(ctx, "peer_memory", False)
-                             else "halo exchange and all-gather run as an NCCL group after the launch"},
-                "cpu_baseline": None,
-                "gcfm": {"metric": "gcfm_agent_steps_per_s", "value": world * agent_steps / float(gt[1].item()),
-                         "unit": "agent-steps/s", "e2e_value": world * agent_steps / float(gt[0].item()),
-                         "agents_per_gpu": simu.N, "steps": args.gcfm_steps,
-                         "note": "replicas: one independent band-sized crowd per GPU"}}
-        print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
-    return 0
-
-
-# ----------------------------------------------------------------------------------------------- GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--T", type=float, default=T_DEFAULT)
-    ap.add_argument("--band-ny", type=int, default=BAND_NY)
-    ap.add_argument("--nx", type=int, default=BAND_NX)
-    ap.add_argument("--agents", type=int, default=BAND_AGENTS)
-    ap.add_argument("--gcfm-steps", type=int, default=20)
-    ap.add_argument("--fused", type=int, default=int(os.environ.get("OC_FUSED", "1")),
-                    help="1: stage-fused RK45 step kernel (default), 0: one kernel per RK stage")
-    ap.add_argument("--field", default=os.environ.get("OC_FIELD", "phi"), choices=["phi", "velocity"],
-                    help="field storage: phi samples (sampler differentiates) or vx/vy slices like the reference")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from optimal_crowds_b200 import _lib, simulations, synthetic
-
-    if world > 1:
-        return run_dist(args, world, rank, local_rank)
-    W, K = max(args.warmup, 0), args.steps
-    nx, ny = args.nx, args.band_ny
     t_start = time.perf_counter()
 
     def note(msg):
         if rank == 0:
             print(f"[bench {time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
-    room = synthetic.slalom_room(nx, ny, agents=args.agents)
-    np.random.seed(1000 + rank)
-    import contextlib, io
+    numa = pin_numa(local_rank)
+    room = synthetic.slalom_room(nx, Ny, agents=args.agents * world)
+    np.random.seed(1000)   # every rank of a row-decomposed run uses the same seed (replicated, deterministic sweep)
     with contextlib.redirect_stdout(io.StringIO()):
-        simu = simulations.simulation(room, args.T, recompute=False, record=False, field_storage=args.field,
-                                      fused=args.fused)
-    note(f"simulation built: N={simu.N} agents, grid {simu.Ny}x{simu.Nx}, keys={len(simu.targets)}")
-    key = list(simu.targets)[0]
-    opt = simu.targets[key]
+        kw = dict(band=True) if world > 1 else {}
+        if args.field != "phi":
+            kw["field_storage"] = args.field
+        simu = simulations.simulation(room, args.T, recompute=False, record=False, fused=args.fused, **kw)
+    note(f"simulation built: N={simu.N} agents, grid {simu.Ny}x{simu.Nx}, keys={len(simu.targets)}, numa node {numa}")
+    opt = list(simu.targets.values())[0]
     opt._prm.profile = 1
-    cells = nx * ny
-    # density input m as a HOST buffer (the reference-facing signature takes a numpy array), pinned
-    m_host = torch.zeros((ny, nx), dtype=torch.float64).pin_memory()
+    cells = nx * Ny
+    own0 = simu._band[0] if simu._band else 0
+    # density input of the solve, m >= 0 and smooth: this rank's rows, as a pinned HOST array (the reference-facing
+    # signature takes a numpy array) and as a device copy
+    m_host = torch.from_numpy(smooth_density(nx, ny, own0)).pin_memory()
     m_dev = m_host.to("cuda")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
 
     def solve(m):
         with contextlib.redirect_stdout(io.StringIO()):
@@ -419,18 +377,16 @@ def main():
     barrier()
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * nfev_total * cells / (ms_max * 1e-3) / 1e9
-
+    ms_max, step_ms_max = allmax([ev0.elapsed_time(ev1), cls_ms[0]])
+    value = nfev_total * cells / (ms_max * 1e-3) / 1e9
     note(f"device-resident: {value:.2f} Gcu/s, {ms_max / K:.1f} ms/solve")
-    # ---- end to end: host m -> H2D, solve, D2H of a scalar checksum of the first field slice -----------
+
+    # ---- end to end: host m -> H2D, solve, D2H of a scalar checksum of the t = 0 field slice ----------
     def checksum():
-        # D2H read of the step's result: checksum of the t = 0 slice of the field
-        return float((opt.d_vx[0] if opt.d_vx is not None else opt.d_phi[opt.nt_opt - 1]).sum().item())
+        if opt.d_vx is not None:
+            return float(opt.d_vx[0].sum().item())
+        sl = opt.d_phi[opt.nt_opt - 1]
+        return float((sl[1:-2] if simu._band else sl).sum().item())
 
     for _ in range(max(min(W, 2), 1)):  # warm-up of the whole e2e step (first use of the reduction loads its module)
         solve(m_host.numpy())
@@ -447,51 +403,71 @@ def main():
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * nfev_e2e * cells / (float(t.item()) * 1e-3) / 1e9
-
+    e2e_ms, = allmax([max(e0.elapsed_time(e1), wall_ms)])
+    e2e_value = nfev_e2e * cells / (e2e_ms * 1e-3) / 1e9
     note(f"e2e: {e2e_value:.2f} Gcu/s")
+
     # ---- GCFM: agent-steps/s through simulation.step (host RNG + H2D + sweep + exit log D2H) -----------
+    fp64_peak = simu._ctx.fp64_peak()
     for _ in range(3):
         simu.step(simu.dt)
     barrier()
     g0 = time.perf_counter()
-    agent_steps, dev_ms = 0, 0.0
+    agent_steps, dev_ms, pairs = 0, 0.0, 0
     for _ in range(args.gcfm_steps):
         agent_steps += int(simu._h_status.sum())
         simu.step(simu.dt)
         dev_ms += simu._ctx.gcfm_last_ms()
+        pairs += simu._ctx.gcfm_last_pairs()
     barrier()
-    g_wall = time.perf_counter() - g0
-    gt = torch.tensor([g_wall, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-    gcfm = {"metric": "gcfm_agent_steps_per_s", "value": world * agent_steps / float(gt[1].item()),
-            "unit": "agent-steps/s", "e2e_value": world * agent_steps / float(gt[0].item()),
-            "agents_per_gpu": simu.N, "steps": args.gcfm_steps, "ms_per_step": float(gt[1].item()) * 1e3 / args.gcfm_steps,
-            "note": "value = CUDA-event time of oc_gcfm_step (H2D perm/noise + kernels + exit log); e2e_value adds the "
-                    "host numpy RNG draw and Python; parity mode (sequential-sweep semantics, host RNG stream)"}
+    g_wall, g_dev = allmax([time.perf_counter() - g0, dev_ms * 1e-3])
+    pair_tflops = pairs * FP64_INST_PER_PAIR * 2.0 / g_dev / 1e12   # FMA-equivalent flops of the FP64-pipe instructions
+    gcfm = {"metric": "gcfm_agent_steps_per_s", "value": agent_steps / g_dev, "unit": "agent-steps/s",
+            "e2e_value": agent_steps / g_wall, "agents": simu.N, "steps": args.gcfm_steps,
+            "ms_per_step": g_dev * 1e3 / args.gcfm_steps, "pairs_per_step": pairs / args.gcfm_steps,
+            "roofline": {"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+                         "peak_source": "measured here (oc_fp64_peak: 8 independent DFMA chains x 16 warps/SM)",
+                         "achieved": pair_tflops, "frac": pair_tflops / fp64_peak,
+                         "work": f"{FP64_INST_PER_PAIR:.0f} FP64-pipe instructions per interacting pair (ncu) x pairs; the "
+                                 "sweep is a dependency chain (sequential-sweep semantics), so the pipe is latency- not "
+                                 "throughput-bound"},
+            "note": ("value = CUDA-event time of oc_gcfm_step (H2D perm/noise + kernels + exit log); e2e_value adds the host "
+                     "numpy RNG draw and Python; parity mode (sequential-sweep semantics, host RNG stream)"
+                     + ("; ONE room of %d agents on %d GPUs: field samples and wall searches sharded by row band, the "
+                        "sweep replicated on every rank (a room's sweep is one dependency chain)" % (simu.N, world)
+                        if world > 1 else ""))}
+    note(f"gcfm: {gcfm['value']:.0f} agent-steps/s device, {gcfm['e2e_value']:.0f} e2e, fp64 peak {fp64_peak:.1f} TF/s")
 
-    note(f"gcfm: {gcfm['value']:.0f} agent-steps/s device, {gcfm['e2e_value']:.0f} e2e")
+    parity = None
+    if world > 1:
+        del m_dev
+        for o in simu.targets.values():
+            o.d_phi = None
+        torch.cuda.empty_cache()
+        parity = parity_block(world, rank, note)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return 0 if (parity is None or all(v for k, v in parity.items() if isinstance(v, bool))) else 1
     peak, peak_src = load_peaks()
-    dom = 0  # RK stage kernels
-    achieved = cls_bytes[dom] / (cls_ms[dom] * 1e-3) / 1e9 if cls_ms[dom] > 0 else 0.0
+    dom = 0  # RK step kernels
+    band_cells = nx * ny
+    achieved = cls_bytes[dom] / (step_ms_max * 1e-3) / 1e9 if step_ms_max > 0 else 0.0
+    p2p = bool(getattr(simu._ctx, "peer_memory", False))
     roof = {"bound": "hbm", "kernel": "hjb_stage_kernel<N,MODE> (RK45 stage: combination + stencil [+ y_new, error])"
-            if not args.fused else "fused::hjb_fused_kernel<NE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
-            else "fallback (B200_PROFILING.md)", "traffic": None,
-            "launches": int(cls_n[dom]), "avg_launch_ms": float(cls_ms[dom] / max(cls_n[dom], 1)),
+            if not args.fused else "fused::hjb_fused_kernel<NE> (TMA-staged stage-fused RK45 step)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs: 1:1 copy; a streaming kernel with this kernel's 3-read : "
+            "5-write mix reaches 0.92 of it, profiles/r2_hbm_mix.md)" if peak_src == "measured" else "fallback (B200_PROFILING.md)",
+            "traffic": None, "launches": int(cls_n[dom]), "avg_launch_ms": float(step_ms_max / max(cls_n[dom], 1)),
             "algorithmic_bytes_per_launch": float(cls_bytes[dom] / max(cls_n[dom], 1)),
-            "share_of_step": float(cls_ms[dom] / (ms * 1.0)) if ms > 0 else None,
-            "other_classes": {"dense_output+velocity": {"ms": float(cls_ms[1]), "GBps": float(cls_bytes[1] / max(cls_ms[1], 1e-9) / 1e6),
-                                                       "launches": int(cls_n[1])},
+            "share_of_step": float(step_ms_max / ms_max) if ms_max > 0 else None,
+            "other_classes": {"dense_output+velocity": {"ms": float(cls_ms[1]), "launches": int(cls_n[1])},
                               "reductions": {"ms": float(cls_ms[2]), "launches": int(cls_n[2])}}}
+    if world > 1:
+        roof["note"] = ("the launch contains the halo exchange (NVLink peer stores) and the cross-GPU error-sum all-gather: its "
+                        "duration includes waiting for the slowest rank") if p2p else \
+                       "halo exchange and all-gather run as an NCCL group after the launch"
     roof["traffic"], roof["traffic_source"] = ncu_traffic(args.fused)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -502,25 +478,78 @@ def main():
             gcfm["cpu_baseline"] = {"value": gc, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": gsample}
         except Exception as e:  # pragma: no cover
             gcfm["cpu_baseline"] = {"error": str(e)}
+    api = "simulations.simulation(room, T" + (", band=True" if world > 1 else "") + ") -> targets[key].compute_optimal_velocity(t, m)"
     line = {"metric": "hjb_gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"slalom (BASELINE configs[3]) cylinder field, {nx}x{ny * world} grid "
+            "config": {"workload": f"slalom (BASELINE configs[3]) cylinder field, {nx}x{Ny} grid "
                                    f"({nx}x{ny} band per GPU; N=8 is the 16384^2 / 100k-agent config), T={args.T} "
-                                   f"(nt={round(args.T / 0.02)} slices), {args.agents * world} agents",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent row bands (no halo exchange)",
+                                   f"(nt={round(args.T / 0.02)} slices), {args.agents * world} agents, smooth density input "
+                                   "0 <= m <= 1",
+                       "parallelism": "1 GPU" if world == 1 else
+                       (f"one room, row bands over {world} GPUs; halo rows (6 of y_new, f_new per side) and the per-chunk error "
+                        "sums are exchanged INSIDE the step launch as NVLink peer stores (CUDA IPC), NCCL only at solve start"
+                        if p2p else f"one room, row bands over {world} GPUs, NCCL halo exchange + all-gather per attempt"),
                        "l2": "inputs larger than L2 (each field 268 MB > 126 MB)", "formulation":
                        "stage-wise RK45 (52 B/cell-update)" if not args.fused else
-                       "stage-fused RK45 step (40 B/cell/attempt + 8 B/cell/emitted phi slice)", "field_storage": args.field,
+                       "stage-fused RK45 step (40 B/cell/attempt + 8 B/cell/emitted phi slice)",
+                       "field_storage": opt.field_storage + " (the API default)", "api": api,
                        "nfev_per_solve": nfev_total // K},
-            "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m_host.numel() * 8),
-                    "d2h_bytes_per_step": 8, "checksum": chk,
-                    "api": "optimals.compute_optimal_velocity(t, m_host) + read of the t=0 field slice checksum"},
+            "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m_host.numel() * 8) * world,
+                    "d2h_bytes_per_step": 8 * world, "checksum": chk,
+                    "api": api + " with m a pinned host numpy array; the result stays on the device (it is the GCFM "
+                           "sampler's input), the read-back is a checksum of the t = 0 slice"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gcfm": gcfm}
+    if parity is not None:
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 0 if (parity is None or all(v for k, v in parity.items() if isinstance(v, bool))) else 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="slalom", choices=["slalom", "metro", "ensemble"],
+                    help="slalom = BASELINE configs[3] (the headline line); metro = configs[2]; ensemble = configs[4]")
+    ap.add_argument("--T", type=float, default=None)
+    ap.add_argument("--band-ny", type=int, default=BAND_NY)
+    ap.add_argument("--nx", type=int, default=BAND_NX)
+    ap.add_argument("--agents", type=int, default=BAND_AGENTS)
+    ap.add_argument("--gcfm-steps", type=int, default=20)
+    ap.add_argument("--rooms", type=int, default=1024, help="ensemble: members in total (sharded over the GPUs)")
+    ap.add_argument("--fused", type=int, default=int(os.environ.get("OC_FUSED", "1")),
+                    help="1: stage-fused RK45 step kernel (default), 0: one kernel per RK stage")
+    ap.add_argument("--field", default=os.environ.get("OC_FIELD", "phi"), choices=["phi", "velocity"],
+                    help="field storage: phi samples (API default; sampler differentiates) or vx/vy slices")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.T is None:
+            args.T = T_DEFAULT
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "metro":
+        from scripts import bench_workloads
+        return bench_workloads.run_metro(args, world, rank, local_rank)
+    if args.workload == "ensemble":
+        from scripts import bench_workloads
+        return bench_workloads.run_ensemble(args, world, rank, local_rank)
+    if args.T is None:
+        args.T = T_DEFAULT
+    return run_slalom(args, world, rank, local_rank)
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 1
+#define OC_ABI_VERSION 2
 
 typedef enum {
     OC_OK = 0,
@@ -35,7 +35,7 @@ typedef enum {
     OC_ERR_ARG = -2,            /* invalid argument */
     OC_ERR_NOMEM = -3,          /* device or host allocation failed */
     OC_ERR_SAMPLER_RANGE = -4,  /* an agent position would make the reference's sampler raise IndexError
-                                   or wrap a negative index (optimals.py:234-248) */
+                                   (optimals.py:234-248; negative indices wrap like numpy's) */
     OC_ERR_STEP_TOO_SMALL = -5, /* RK45 TOO_SMALL_STEP (scipy rk.py:133-134): solve_ivp status -1 */
     OC_ERR_NCCL = -6
 } oc_status;
@@ -196,6 +196,11 @@ typedef struct {
      * communicator of oc_dist_init, and every rank then runs the identical sequential sweep (a room's sweep is one
      * dependency chain).  own0 = own1 = 0: single-GPU step, everything local. */
     int own0, own1;
+    /* Target sets sharded over the ranks (BASELINE configs[2]: one HJB key per GPU; the reference builds and solves one
+     * optimals object per key, simulations.py:113-121,424-425): with key_mod > 0 a rank evaluates the field sample and
+     * the wall force only for agents whose key index k satisfies k % key_mod == key_rem -- the keys whose fields it
+     * solved and holds -- and the terms are merged exactly like the row-band case.  key_mod = 0: all keys are local. */
+    int key_mod, key_rem;
 } oc_gcfm_params;
 
 typedef struct {
@@ -250,6 +255,21 @@ int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit);
 
 /* CUDA-event time (ms) of the last oc_gcfm_step on this context (H2D of perm/noise, all kernels, exit-log copy). */
 double oc_gcfm_last_ms(oc_ctx *ctx);
+/* Interacting pairs of the last step: calls of ped.agents_repulsion the reference would have made
+ * (simulations.py:291-295) -- the work unit of the pair-force roofline (bench.py "gcfm.roofline"). */
+long long oc_gcfm_last_pairs(oc_ctx *ctx);
+/* How many times the last step was redone on the exact slow path.  The fast path keeps at most 512 candidates per
+ * agent in shared memory and assumes that no agent moves more than 0.5 m per axis in one step; a step that breaks
+ * either assumption is restored from its snapshot and redone with global-memory candidate lists and a search
+ * radius covering the measured displacement (the reference has neither limit: simulations.py:285-303). */
+int oc_gcfm_last_redos(oc_ctx *ctx);
+/* Packed copy of the crowd state, d_out (N,4) = x,y,vx,vy (32-byte aligned): one row of the device-resident record
+ * behind ped.traj / ped.vels (pedestrians.py:106-110,189-190) and simulation.history (simulations.py:579-589). */
+int oc_state_pack(oc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_vx, const double *d_vy,
+                  double *d_out, void *stream);
+/* Measured FP64 FMA throughput of the context's GPU in TFLOP/s (2 flops per FMA): denominator of the GCFM
+ * pair-force roofline.  Takes ~2 ms; synchronises the device. */
+int oc_fp64_peak(oc_ctx *ctx, double *tflops);
 
 /* Nearest-wall search + wall force only (pedestrians.py:282-334) for N independent probes (unit parity):
  * d_ind (nullable, N int64): the np.argmin flat index. */

@@ -66,7 +66,8 @@ class GcfmParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("dt", "dt2", "half_noise", "relaxation", "v_max", "cutoff", "a_min", "tau_a", "b_min", "b_max",
                  "eta", "eta_walls", "cos_fov", "one_minus_cos_fov", "dx", "dy", "room_length", "room_height")] + \
-               [("Ny", C.c_int), ("Nx", C.c_int), ("own0", C.c_int), ("own1", C.c_int)]
+               [("Ny", C.c_int), ("Nx", C.c_int), ("own0", C.c_int), ("own1", C.c_int), ("key_mod", C.c_int),
+                ("key_rem", C.c_int)]
 
 
 class Key(C.Structure):
@@ -82,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak"]
 
 
 def load():
@@ -99,6 +100,11 @@ def load():
     lib.oc_wall_tiles_bytes.restype = C.c_longlong
     lib.oc_gcfm_last_ms.restype = C.c_double
     lib.oc_gcfm_last_ms.argtypes = [C.c_void_p]
+    lib.oc_gcfm_last_pairs.restype = C.c_longlong
+    lib.oc_gcfm_last_pairs.argtypes = [C.c_void_p]
+    lib.oc_gcfm_last_redos.argtypes = [C.c_void_p]
+    lib.oc_state_pack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    lib.oc_fp64_peak.argtypes = [C.c_void_p, dp]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
     lib.oc_ctx_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.oc_ctx_destroy.restype = None
@@ -419,6 +425,28 @@ class Context:
     def gcfm_last_ms(self):
         return float(load().oc_gcfm_last_ms(self.h))
 
+    def gcfm_last_pairs(self):
+        """interacting pairs (ped.agents_repulsion calls of the reference) evaluated by the last step"""
+        return int(load().oc_gcfm_last_pairs(self.h))
+
+    def gcfm_last_redos(self):
+        """how often the last step was redone on the exact slow path (oc_gcfm_last_redos)"""
+        return int(load().oc_gcfm_last_redos(self.h))
+
+    def state_pack(self, state, out):
+        """out (N,4) <- packed (x, y, vx, vy): one row of the device-resident trajectory record"""
+        N = state["x"].numel()
+        assert out.is_contiguous() and out.numel() == 4 * N
+        check(load().oc_state_pack(self.h, N, _dev(state["x"]), _dev(state["y"]), _dev(state["vx"]), _dev(state["vy"]),
+                                   _dev(out), _stream()))
+        return out
+
+    def fp64_peak(self):
+        """measured FP64 FMA throughput of this GPU in TFLOP/s (roofline denominator of the pair forces)"""
+        v = C.c_double()
+        check(load().oc_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
+
     def wall_force(self, prm: GcfmParams, V, x, y, vx, vy, vdes):
         import torch
         N = x.numel()
@@ -459,6 +487,7 @@ def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: 
     p.dx = p.dy = cfg["grid_step"]
     p.room_length, p.room_height, p.Ny, p.Nx = room_length, room_height, Ny, Nx
     p.own0 = p.own1 = 0   # single-GPU step; a row-decomposed run sets its band here
+    p.key_mod = p.key_rem = 0  # all target sets local; a key-sharded run (one HJB key per GPU) sets its share here
     return p
 
 

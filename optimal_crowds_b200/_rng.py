@@ -23,7 +23,7 @@ class StepRandomness:
     # checkpoints (pairs before the end of the speculative block): get_state/set_state cost ~75 us each, a pair
     # ~50 ns, so a handful of checkpoints and a short re-draw beat many checkpoints
     CKPT_BEFORE_END = (4096, 1024, 256, 64)
-    MIN_N = 25000  # below this the draws take less time than the bookkeeping: no look-ahead
+    MIN_N = 4096  # below this the draws take less time than the bookkeeping (get_state / set_state): no look-ahead
 
     def __init__(self, lookahead: bool = True, rng=np.random):
         # rng: the global ``np.random`` module (reference behaviour) or a ``np.random.RandomState`` of an ensemble member
@@ -56,7 +56,9 @@ class StepRandomness:
         ckpt = [(0, self.rng.get_state())]
         parts = []
         done = 0
-        for back in self.CKPT_BEFORE_END + (0,):
+        # small crowds: fewer checkpoints (each costs a get_state), the re-draw after the nearest one stays short
+        backs = self.CKPT_BEFORE_END if n_upper >= 16 * self.CKPT_BEFORE_END[0] else (256, 32)
+        for back in backs + (0,):
             stop = n_upper - back
             if stop > done:
                 parts.append(self.rng.normal(size=(stop - done, 2)))

@@ -84,6 +84,7 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->dist_ws);
     oc_dist_finalize(c);
     cudaFree(c->gcfm_ws);
+    oc_gcfm_free_launch_state(c);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
     cudaFree(c->fr_ticket);
@@ -108,6 +109,77 @@ extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long b
     if (bytes == 0) return OC_OK;
     OC_CUDA(cudaSetDevice(ctx->device));
     OC_CUDA(cudaMemcpyAsync(d_dst, host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 pipe peak of this GPU, measured: the roofline denominator of the GCFM pair forces (SURVEY.md section 8d asks
+// for a measured FP64 FMA peak; MEASURED_PEAKS.json only carries HBM and bf16 tensor figures).  8 independent DFMA
+// chains per thread, 16 warps per SM, ~10^9 FMAs: B200 sustains ~1.84 warp-DFMA per clock and SM (34 TFLOP/s).
+namespace {
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = fma(v[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int oc_fp64_peak(oc_ctx *ctx, double *tflops) {
+    OC_ARG(ctx && tflops, "NULL argument");
+    OC_CUDA(cudaSetDevice(ctx->device));
+    int n_sm = 0;
+    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    double *d = nullptr;
+    OC_CUDA(cudaMalloc(&d, sizeof(double) * 512 * n_sm));
+    const int iters = 4000;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        OC_CUDA(cudaEventRecord(ctx->ev0, 0));
+        fp64_peak_kernel<<<n_sm, 512>>>(d, iters, 0.999, 1e-3);
+        OC_CUDA(cudaEventRecord(ctx->ev1, 0));
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cudaFree(d); OC_CUDA(e); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    oc::count_launch(4);
+    *tflops = 2.0 * (double)iters * 16 * 8 * 512 * n_sm / (best * 1e-3) / 1e12;
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed copy of the crowd state: out[i] = (x, y, vx, vy) of agent i, one row of the device-resident trajectory
+// record (ped.traj / ped.vels, pedestrians.py:189-190; history frames, simulations.py:579-589).
+namespace {
+__global__ void state_pack_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
+                                  const double *__restrict__ vx, const double *__restrict__ vy, double4 *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = make_double4(x[i], y[i], vx[i], vy[i]);
+}
+}  // namespace
+
+extern "C" int oc_state_pack(oc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_vx,
+                             const double *d_vy, double *d_out, void *stream) {
+    OC_ARG(ctx && N >= 0 && (N == 0 || (d_x && d_y && d_vx && d_vy && d_out)), "NULL argument");
+    OC_ARG(((uintptr_t)d_out % 32) == 0, "d_out must be 32-byte aligned");
+    if (N == 0) return OC_OK;
+    OC_CUDA(cudaSetDevice(ctx->device));
+    state_pack_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, d_x, d_y, d_vx, d_vy,
+                                                                         reinterpret_cast<double4 *>(d_out));
+    oc::count_launch();
+    OC_CUDA(cudaGetLastError());
     return OC_OK;
 }
 

@@ -40,6 +40,12 @@ struct oc_ctx {
     double gcfm_last_ms = 0.0;
     void *gcfm_stream = nullptr;
     bool gcfm_pending = false;
+    void *gcfm_last = nullptr;        // launch state of the step in flight (oc_gcfm.cu: GcfmLaunch), for the slow-path redo
+    void *gcfm_glist = nullptr;       // global-memory candidate lists of the exact slow path
+    size_t gcfm_glist_bytes = 0;
+    int gcfm_tag = 0;                 // generation of the sweep's done-flags (they live in this context's workspace)
+    int gcfm_redos = 0;               // slow-path redos of the last step
+    long long gcfm_last_pairs = 0;    // interacting pairs evaluated by the last step
     int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
     int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
     // in-kernel final reduction of the fused step (oc_hjb_fused.cuh): ticket counters on the device, results in
@@ -65,6 +71,7 @@ struct oc_ctx {
 };
 
 int oc_dist_allreduce_max_u64(oc_ctx *ctx, void *d_buf, size_t count, cudaStream_t st);  // oc_hjb_dist.cu
+void oc_gcfm_free_launch_state(oc_ctx *ctx);                                               // oc_gcfm.cu
 
 namespace oc {
 void set_error(const char *fmt, ...);

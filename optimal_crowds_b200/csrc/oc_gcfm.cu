@@ -27,10 +27,11 @@
 namespace {
 
 constexpr int WT = OC_WALL_TILE;
-constexpr double DISP_MARGIN = 1.0;  // max displacement per step assumed by the candidate search (checked)
+constexpr double DISP_MARGIN = 1.0;  // displacement per step (2 x per-axis bound) the FAST candidate search assumes (checked)
 constexpr int SWEEP_WARPS = 4;       // warps per block in the sweep
-constexpr int CAND_CAP = 512;        // candidates (agents within cutoff + margin of the old position) per agent
-constexpr int LIST_CAP = CAND_CAP;
+constexpr int CAND_CAP = 512;        // fast path: candidates (agents within cutoff + margin of the old position) per agent
+constexpr int CAND_CAP_MAX = 65536;  // exact slow path: candidate lists in global memory, 16-bit slot indices
+constexpr int OUT_HDR = 8;           // ints in front of the exit ids in the host-visible step result
 constexpr size_t SWEEP_SLOT_BYTES = 2 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned short);  // 28 B
 constexpr size_t SWEEP_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * SWEEP_SLOT_BYTES;  // 56 KB: 4 CTAs (16 warps) per SM
 static_assert(CAND_CAP <= 65536, "slot indices are stored as 16-bit");
@@ -56,8 +57,11 @@ struct Ws {  // device workspace carved out of ctx->gcfm_ws
     double *doors;                          // flattened door rectangles of all keys
     int *perm, *rank, *nzidx, *flags, *exit_mark, *agent_bin, *cell_agents, *bin_start, *bin_cursor;
     uint8_t *status0;
+    double *time0;   // per-agent clock at step start (restored when a step is redone on the exact slow path)
     KeyDev *keys;
-    int *counters;  // [0] ticket [1] flags: bit0 sampler range, bit1 list overflow, bit2 displacement > margin
+    // [0] ticket [1] flags: bit0 sampler range, bit1 list overflow, bit2 displacement > margin [2] interacting pairs
+    // evaluated (pair_force calls) [3] largest candidate count [4..5] largest per-axis displacement (bits of a double)
+    int *counters;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -94,7 +98,7 @@ __device__ __forceinline__ int sampler_owner_row(const oc_gcfm_params &p, double
     return (int)i0 + 1;
 }
 
-// optimals.py:212-250 -- returns 1 if the reference would raise IndexError / wrap a negative index
+// optimals.py:212-250 -- returns 1 if the reference would raise IndexError (negative indices wrap like numpy's)
 __device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double x, double y, int t, double &ox,
                                double &oy) {
     ox = 0.0;
@@ -114,6 +118,9 @@ __device__ int choose_velocity(const oc_gcfm_params &p, const KeyDev &k, double 
         i0 = i1 = p.Ny - 3;
     }
     const int W = p.Nx - 2, H = p.Ny - 2;
+    // numpy wraps negative indices: an agent at x < 0 (then j1 == j0) reads column W + j0, silently (App. C #7)
+    if (j0 < 0) { j0 += W; j1 = j0; }
+    if (i0 < 0) { i0 += H; i1 = i0; }
     if (j0 < 0 || j1 >= W || i0 < 0 || i1 >= H || t < 0) return 1;
     double ax, ay, bx, by;
     if (k.vx) {
@@ -158,7 +165,7 @@ __device__ __forceinline__ AgentEllipse ellipse_of(const oc_gcfm_params &p, doub
     AgentEllipse e;
     e.ni = ocm_norm2(vx, vy);
     e.a_i = p.a_min + p.tau_a * e.ni;
-    e.b_i = p.b_max - (p.b_max - p.b_min) * fmin(e.ni / v_des, 1.0);
+    e.b_i = p.b_max - (p.b_max - p.b_min) * ocm_npmin(e.ni / v_des, 1.0);
     e.beta_i = ocm_atan2(vy, vx);
     return e;
 }
@@ -169,7 +176,7 @@ __device__ void pair_force(const oc_gcfm_params &p, const AgentEllipse &ei, doub
                            double &fy) {
     double nj = ocm_norm2(vxj, vyj);
     double a_j = p.a_min + p.tau_a * nj;
-    double b_j = p.b_max - (p.b_max - p.b_min) * fmin(nj / v_des_i, 1.0);  // v_des of i: pedestrians.py:245
+    double b_j = p.b_max - (p.b_max - p.b_min) * ocm_npmin(nj / v_des_i, 1.0);  // v_des of i: pedestrians.py:245
     double Rx = xj - xi, Ry = yj - yi;
     double nR = ocm_norm2(Rx, Ry);
     double ex = Rx / nR, ey = Ry / nR;
@@ -177,7 +184,7 @@ __device__ void pair_force(const oc_gcfm_params &p, const AgentEllipse &ei, doub
     double d = wx * (-ex) + wy * (-ey);
     double v_rel = 0.5 * (d + fabs(d));
     double k = 0.0;
-    if (ei.ni > 0) k = fmax((vxi * ex + vyi * ey) / ei.ni - p.cos_fov, 0.0) / p.one_minus_cos_fov;
+    if (ei.ni > 0) k = ocm_npmax((vxi * ex + vyi * ey) / ei.ni - p.cos_fov, 0.0) / p.one_minus_cos_fov;
     // alpha_i = atan2(Ry,Rx), alpha_j = atan2(-Ry,-Rx): one arctangent core, same bits as two calls
     double alpha_i, alpha_j;
     ocm_atan2_both(Ry, Rx, &alpha_i, &alpha_j);
@@ -190,7 +197,7 @@ __device__ void pair_force(const oc_gcfm_params &p, const AgentEllipse &ei, doub
     double cj = csj / a_j, sj = snj / b_j;
     double q_j = sqrt(1.0 / (cj * cj + sj * sj));
     double dist = nR - q_i - q_j;
-    double rep = fmin(k * ocm_exp(-dist / (p.eta * (1.0 + v_rel))), 1.0);
+    double rep = ocm_npmin(k * ocm_exp(-dist / (p.eta * (1.0 + v_rel))), 1.0);
     fx = -rep * Rx;
     fy = -rep * Ry;
 }
@@ -209,7 +216,7 @@ __device__ void wall_force_from_node(const oc_gcfm_params &p, const AgentEllipse
     double c = cs / ei.a_i, s = sn / ei.b_i;
     double q_i = 1.0 / (c * c + s * s);  // no sqrt: pedestrians.py:328
     double dist = nR - q_i;
-    double rep = fmin(ocm_exp(-dist / (p.eta_walls * (1.0 + v_rel))), 1.0);
+    double rep = ocm_npmin(ocm_exp(-dist / (p.eta_walls * (1.0 + v_rel))), 1.0);
     fx = -3.0 * rep * Rx;
     fy = -3.0 * rep * Ry;
 }
@@ -348,7 +355,8 @@ __global__ void tile_ring_kernel(const uint8_t *__restrict__ occ, int ntx, int n
 // rank = inverse permutation; snapshot; bin histogram
 __global__ void setup_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ vx, const double *__restrict__ vy,
-                             const uint8_t *__restrict__ status, Ws w, double inv_cs, int nbx, int nby) {
+                             const double *__restrict__ tim, const uint8_t *__restrict__ status, Ws w, double inv_cs,
+                             int nbx, int nby) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     w.rank[w.perm[i]] = i;
@@ -358,6 +366,7 @@ __global__ void setup_kernel(int N, const double *__restrict__ x, const double *
     w.snap4[i] = make_double4(xi, yi, vxi, vyi);
     uint8_t s = status[i];
     w.status0[i] = s;
+    w.time0[i] = tim[i];
     int bx = min(max((int)floor(xi * inv_cs), 0), nbx - 1), by = min(max((int)floor(yi * inv_cs), 0), nby - 1);
     int b = by * nbx + bx;
     w.agent_bin[i] = b;
@@ -392,6 +401,23 @@ __global__ void scatter_kernel(int N, Ws w) {
     w.cell_agents[pos] = i;
     w.cell_state[pos] = w.snap4[i];
     w.cell_jr[pos] = make_int2(i, w.rank[i]);
+}
+
+// undo a step that the fast path could not complete exactly (candidate-list overflow or a displacement beyond the
+// search margin): the state goes back to the snapshot taken by setup_kernel, then the step is redone (slow path)
+__global__ void restore_kernel(int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
+                               double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double4 s = w.snap4[i];
+    x[i] = s.x; y[i] = s.y; vx[i] = s.z; vy[i] = s.w;
+    tim[i] = w.time0[i];
+    status[i] = w.status0[i];
+    if (i == 0) {  // the sampler-range flag (bit 0, set by prepare_kernel) survives a redo; everything else restarts
+        w.counters[0] = 0;
+        w.counters[1] &= 1;
+        for (int q = 2; q < 8; q++) w.counters[q] = 0;
+    }
 }
 
 // nzidx[agent] = number of agents active at step start that precede it in the sweep (simulations.py:303
@@ -430,6 +456,11 @@ __global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, W
     const int lane = threadIdx.x & 31;
     const KeyDev k = w.keys[key_id[i]];
     double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i];
+    if (p.key_mod > 0 && key_id[i] % p.key_mod != p.key_rem) {
+        // key-sharded run: the rank that solved this agent's target set evaluates it -- all-zero bits for the merge
+        if (lane == 0) { w.des_x[i] = 0.0; w.des_y[i] = 0.0; w.wfx[i] = 0.0; w.wfy[i] = 0.0; }
+        return;
+    }
     if (p.own1 > p.own0) {
         // row-decomposed run: another rank owns this agent -- leave all-zero bits for the bit-exact merge
         const int orow = sampler_owner_row(p, yi);
@@ -490,17 +521,19 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
              uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
-             double inv_cs, int nbx, int nby, unsigned poll_ns) {
+             double inv_cs, int nbx, int nby, unsigned poll_ns, double margin, int cap, unsigned char *glists) {
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj (ints), proc, ord
-    // (16-bit slot indices)
-    unsigned char *base = sweep_smem + (size_t)wid * CAND_CAP * SWEEP_SLOT_BYTES;
-    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + CAND_CAP;
-    int *ckk = reinterpret_cast<int *>(lfy + CAND_CAP), *cj = ckk + CAND_CAP;
-    unsigned short *proc = reinterpret_cast<unsigned short *>(cj + CAND_CAP), *ord = proc + CAND_CAP;
+    // (16-bit slot indices).  Fast path: `cap` = CAND_CAP slots in shared memory; exact slow path (glists != NULL): `cap`
+    // slots per warp in global memory, sized from the candidate count the refused fast attempt measured
+    unsigned char *base = glists ? glists + ((size_t)blockIdx.x * SWEEP_WARPS + wid) * cap * SWEEP_SLOT_BYTES
+                                 : sweep_smem + (size_t)wid * CAND_CAP * SWEEP_SLOT_BYTES;
+    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + cap;
+    int *ckk = reinterpret_cast<int *>(lfy + cap), *cj = ckk + cap;
+    unsigned short *proc = reinterpret_cast<unsigned short *>(cj + cap), *ord = proc + cap;
     unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(lfx), *sort_b = reinterpret_cast<unsigned long long *>(lfy);
-    const double reach = p.cutoff + DISP_MARGIN;
+    const double reach = p.cutoff + margin;
     const double reach2 = reach * reach;
     const int span = (int)ceil(reach * inv_cs);
     const unsigned lt_mask = (1u << lane) - 1;
@@ -556,7 +589,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             const bool later = jr.y > r;
             if (keep) {
                 const int pos = nc + __popc(m & lt_mask);
-                if (pos < CAND_CAP) {
+                if (pos < cap) {
                     ckk[pos] = kk;
                     cj[pos] = jr.x;
                     // processing key: later candidates first (key 0), earlier ones by ascending sweep rank
@@ -566,11 +599,12 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             }
             nc += __popc(m);
         }
-        if (nc > CAND_CAP) {  // uniform across the warp
+        if (lane == 0) atomicMax(&w.counters[3], nc);
+        if (nc > cap) {  // uniform across the warp
             if (lane == 0) atomicOr(&w.counters[1], 2);
-            // too many neighbours for the shared-memory lists: the step is refused (flag), the agent still advances
-            // with the first CAND_CAP candidates so that later agents do not wait forever
-            nc = CAND_CAP;
+            // too many neighbours for the lists: this attempt is void (flag; the host redoes the step with lists sized for
+            // counters[3]); the agent still advances with the first `cap` candidates so that later agents do not wait forever
+            nc = cap;
         }
         __syncwarp();
         // everything the final Euler step needs that does not depend on the neighbours is fetched now, so that no global
@@ -604,10 +638,12 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         }
         __syncwarp();
         // ---- C. forces in processing order
+        int n_pairs = 0;
         for (int base_c = 0; base_c < nc; base_c += 32) {
             const int c = base_c + lane;
             double fx = 0.0, fy = 0.0;
             int slot = -1;
+            bool hit = false;
             if (c < nc) {
                 slot = proc[c];
                 const int kk = ckk[slot], j = cj[slot];
@@ -625,12 +661,13 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 }
                 if (alive) {
                     const double ddx = sj.x - xi, ddy = sj.y - yi;
-                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff)  // pedestrians.py:354, simulations.py:291
+                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
                         pair_force(p, ei, xi, yi, vxi, vyi, vd, sj.x, sj.y, sj.z, sj.w, fx, fy);
-                    else { fx = 0.0; fy = 0.0; }
+                        hit = true;
+                    } else { fx = 0.0; fy = 0.0; }
                 }
             }
-            __syncwarp();
+            n_pairs += __popc(__ballot_sync(0xffffffffu, hit));
             if (slot >= 0) { lfx[slot] = fx; lfy[slot] = fy; }  // the sort buffers are dead: proc/ord were extracted
         }
         __syncwarp();
@@ -654,8 +691,14 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 nvx = nvx * sc;
                 nvy = nvy * sc;
             }
-            if (!(fabs(nx_ - xi) <= DISP_MARGIN * 0.5) || !(fabs(ny_ - yi) <= DISP_MARGIN * 0.5))
+            // the candidate search of every agent assumed that nobody moves more than margin/2 per axis in one step
+            const double disp = fmax(fabs(nx_ - xi), fabs(ny_ - yi));
+            if (!(disp <= margin * 0.5)) {
                 atomicOr(&w.counters[1], 4);
+                // (NaN displacements stay flagged with the largest margin: the host then gives up with an error)
+                atomicMax(reinterpret_cast<unsigned long long *>(w.counters + 4), (unsigned long long)__double_as_longlong(disp));
+            }
+            if (n_pairs) atomicAdd(&w.counters[2], n_pairs);
             bool out = false;
             for (int d = 0; d < n_doors; d++) {  // pedestrians.py:132-136
                 const double *door = w.doors + 4 * (door_off + d);
@@ -675,7 +718,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
     }
 }
 
-// ordered compaction of the exit marks (by sweep position) into host-visible memory: out[0]=count, out[1]=flags
+// ordered compaction of the exit marks (by sweep position) into host-visible memory: out[0]=count, out[1..5]=counters[1..5]
 __global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
     __shared__ int tot[1024];
     int t = threadIdx.x;
@@ -693,9 +736,9 @@ __global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__
     }
     int run = tot[t] - s;
     for (int r = lo; r < hi; r++)
-        if (w.exit_mark[r]) out[2 + run++] = w.exit_mark[r] - 1;
+        if (w.exit_mark[r]) out[OUT_HDR + run++] = w.exit_mark[r] - 1;
     if (t == 1023) out[0] = tot[1023];
-    if (t == 0) out[1] = w.counters[1];
+    if (t < 5) out[1 + t] = w.counters[1 + t];  // flags, pairs, largest candidate count, largest displacement (2 ints)
 }
 
 // unit-probe kernels ---------------------------------------------------------------------------------
@@ -819,7 +862,7 @@ extern "C" int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, d
 static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins, Ws &w, int **pinned, cudaStream_t st) {
     size_t need = 0;
     auto al = [&](size_t b) { need += ((b + 255) / 256) * 256; };
-    for (int q = 0; q < 8; q++) al(sizeof(double) * N);
+    for (int q = 0; q < 9; q++) al(sizeof(double) * N);
     al(sizeof(double4) * N);
     al(sizeof(double4) * N);
     al(sizeof(double4) * N);
@@ -854,6 +897,7 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.cell_jr = carve<int2>(p, N);
     w.x0 = carve<double>(p, N); w.y0 = carve<double>(p, N); w.vx0 = carve<double>(p, N); w.vy0 = carve<double>(p, N);
     w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
+    w.time0 = carve<double>(p, N);
     w.noise = carve<double>(p, 2 * (size_t)N);
     w.doors = carve<double>(p, 4 * (size_t)std::max(n_doors, 1));
     w.perm = carve<int>(p, N); w.rank = carve<int>(p, N); w.nzidx = carve<int>(p, N);
@@ -862,7 +906,7 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.status0 = carve<uint8_t>(p, N);
     w.keys = carve<KeyDev>(p, std::max(n_keys, 1));
     w.counters = carve<int>(p, 8);
-    size_t pin = sizeof(int) * ((size_t)N + 8);
+    size_t pin = sizeof(int) * ((size_t)N + OUT_HDR + 8);
     if (ctx->gcfm_pinned_bytes < pin) {
         if (ctx->gcfm_pinned) cudaFreeHost(ctx->gcfm_pinned);
         OC_CUDA(cudaMallocHost(&ctx->gcfm_pinned, pin));
@@ -872,7 +916,48 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     return OC_OK;
 }
 
-static int g_tag = 0;
+namespace {
+// what oc_gcfm_step_finish needs to redo a step on the exact slow path (kept per context between _launch and _finish)
+struct GcfmLaunch {
+    oc_gcfm_params prm;
+    int N, n_keys, n_doors, nbins_alloc;
+    double *x, *y, *vx, *vy, *tim;
+    uint8_t *status;
+    const double *vdes;
+    const int *key;
+    Ws w;
+    int *pinned;
+};
+
+// bins + cell list of one attempt of the current step; returns the attempt's done-flag generation (tag) or an error.
+// margin: displacement (2 x per axis) the candidate search allows for.  first = false: the state is restored first.
+int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, bool first) {
+    const int N = L.N;
+    Ws &w = L.w;
+    const double reach = L.prm.cutoff + margin;
+    const double cs = reach / 2.0, inv_cs = 1.0 / cs;  // candidate bins: cell size (cutoff + margin)/2, search +-2 cells
+    const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
+              nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
+    const int nbins = nbx * nby;
+    if (nbins > L.nbins_alloc) { oc::set_error("internal: GCFM bin table too small"); return OC_ERR_ARG; }
+    const int nb = (N + 255) / 256;
+    if (!first) {
+        restore_kernel<<<nb, 256, 0, st>>>(N, w, L.x, L.y, L.vx, L.vy, L.tim, L.status);
+        oc::count_launch();
+    }
+    OC_CUDA(cudaMemsetAsync(w.bin_start, 0, sizeof(int) * (nbins + 1), st));
+    OC_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int) * (nbins + 1), st));
+    OC_CUDA(cudaMemsetAsync(w.exit_mark, 0, sizeof(int) * N, st));
+    if (first) OC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * 8, st));  // (a redo resets them in restore_kernel)
+    if (++ctx->gcfm_tag >= 0x3fffffff) ctx->gcfm_tag = 1;  // per context: the done-flags live in the context's workspace
+    const int tag = ctx->gcfm_tag;
+    setup_kernel<<<nb, 256, 0, st>>>(N, L.x, L.y, L.vx, L.vy, L.tim, L.status, w, inv_cs, nbx, nby);
+    scan_kernel<<<1, 1024, 0, st>>>(w.bin_start, nbins + 1);
+    scatter_kernel<<<nb, 256, 0, st>>>(N, w);
+    oc::count_launch(3);
+    return tag;
+}
+}  // namespace
 
 extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx,
                             double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
@@ -882,6 +967,49 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
                                  noise, n_noise, simu_step, stream);
     if (rc) return rc;
     return oc_gcfm_step_finish(ctx, exit_log, n_exit);
+}
+
+// the sweep launch of one attempt (fast: shared-memory lists of CAND_CAP slots; slow: global-memory lists of `cap` slots)
+static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int tag, double margin, int cap, bool slow) {
+    const int N = L.N;
+    const double reach = L.prm.cutoff + margin, inv_cs = 2.0 / reach;
+    const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
+              nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
+    int n_sm = 0, occ = 0;
+    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    // per device, so set on every launch path (a second context on another GPU of the same process needs it too)
+    OC_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    const size_t smem = slow ? 0 : SWEEP_SMEM;
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, smem));
+    int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
+    // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
+    // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
+    // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
+    if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
+    unsigned char *glists = nullptr;
+    if (slow) {
+        const size_t per_warp = (size_t)cap * SWEEP_SLOT_BYTES;
+        const size_t budget = (size_t)1 << 30;  // at most 1 GiB of candidate lists: fewer resident warps instead
+        grid = (int)std::max<size_t>(1, std::min<size_t>(grid, budget / (per_warp * SWEEP_WARPS)));
+        const size_t need = per_warp * SWEEP_WARPS * grid;
+        if (ctx->gcfm_glist_bytes < need) {
+            if (ctx->gcfm_glist) cudaFree(ctx->gcfm_glist);
+            ctx->gcfm_glist = nullptr; ctx->gcfm_glist_bytes = 0;
+            if (cudaMalloc(&ctx->gcfm_glist, need) != cudaSuccess) {
+                cudaGetLastError();
+                oc::set_error("cannot allocate %zu bytes of candidate lists for the exact slow path", need);
+                return OC_ERR_NOMEM;
+            }
+            ctx->gcfm_glist_bytes = need;
+        }
+        glists = (unsigned char *)ctx->gcfm_glist;
+    }
+    sweep_kernel<<<grid, SWEEP_WARPS * 32, smem, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes, L.key, tag,
+                                                      inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns, margin, cap, glists);
+    exit_compact_kernel<<<1, 1024, 0, st>>>(N, L.w, L.pinned);
+    oc::count_launch(2);
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
 }
 
 extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y,
@@ -894,18 +1022,23 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
     OC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    // candidate bins: cell size (cutoff + margin)/2, search +-2 cells
+    // the bin table is sized for the fast path's cells (the slow path only ever uses larger cells, i.e. fewer bins)
     const double reach = prm->cutoff + DISP_MARGIN;
-    const double cs = reach / 2.0, inv_cs = 1.0 / cs;
+    const double inv_cs = 2.0 / reach;
     const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
               nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
     const int nbins = nbx * nby;
     int n_doors = 0;
     for (int k = 0; k < n_keys; k++) n_doors += keys[k].n_doors;
-    Ws w{};
+    if (!ctx->gcfm_last) ctx->gcfm_last = new GcfmLaunch();
+    GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
+    Ws &w = L.w;
     int *pinned = nullptr;
     int rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned, st);
     if (rc) return rc;
+    L.prm = *prm; L.N = N; L.n_keys = n_keys; L.n_doors = n_doors; L.nbins_alloc = nbins;
+    L.x = d_x; L.y = d_y; L.vx = d_vx; L.vy = d_vy; L.tim = d_time; L.status = d_status; L.vdes = d_vdes; L.key = d_key;
+    L.pinned = pinned;
     // upload keys, doors, perm, noise
     std::vector<KeyDev> hk(n_keys);
     std::vector<double> hd(4 * (size_t)std::max(n_doors, 1));
@@ -926,44 +1059,19 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     OC_CUDA(cudaMemcpyAsync(w.doors, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
     OC_CUDA(cudaMemcpyAsync(w.perm, perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
     if (n_noise) OC_CUDA(cudaMemcpyAsync(w.noise, noise, sizeof(double) * 2 * n_noise, cudaMemcpyHostToDevice, st));
-    OC_CUDA(cudaMemsetAsync(w.bin_start, 0, sizeof(int) * (nbins + 1), st));
-    OC_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int) * (nbins + 1), st));
-    OC_CUDA(cudaMemsetAsync(w.exit_mark, 0, sizeof(int) * N, st));
-    OC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * 8, st));
-    if (++g_tag >= 0x3fffffff) g_tag = 1;
-    const int tag = g_tag;
-    const int nb = (N + 255) / 256;
-    setup_kernel<<<nb, 256, 0, st>>>(N, d_x, d_y, d_vx, d_vy, d_status, w, inv_cs, nbx, nby);
-    scan_kernel<<<1, 1024, 0, st>>>(w.bin_start, nbins + 1);
-    scatter_kernel<<<nb, 256, 0, st>>>(N, w);
+    const int tag = gcfm_sweep_attempt(ctx, L, st, DISP_MARGIN, true);
+    if (tag < 0) return tag;
     noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
     prepare_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(*prm, N, w, ctx->d_X, ctx->d_Y, d_vdes, d_key, simu_step);
-    if (prm->own1 > prm->own0 && ctx->nccl_comm && ctx->nranks > 1) {
+    oc::count_launch(2);
+    if ((prm->own1 > prm->own0 || prm->key_mod > 0) && ctx->nccl_comm && ctx->nranks > 1) {
         // merge the per-agent terms over the ranks: des_x, des_y, wfx, wfy are carved back to back (padding is zero),
         // every agent was written by exactly one rank and is all-zero bits elsewhere; the sampler-range flag likewise
         const size_t words = (size_t)((w.wfy + N) - w.des_x);
         if ((rc = oc_dist_allreduce_max_u64(ctx, w.des_x, words, st))) return rc;
         if ((rc = oc_dist_allreduce_max_u64(ctx, w.counters, 4, st))) return rc;  // 8 ints
     }
-    int n_sm = 0;
-    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-    int occ = 0;
-    static bool sweep_attr = false;
-    if (!sweep_attr) {
-        OC_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
-        sweep_attr = true;
-    }
-    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, SWEEP_SMEM));
-    int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
-    // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
-    // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
-    // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
-    if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
-    sweep_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_SMEM, st>>>(*prm, N, w, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key,
-                                                    tag, inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns);
-    exit_compact_kernel<<<1, 1024, 0, st>>>(N, w, pinned);
-    oc::count_launch(7);
-    OC_CUDA(cudaGetLastError());
+    if ((rc = gcfm_launch_sweep(ctx, L, st, tag, DISP_MARGIN, CAND_CAP, false))) return rc;
     OC_CUDA(cudaEventRecord(ctx->ev1, st));
     // hk / hd are pageable: cudaMemcpyAsync has already staged them when it returned
     ctx->gcfm_stream = st;
@@ -972,37 +1080,77 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
 }
 
 extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
-    OC_ARG(ctx && ctx->gcfm_pending, "no GCFM step in flight");
+    OC_ARG(ctx && ctx->gcfm_pending && ctx->gcfm_last, "no GCFM step in flight");
     OC_CUDA(cudaSetDevice(ctx->device));
     ctx->gcfm_pending = false;
-    OC_CUDA(cudaStreamSynchronize((cudaStream_t)ctx->gcfm_stream));  // host-visible exit log
+    cudaStream_t st = (cudaStream_t)ctx->gcfm_stream;
+    GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
+    OC_CUDA(cudaStreamSynchronize(st));  // host-visible exit log
+    const int *pinned = (const int *)ctx->gcfm_pinned;
+    // Exact slow path (rare).  The fast attempt keeps at most CAND_CAP candidates per agent in shared memory and
+    // searches them within cutoff + DISP_MARGIN of the agent's old position.  An attempt that met more candidates, or
+    // moved an agent further than the margin covers, is void: the state is restored from the step-start snapshot and
+    // the step is redone with global-memory lists sized from the measured candidate count and with a margin that
+    // covers the measured displacement, until an attempt is self-consistent.  The reference has neither limit
+    // (simulations.py:285-303: all pairs, repulsions add to the velocity unclipped).
+    double margin = DISP_MARGIN;
+    int cap = CAND_CAP;
+    ctx->gcfm_redos = 0;
+    for (int redo = 0; (pinned[1] & 6) != 0; redo++) {
+        const double room_diag = std::sqrt(ctx->room_length * ctx->room_length + ctx->room_height * ctx->room_height);
+        if (redo >= 12 || margin > 4.0 * room_diag + 8.0) {
+            oc::set_error("GCFM step: no self-consistent candidate search (displacement %g m, %d candidates)", margin * 0.5, cap);
+            return OC_ERR_ARG;
+        }
+        if (pinned[1] & 4) {
+            double disp;
+            memcpy(&disp, pinned + 4, sizeof(double));
+            // NaN / inf displacement: widen geometrically up to the whole room, then give up above
+            margin = (disp == disp && disp < 1e300) ? std::max(2.0 * margin, 2.2 * disp) : 4.0 * margin;
+        }
+        {   // lists for every candidate the void attempt counted; a wider search finds more: the loop adapts
+            long long want = std::max<long long>(pinned[3], cap);
+            if (pinned[1] & 4) want = std::max<long long>(want, 2 * (long long)pinned[3]);
+            int c2 = CAND_CAP;
+            while (c2 < want && c2 < CAND_CAP_MAX) c2 <<= 1;
+            if (want > CAND_CAP_MAX) {
+                oc::set_error("more than %d agents within the repulsion reach of one agent", CAND_CAP_MAX);
+                return OC_ERR_ARG;
+            }
+            cap = c2;
+        }
+        const int tag = gcfm_sweep_attempt(ctx, L, st, margin, false);
+        if (tag < 0) return tag;
+        int rc = gcfm_launch_sweep(ctx, L, st, tag, margin, cap, true);
+        if (rc) return rc;
+        OC_CUDA(cudaEventRecord(ctx->ev1, st));
+        OC_CUDA(cudaStreamSynchronize(st));
+        ctx->gcfm_redos = redo + 1;
+    }
     {
         float ms = 0;
         OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->gcfm_last_ms = ms;
     }
-    const int *pinned = (const int *)ctx->gcfm_pinned;
+    ctx->gcfm_last_pairs = pinned[2];
     int ne = pinned[0], fl = pinned[1];
     if (n_exit) *n_exit = ne;
     if (exit_log)
-        for (int q = 0; q < ne; q++) exit_log[q] = pinned[2 + q];
-    if (fl & 2) {
-        oc::set_error("more than %d agents within the repulsion cutoff of one agent", LIST_CAP);
-        return OC_ERR_ARG;
-    }
-    if (fl & 4) {
-        oc::set_error("an agent moved more than %.2f m in one step: outside the sweep's candidate search margin",
-                      DISP_MARGIN * 0.5);
-        return OC_ERR_ARG;
-    }
+        for (int q = 0; q < ne; q++) exit_log[q] = pinned[OUT_HDR + q];
     if (fl & 1) {
-        oc::set_error("agent position outside the sampler's index range (reference: IndexError / negative wrap)");
+        oc::set_error("agent position outside the sampler's index range (the reference raises IndexError here)");
         return OC_ERR_SAMPLER_RANGE;
     }
     return OC_OK;
 }
 
 extern "C" double oc_gcfm_last_ms(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_ms : 0.0; }
+extern "C" long long oc_gcfm_last_pairs(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_pairs : 0; }
+extern "C" int oc_gcfm_last_redos(oc_ctx *ctx) { return ctx ? ctx->gcfm_redos : 0; }
+void oc_gcfm_free_launch_state(oc_ctx *ctx) {  // oc_ctx_destroy (oc_api.cu)
+    if (ctx && ctx->gcfm_last) { delete static_cast<GcfmLaunch *>(ctx->gcfm_last); ctx->gcfm_last = nullptr; }
+    if (ctx && ctx->gcfm_glist) { cudaFree(ctx->gcfm_glist); ctx->gcfm_glist = nullptr; ctx->gcfm_glist_bytes = 0; }
+}
 
 extern "C" int oc_wall_force(oc_ctx *ctx, const oc_gcfm_params *prm, const double *d_V, int N, const double *d_x,
                              const double *d_y, const double *d_vx, const double *d_vy, const double *d_vdes,

@@ -12,7 +12,20 @@
  * Algorithms: classic argument reduction + minimax polynomials (Sun fdlibm family of
  * approximations: exp via r = x - k ln2 and a degree-5 rational-form kernel, atan via 4-interval
  * reduction and a degree-11 odd polynomial, sin/cos via 3-term Cody-Waite reduction by pi/2 and
- * degree-13/14 kernels).  Max observed error vs numpy < 1 ulp (tests/test_oc_math.py).
+ * degree-13/14 kernels).  Max observed error vs numpy < 1 ulp (tests/test_cpu_oracle.py::test_oc_math_*).
+ *
+ * The polynomial coefficients and the reduction constants (P1..P5, aT[], atanhi/atanlo, S1..S6, C1..C6, the
+ * pio2 splits) are those of FreeBSD/Sun fdlibm (e_exp.c, s_atan.c, k_sin.c, k_cos.c, e_rem_pio2.c), whose notice
+ * is reproduced here as its licence asks:
+ *
+ *   ====================================================
+ *   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *
+ *   Developed at SunSoft, a Sun Microsystems, Inc. business.
+ *   Permission to use, copy, modify, and distribute this
+ *   software is freely granted, provided that this notice
+ *   is preserved.
+ *   ====================================================
  *
  * This header is product code.  The CPU oracle (oracle/) includes it for these elementary
  * functions ONLY, and tests pin them against numpy; all GCFM formulae are restated independently
@@ -60,6 +73,12 @@ OCM_FN int ocm_isnan(double x) { return x != x; }
 /* sqrt(fma(y,y,x*x)): what np.linalg.norm of a 2-vector evaluates to through OpenBLAS ddot on
  * FMA-capable x86.  fma and sqrt are correctly rounded everywhere. */
 OCM_FN double ocm_norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+
+/* np.minimum / np.maximum: a NaN operand gives NaN (C's and CUDA's fmin / fmax return the other operand instead).
+ * pedestrians.py:243-245,262,278,332 use them on quantities that are NaN for coincident agents or an agent exactly
+ * on a wall node (R = 0 -> e = 0/0), and the reference's forces are NaN there. */
+OCM_FN double ocm_npmin(double a, double b) { return (a <= b || a != a) ? a : b; }  /* numpy's scalar loop, verbatim */
+OCM_FN double ocm_npmax(double a, double b) { return (a >= b || a != a) ? a : b; }
 
 /* 2^k for k in [-1022, 1023] */
 OCM_FN double ocm_pow2i(int k) { return ocm_from_bits((uint64_t)(k + 1023) << 52); }

@@ -77,6 +77,13 @@ def enable_peer_memory(ctx, all_agree=None) -> bool:
     return ok
 
 
+def init_comm(ctx, make_id=nccl_unique_id):
+    """communicator only (key-sharded runs: no row bands, no peer-memory mapping)"""
+    import torch.distributed as dist
+    ctx.dist_init(share_unique_id(make_id), dist.get_rank(), dist.get_world_size())
+    ctx.peer_memory = False
+
+
 def init_context(ctx, make_id=nccl_unique_id, peer_memory=True):
     """create the library's communicator for `ctx` on every rank of the default process group (and, on one NVSwitch box,
     map the ranks' band arrays into each other for the peer-memory exchange)"""

@@ -6,8 +6,10 @@ Same constructor, methods and attributes as the reference:
 ``draw_optimal_velocity()``, ``vx_opt, vy_opt, nt_opt, V, phi_T, lim, ...``.
 
 Differences that do not change results:
-  * the field lives on the device (``d_vx``, ``d_vy``: torch CUDA tensors of shape (nt-1, Ny-2, Nx-2));
-    ``vx_opt`` / ``vy_opt`` are numpy views materialised on first access after a solve;
+  * the field lives on the device, by default as the value-function samples ``d_phi`` (nt, Ny, Nx) from which the
+    GCFM sampler and ``vx_opt`` / ``vy_opt`` (numpy arrays materialised on first access after a solve) are derived
+    with the reference's ``vels`` formula, bit-identically; ``field_storage='velocity'`` stores ``d_vx``, ``d_vy``
+    (nt-1, Ny-2, Nx-2) like the reference instead;
   * ``V`` may be handed over as a numpy array (mutated in place like optimals.py:89-91) or a CUDA tensor.
 """
 from __future__ import annotations
@@ -37,9 +39,11 @@ def _load_room(room):
 
 
 class optimals:
-    def __init__(self, room, V, T, target, _ctx=None, _config=None, field_storage="velocity", fused=1, band=None):
+    def __init__(self, room, V, T, target, _ctx=None, _config=None, field_storage="phi", fused=1, band=None, owned=True):
         """``band = (own0, own1)``: this process holds only node rows [own0, own1) of the field (one rank of a
-        row-decomposed run; the context must carry a communicator, dist.init_context)."""
+        row-decomposed run; the context must carry a communicator, dist.init_context).
+        ``owned = False``: another rank solves and holds this target set's field (key-sharded run, one HJB key per
+        GPU): no field is allocated here and compute_optimal_velocity only keeps ``nt_opt`` in step."""
         var_config = _config if _config is not None else _load_config()
         var_room = _load_room(room)
         self.room_length = var_room['room_length']
@@ -82,7 +86,10 @@ class optimals:
         self.d_tiles, self.v_min = self._ctx.wall_tiles(self.d_V)
         n_slices = max(self.nt_opt - 1, 0)
         self._n_slices = n_slices
-        if field_storage == "velocity":
+        self.owned = bool(owned)
+        if not self.owned:
+            self.d_vx = self.d_vy = self.d_phi = None
+        elif field_storage == "velocity":
             self.d_vx = torch.empty((n_slices, self.Ny - 2, self.Nx - 2), dtype=torch.float64, device=self.d_V.device)
             self.d_vy = torch.empty_like(self.d_vx)
             self.d_phi = None
@@ -154,23 +161,35 @@ class optimals:
         if nt < 1:
             # reference: np.linspace(T,0,0) -> solve_ivp raises on an empty t_eval
             raise ValueError("Values in `t_eval` are not within `t_span`.")
+        if not self.owned:
+            return  # the owning rank solves (and prints); only nt_opt changes here
         if m is None or (np.isscalar(m) and m == 0):
             d_m = None
         elif isinstance(m, np.ndarray):
             # host density -> persistent device buffer; the solve below synchronises the stream, which also
-            # covers the (asynchronous) copy from a page-locked source
+            # covers the (asynchronous) copy from a page-locked source.  A row-decomposed field only needs (and only
+            # uploads) the rows of its band.
+            mh = np.asarray(m, dtype=np.float64)
+            if self.band is not None and mh.size == (self.band[1] - self.band[0]) * self.Nx:
+                mh = mh.reshape(-1, self.Nx)            # already this rank's rows
+            else:
+                mh = mh.reshape(self.Ny, self.Nx)
+                if self.band is not None:
+                    mh = mh[self.band[0]:self.band[1]]
             if self._d_m is None:
-                self._d_m = self._ctx.empty(self.Ny, self.Nx)
-            _keep = self._ctx.upload(np.asarray(m, dtype=np.float64).reshape(self.Ny, self.Nx), self._d_m)
+                self._d_m = self._ctx.empty(*mh.shape)
+            _keep = self._ctx.upload(mh, self._d_m)
             d_m = self._d_m
         else:
-            d_m = m.reshape(self.Ny, self.Nx)
+            d_m = m if (self.band is not None and m.shape[0] == self.band[1] - self.band[0]) else m.reshape(self.Ny, self.Nx)
         if nt - 1 > self._n_slices:
             raise IndexError("re-solve asks for more slices than the field was allocated for")  # as numpy would
         if self.band is not None:
             own0, own1 = self.band
-            res = self._ctx.hjb_solve_band(self.d_V[own0:own1], None if d_m is None else d_m[own0:own1].contiguous(),
-                                           self._prm, self.T, nt, own=(own0, own1), out_phi=self.d_phi, phi_extra_hi=1)
+            if d_m is not None and d_m.shape[0] != own1 - own0:
+                d_m = d_m[own0:own1].contiguous()   # a full-grid device density: this rank's rows
+            res = self._ctx.hjb_solve_band(self.d_V[own0:own1], d_m, self._prm, self.T, nt, own=(own0, own1),
+                                           out_phi=self.d_phi, phi_extra_hi=1)
         elif self.field_storage == "velocity":
             res = self._ctx.hjb_solve(self.d_V, d_m, self._prm, self.T, nt, want_phi=False, want_vel=nt > 1,
                                       out_vx=self.d_vx, out_vy=self.d_vy)

@@ -25,20 +25,36 @@ warnings.filterwarnings("ignore")  # simulations.py:15
 
 
 class _Frame(list):
-    """One history frame: a list whose LAST element (the density array) is materialised on first access."""
+    """One history frame ``[[pos, vel, target, v_des] per agent inside ..., density]`` (simulations.py:579-589), built
+    on first access: the agents' rows come from the device-resident trajectory record (row k = state before step k)
+    and the density -- which the reference splats on every step although only draw_history('density') reads it --
+    is computed when the LAST element is read."""
 
     def __init__(self, agents, density_fn):
-        super().__init__(agents)
-        super().append(None)
+        """agents: the rows, or a function that returns them (called on first access)"""
+        super().__init__()
+        self._agents_fn = agents if callable(agents) else (lambda: agents)
         self._density_fn = density_fn
 
+    def _rows(self):
+        if self._agents_fn is not None:
+            fn, self._agents_fn = self._agents_fn, None
+            list.extend(self, fn())
+            list.append(self, None)
+
     def _fill(self):
+        self._rows()
         if self._density_fn is not None:
             fn, self._density_fn = self._density_fn, None
-            list.__setitem__(self, len(self) - 1, fn())
+            list.__setitem__(self, list.__len__(self) - 1, fn())
+
+    def __len__(self):
+        self._rows()
+        return list.__len__(self)
 
     def __getitem__(self, i):
-        n = len(self)
+        self._rows()
+        n = list.__len__(self)
         if (len(range(*i.indices(n))[-1:]) and range(*i.indices(n))[-1] == n - 1) if isinstance(i, slice) \
                 else (i == -1 or i == n - 1):
             self._fill()
@@ -48,18 +64,33 @@ class _Frame(list):
         self._fill()
         return list.__iter__(self)
 
+    def __repr__(self):
+        self._fill()
+        return list.__repr__(self)
+
+    def __eq__(self, other):
+        self._fill()
+        return list.__eq__(self, other)
+
 
 class simulation:
 
-    def __init__(self, room, T, recompute=False, record=True, field_storage="velocity", fused=1, lookahead=True,
-                 rng=None, chunk_rows=0, band=False):
+    TRACK_CHUNK = 64  # steps per block of the device-resident trajectory record
+
+    def __init__(self, room, T, recompute=False, record=True, field_storage="phi", fused=1, lookahead=True,
+                 rng=None, chunk_rows=0, band=False, shard_keys=False):
         """``room, T, recompute`` as in the reference (simulations.py:20).  Extras, all defaulting to reference
-        behaviour: ``record`` (keep per-step host copies for traj/history), ``field_storage`` ('velocity' slices like
-        the reference or 'phi' samples, half the memory), ``rng`` (a ``np.random.RandomState``; default = numpy's
+        behaviour: ``record`` (keep the per-step record behind ped.traj / ped.vels / history; it lives on the device and
+        is read back on access), ``field_storage`` ('phi': the value-function samples, from which ``vx_opt`` /
+        ``vy_opt`` are produced on access and which the sampler differentiates on the fly, bit-identical and half the
+        memory; 'velocity': (vx, vy) slices stored like the reference), ``rng`` (a ``np.random.RandomState``; default = numpy's
         legacy global generator, which the reference uses), ``chunk_rows`` (fixes the HJB reduction order),
         ``band`` (True: this process is one rank of a row-decomposed run under torch.distributed -- it solves and
         stores only its band of rows of every HJB field, evaluates the field samples and wall forces of the agents
-        in its band, and runs the (replicated, deterministic) sweep; every rank must use the same seed)."""
+        in its band, and runs the (replicated, deterministic) sweep; every rank must use the same seed),
+        ``shard_keys`` (True: the target sets -- one HJB field each, simulations.py:113-121 -- are dealt round-robin to the
+        ranks of torch.distributed: a rank solves and stores only its keys' fields and evaluates the field samples / wall
+        forces of the agents heading for them; merge and sweep as for ``band``)."""
         import torch
         self._np_random = rng if rng is not None else np.random
         self.recompute = recompute
@@ -99,6 +130,16 @@ class simulation:
             self._gcfm_prm.own0, self._gcfm_prm.own1 = self._band
             if field_storage != "phi":
                 raise ValueError("band=True stores the field as phi samples: pass field_storage='phi'")
+        self._key_shard = None
+        if shard_keys:
+            import torch.distributed as tdist
+            from . import dist as _dist
+            if band:
+                raise ValueError("band and shard_keys are alternative decompositions")
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                _dist.init_comm(self._ctx)
+                self._key_shard = (tdist.get_world_size(), tdist.get_rank())
+                self._gcfm_prm.key_mod, self._gcfm_prm.key_rem = self._key_shard
         diag = float(np.hypot(self.room_length, self.room_height))
         if abs(self.pot) * 10e3 <= diag:
             raise NotImplementedError("wall search assumes |wall_potential|*10e3 exceeds the room diagonal")
@@ -123,8 +164,10 @@ class simulation:
                 # SURVEY App. C #12); building them once per key gives the same objects and the same RNG stream.
                 V = self.create_potential(var_room, targets)
                 self.Vs[key] = V
+                owned = self._key_shard is None or len(self.targets) % self._key_shard[0] == self._key_shard[1]
                 self.targets[key] = optimals.optimals(var_room, V, T, key, _ctx=self._ctx, _config=var_config,
-                                                      field_storage=field_storage, fused=fused, band=self._band)
+                                                      field_storage=field_storage, fused=fused, band=self._band,
+                                                      owned=owned)
                 self.targets[key]._prm.chunk_rows = int(chunk_rows)
             box_count[key] = box_count.get(key, 0) + 1
             xs, ys, v_des_all = _crowd.place_box(box, X1, Y1, self.place_ped, r_in, self._np_random)
@@ -161,12 +204,18 @@ class simulation:
         self._d_vdes = ctx.to_device(self._h_vdes)
         self._d_key = ctx.to_device(self._h_key)
         self._d_Vglobal = ctx.to_device(self.V)
-        # per-step host record of (x, y, vx, vy); row k = state after k steps (ped.traj / ped.vels views)
-        self._track = [np.column_stack([x0, y0, np.zeros(N), np.zeros(N)])]
+        # per-step record of (x, y, vx, vy); row k = state after k steps (ped.traj / ped.vels / history views).  It
+        # lives on the DEVICE in blocks of TRACK_CHUNK steps, written by one small kernel per step (oc_state_pack), and
+        # is read back -- once per row -- only when somebody looks at it
+        self._row0 = np.column_stack([x0, y0, np.zeros(N), np.zeros(N)])
+        self._d_track = []                                  # device blocks (TRACK_CHUNK, N, 4)
+        self._n_rows = 1                                    # rows recorded so far (row 0 = initial state)
+        self._h_rows = [self._row0]                         # host copies of rows 0 .. len-1 (filled on demand)
         self._exit_step = np.full(N, -1, dtype=np.int64)   # step index at which the agent left
         self._exit_order = []                               # agent ids in exit order over the whole run
-        self._h_now = self._track[0]
-        self._h_timev = np.zeros(N)
+        self._h_now_cache = self._row0
+        self._h_timev_cache = np.zeros(N)
+        self._host_dirty = False                            # device state is ahead of _h_now_cache / _h_timev_cache
         print('ABM simulation room created!')               # simulations.py:162
 
     # ---- helpers -------------------------------------------------------------------------------------
@@ -182,8 +231,50 @@ class simulation:
         st = self._state
         import torch
         packed = torch.stack([st["x"], st["y"], st["vx"], st["vy"], st["time"]], dim=1).cpu().numpy()
-        self._h_now = packed[:, :4]
-        self._h_timev = packed[:, 4].copy()
+        self._h_now_cache = packed[:, :4]
+        self._h_timev_cache = packed[:, 4].copy()
+        self._host_dirty = False
+
+    @property
+    def _h_now(self):
+        """(N,4) host copy of the current x, y, vx, vy (refreshed from the device when a step has run since)"""
+        if self._host_dirty:
+            self._sync_host()
+        return self._h_now_cache
+
+    @property
+    def _h_timev(self):
+        if self._host_dirty:
+            self._sync_host()
+        return self._h_timev_cache
+
+    @property
+    def _track(self):
+        """host view of the whole record: list of (N,4) rows, row k = state after k steps"""
+        return self._rows_upto(self._n_rows - 1)
+
+    def _record_row(self):
+        """append the current device state to the device-resident record"""
+        import torch
+        k = self._n_rows - 1                                # rows 1.. live in the blocks: row r -> block (r-1)//C
+        blk, off = divmod(k, self.TRACK_CHUNK)
+        if blk == len(self._d_track):
+            self._d_track.append(torch.empty((self.TRACK_CHUNK, max(self.N, 1), 4), dtype=torch.float64,
+                                             device=self._ctx.torch_device))
+        if self.N:
+            self._ctx.state_pack(self._state, self._d_track[blk][off])
+        self._n_rows += 1
+
+    def _rows_upto(self, last):
+        """host copies of rows 0..last (one device read per block touched, cached)"""
+        have = len(self._h_rows)
+        while have <= last:
+            blk, off = divmod(have - 1, self.TRACK_CHUNK)
+            n = min(self.TRACK_CHUNK - off, self._n_rows - have)
+            part = self._d_track[blk][off:off + n].cpu().numpy()
+            self._h_rows.extend(part[q] for q in range(n))
+            have += n
+        return self._h_rows
 
     def _agent_now(self, i):
         r = self._h_now[i]
@@ -195,9 +286,13 @@ class simulation:
 
     def _agent_track(self, i, which):
         """list of per-step positions (which=0) or velocities (which=1) up to the agent's exit (ped.traj/vels)."""
-        last = self._exit_step[i] + 1 if self._exit_step[i] >= 0 else len(self._track) - 1
+        if not self._record and self._n_rows == 1 and self.simu_step > 0:
+            raise RuntimeError("this simulation was created with record=False: no trajectories were kept")
+        last = self._exit_step[i] + 1 if self._exit_step[i] >= 0 else self._n_rows - 1
+        last = min(last, self._n_rows - 1)
+        rows = self._rows_upto(last)
         sl = slice(0, 2) if which == 0 else slice(2, 4)
-        return [np.array(self._track[k][i, sl], dtype=float) for k in range(min(last, len(self._track) - 1) + 1)]
+        return [np.array(rows[k][i, sl], dtype=float) for k in range(last + 1)]
 
     def _set_status(self, i, v):
         self._h_status[i] = 1 if v else 0
@@ -227,6 +322,7 @@ class simulation:
         if dt != self.dt:
             prm = _lib.gcfm_params(dict(self._config, dt=dt), self.room_length, self.room_height, self.Ny, self.Nx)
             prm.own0, prm.own1 = self._gcfm_prm.own0, self._gcfm_prm.own1
+            prm.key_mod, prm.key_rem = self._gcfm_prm.key_mod, self._gcfm_prm.key_rem
         else:
             prm = self._gcfm_prm
         pending = None
@@ -246,15 +342,15 @@ class simulation:
             exits, rc = self._ctx.gcfm_step_finish(pending)
             if rc == _lib.OC_ERR_SAMPLER_RANGE:
                 raise IndexError("agent position outside the velocity field's index range "
-                                 "(the reference raises here too: optimals.py:247)")
+                                 "(numpy raises IndexError in the reference's sampler too: optimals.py:247)")
             for a in exits:
                 self._h_status[a] = 0
                 self._exit_step[a] = self.simu_step
                 self._exit_order.append(int(a))
             self.inside += -len(exits)
+            self._host_dirty = True
             if self._record:
-                self._sync_host()
-                self._track.append(np.array(self._h_now))
+                self._record_row()
         self.time += dt
         self.simu_step += 1
         if verbose:
@@ -264,8 +360,6 @@ class simulation:
     def evac_times(self, draw=False):
         if self.inside > 0:
             raise ValueError('There are still people inside!')
-        if not self._record:
-            self._sync_host()
         times = np.array(self._h_timev, dtype=float)
         if draw:
             import matplotlib.pyplot as plt
@@ -280,7 +374,7 @@ class simulation:
             return times
 
     def initial_positions(self):
-        return np.array(self._track[0][:, 0], dtype=float), np.array(self._track[0][:, 1], dtype=float)
+        return np.array(self._row0[:, 0], dtype=float), np.array(self._row0[:, 1], dtype=float)
 
     # ---- simulations.py:401-451 ----------------------------------------------------------------------
     def run(self, verbose=False, draw=False, mode='scatter'):
@@ -326,17 +420,29 @@ class simulation:
     # ---- simulations.py:579-589 ----------------------------------------------------------------------
     def write_history(self, time):
         """history[time] = [[pos, vel, target, v_des] per agent inside, ..., density] (simulations.py:579-589).
-        The reference splats the density (O(N Nx Ny) exps) on every step although only draw_history('density')
-        reads it; here the last element is computed on first access, from the positions stored in the frame."""
-        frame = []
-        now = self._h_now
+        The frame is a view of the device-resident record: row ``simu_step`` holds the state this frame describes and
+        the agents inside are those that have not left before this step; nothing is copied or splatted until the frame
+        is read (the reference splats the density, O(N Nx Ny) exps, on every step although only
+        draw_history('density') reads it).  With ``record=False`` no record exists: the frame is built right away from
+        the current state (one device read), as the reference does."""
         keys = list(self.targets)
-        act = np.nonzero(self._h_status)[0]
-        for i in act:
-            frame.append([np.array(now[i, :2], dtype=float), np.array(now[i, 2:], dtype=float),
-                          keys[self._h_key[i]], self._h_vdes[i]])
-        xy = np.array(now[act, :2], dtype=np.float64)
-        self.history[time] = _Frame(frame, lambda xy=xy: self._density_of(xy, self.sigma_convolution))
+        k = self.simu_step
+
+        def rows_of(now, act):
+            return [[np.array(now[i, :2], dtype=float), np.array(now[i, 2:], dtype=float), keys[self._h_key[i]],
+                     self._h_vdes[i]] for i in act]
+
+        if self._record and k < self._n_rows:
+            active = lambda: np.nonzero((self._exit_step < 0) | (self._exit_step >= k))[0]
+            agents_fn = lambda: rows_of(self._rows_upto(k)[k], active())
+            dens_fn = lambda: self._density_of(np.array(self._rows_upto(k)[k][active(), :2], dtype=np.float64),
+                                               self.sigma_convolution)
+            self.history[time] = _Frame(agents_fn, dens_fn)
+        else:
+            now = np.array(self._h_now)
+            act = np.nonzero(self._h_status)[0]
+            xy = np.array(now[act, :2], dtype=np.float64)
+            self.history[time] = _Frame(lambda: rows_of(now, act), lambda: self._density_of(xy, self.sigma_convolution))
 
     def _density_of(self, xy, sigma):
         """density of the crowd at positions xy (n,2), all inside: same kernel, same summation order (agents inside,

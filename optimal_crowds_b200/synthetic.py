@@ -86,3 +86,29 @@ def ensemble_room(n: int = 512, agents: int = 1000) -> dict:
             "targets": {"door": [L, H / 2, 0.6, 2.0]}, "walls": {}, "holes": {},
             "cylinders": {"c1": [L - 2.0, H / 2 + 2.0, 0.3], "c2": [L - 2.0, H / 2 - 2.0, 0.3],
                           "c3": [L - 3.5, H / 2, 0.3]}}
+
+
+def parity_room(nx: int = 2048, ny: int = 512, bands: int = 2, per_box: int = 30) -> dict:
+    """Reduced room for the multi-GPU parity check of bench.py: one target set, and per row band a door with a small
+    box of agents right next to it (so that agents leave within ~40 steps, in every band), a wall that straddles every
+    internal band edge and a pillar -- everything a row-decomposed run can get wrong sits on or near a band edge."""
+    L, H = nodes_to_length(nx), nodes_to_length(ny)
+    bh = H / bands
+    targets, boxes, walls, cyl = {}, {}, {}, {}
+    for b in range(bands):
+        yc = (b + 0.5) * bh
+        for q, xc in enumerate((L * 0.25, L * 0.7)):
+            targets[f"door_{b}_{q}"] = [xc, yc, 1.2, 1.2]
+            cyl[f"pillar_{b}_{q}"] = [xc + 2.5, yc + 0.4, 0.3]
+        if b > 0:
+            walls[f"edge_{b}"] = [L / 2, b * bh, L / 3, 0.6]          # straddles the edge between bands b-1 and b
+            targets[f"edge_door_{b}"] = [L * 0.9, b * bh, 1.0, 1.0]   # a door cut by the band edge
+    names = list(targets)
+    for b in range(bands):
+        yc = (b + 0.5) * bh
+        for q, xc in enumerate((L * 0.25, L * 0.7)):
+            boxes[f"box_{b}_{q}"] = [xc - 1.4, yc, 2.0, 2.0, (per_box + 0.5) / 4.0] + names   # int(rho*w*h) == per_box
+        if b > 0:
+            boxes[f"edge_box_{b}"] = [L * 0.9 - 1.4, b * bh, 2.0, 2.0, (per_box + 0.5) / 4.0] + names
+    return {"room_length": L, "room_height": H, "initial_boxes": boxes, "targets": targets, "walls": walls,
+            "holes": {}, "cylinders": cyl}

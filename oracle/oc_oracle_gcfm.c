@@ -85,7 +85,7 @@ static double py_floordiv(double vx, double wx) {
     return copysign(0.0, vx / wx);
 }
 
-/* optimals.py:212-250.  Returns 0 ok, 1 if the reference would index out of range / wrap (App. C #7). */
+/* optimals.py:212-250.  Returns 0 ok, 1 if the reference would raise IndexError (App. C #7). */
 int oco_choose_velocity(const oco_gcfm_params *p, const oco_key *k, double x, double y, int t,
                         double *ox, double *oy) {
     if (t >= k->nt_opt - 1) { *ox = 0.0; *oy = 0.0; return 0; }
@@ -99,6 +99,9 @@ int oco_choose_velocity(const oco_gcfm_params *p, const oco_key *k, double x, do
         i1 = (y > p->dy) ? i0 + 1 : i0;
     } else { i0 = i1 = p->Ny - 3; }
     int W = p->Nx - 2, H = p->Ny - 2;
+    /* numpy wraps negative indices (x < 0 or y < 0; then the index list has one element) */
+    if (j0 < 0) { j0 += W; j1 = j0; }
+    if (i0 < 0) { i0 += H; i1 = i0; }
     if (j0 < 0 || j1 >= W || i0 < 0 || i1 >= H || t < 0 || t >= k->n_slices) { *ox = 0; *oy = 0; return 1; }
     const double *sx = k->vx_opt + (size_t)t * W * H, *sy = k->vy_opt + (size_t)t * W * H;
     if (j0 == j1 && i0 == i1) { /* scalar: np.mean of a 0-d value */
@@ -117,9 +120,9 @@ static void pair_force(const oco_gcfm_params *p, double xi, double yi, double vx
                        double *fy) {
     double ni = ocm_norm2(vxi, vyi), nj = ocm_norm2(vxj, vyj);
     double a_i = p->a_min + p->tau_a * ni;
-    double b_i = p->b_max - (p->b_max - p->b_min) * fmin(ni / v_des_i, 1.0);
+    double b_i = p->b_max - (p->b_max - p->b_min) * ocm_npmin(ni / v_des_i, 1.0);
     double a_j = p->a_min + p->tau_a * nj;
-    double b_j = p->b_max - (p->b_max - p->b_min) * fmin(nj / v_des_i, 1.0);
+    double b_j = p->b_max - (p->b_max - p->b_min) * ocm_npmin(nj / v_des_i, 1.0);
     double Rx = xj - xi, Ry = yj - yi;
     double nR = ocm_norm2(Rx, Ry);
     double ex = Rx / nR, ey = Ry / nR;
@@ -127,7 +130,7 @@ static void pair_force(const oco_gcfm_params *p, double xi, double yi, double vx
     double d = wx * (-ex) + wy * (-ey);
     double v_rel = 0.5 * (d + fabs(d));
     double k = 0.0;
-    if (ni > 0) k = fmax((vxi * ex + vyi * ey) / ni - p->cos_fov, 0.0) / p->one_minus_cos_fov;
+    if (ni > 0) k = ocm_npmax((vxi * ex + vyi * ey) / ni - p->cos_fov, 0.0) / p->one_minus_cos_fov;
     double alpha_i = ocm_atan2(Ry, Rx), beta_i = ocm_atan2(vyi, vxi);
     double alpha_j = ocm_atan2(-Ry, -Rx), beta_j = ocm_atan2(vyj, vxj);
     double ci = ocm_cos(alpha_i - beta_i) / a_i, si = ocm_sin(alpha_i - beta_i) / b_i;
@@ -135,7 +138,7 @@ static void pair_force(const oco_gcfm_params *p, double xi, double yi, double vx
     double cj = ocm_cos(alpha_j - beta_j) / a_j, sj = ocm_sin(alpha_j - beta_j) / b_j;
     double q_j = sqrt(1.0 / (cj * cj + sj * sj));
     double dist = nR - q_i - q_j;
-    double rep = fmin(k * ocm_exp(-dist / (p->eta * (1.0 + v_rel))), 1.0);
+    double rep = ocm_npmin(k * ocm_exp(-dist / (p->eta * (1.0 + v_rel))), 1.0);
     *fx = -rep * Rx;
     *fy = -rep * Ry;
 }
@@ -167,11 +170,11 @@ static void wall_force(const oco_gcfm_params *p, double xi, double yi, double vx
     double alpha = ocm_atan2(Ry, Rx), beta = ocm_atan2(vyi, vxi);
     double ni = ocm_norm2(vxi, vyi);
     double a_i = p->a_min + p->tau_a * ni;
-    double b_i = p->b_max - (p->b_max - p->b_min) * fmin(ni / v_des_i, 1.0);
+    double b_i = p->b_max - (p->b_max - p->b_min) * ocm_npmin(ni / v_des_i, 1.0);
     double c = ocm_cos(alpha - beta) / a_i, s = ocm_sin(alpha - beta) / b_i;
     double q_i = 1.0 / (c * c + s * s); /* no sqrt: pedestrians.py:328 */
     double dist = nR - q_i;
-    double rep = fmin(ocm_exp(-dist / (p->eta_walls * (1.0 + v_rel))), 1.0);
+    double rep = ocm_npmin(ocm_exp(-dist / (p->eta_walls * (1.0 + v_rel))), 1.0);
     *fx = -3.0 * rep * Rx;
     *fy = -3.0 * rep * Ry;
 }

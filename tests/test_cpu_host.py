@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in optimal_crowds.h but not exported"
     assert set(_lib.EXPORTS) <= declared
     lib.oc_abi_version.restype = ctypes.c_int
-    assert lib.oc_abi_version() == 1
+    assert lib.oc_abi_version() == 2
 
 
 def test_no_cpu_fallback_context_raises_without_gpu():
@@ -160,3 +160,7 @@ def test_history_frame_is_lazy():
     assert f[2] is f[-1] and calls == [1]                              # computed once
     g = _Frame([], lambda: np.zeros((2, 2)))
     assert [type(x) for x in g] == [np.ndarray]                        # iteration materialises the density
+    rows = []
+    h = _Frame(lambda: rows.append(1) or [["p", "v", "door", 1.0]], lambda: calls.append(2) or np.zeros(1))
+    assert not rows                                                    # the agents' rows are lazy too (device record)
+    assert len(h) == 2 and rows == [1] and h[0][0] == "p" and rows == [1] and calls == [1]

@@ -101,8 +101,11 @@ def test_sampler_index_semantics(L, H, seed):
     vx, vy = rng.normal(size=(nsl, Ny - 2, Nx - 2)), rng.normal(size=(nsl, Ny - 2, Nx - 2))
     P = co.gcfm_params(cfg, L, H, Ny, Nx)
     key = co.KeyData(np.zeros((Ny, Nx)), vx, vy, nsl + 1, [[L, H / 2, 0.5, 0.5]])
-    xs = np.concatenate([rng.uniform(0, L, 40), [0.0, 0.05, 0.049999, 0.050001, L - 0.05, L - 0.1, L - 0.0999, L]])
-    ys = np.concatenate([rng.uniform(0, H, 40), [0.0, 0.05, H - 0.05, H - 0.1, H - 0.0999, H, 0.1, 0.15000000000000002]])
+    # incl. positions outside the room: numpy wraps the negative indices of x < 0 / y < 0 silently (App. C #7)
+    xs = np.concatenate([rng.uniform(0, L, 40), [0.0, 0.05, 0.049999, 0.050001, L - 0.05, L - 0.1, L - 0.0999, L],
+                         [-0.01, -0.05, -0.3, 1.0, -1e-9, -L, -L - 1.0, L + 0.3]])
+    ys = np.concatenate([rng.uniform(0, H, 40), [0.0, 0.05, H - 0.05, H - 0.1, H - 0.0999, H, 0.1, 0.15000000000000002],
+                         [0.5, -0.07, -0.02, -0.2, 0.3, 0.4, 0.5, -H - 0.5]])
     for x, y in zip(xs, ys):
         for t in (0, nsl - 1, nsl, nsl + 3):
             want = _sampler_spec(vx, vy, nsl + 1, L, H, 0.05, float(x), float(y), t)

@@ -395,3 +395,121 @@ def test_sweep_result_is_independent_of_the_schedule(cfg):
         assert all(np.array_equal(a, b) for a, b in zip(outs[0][1], ex))
     moved = (outs[0][0]["x"].cpu().numpy() - pos[:, 0])
     assert np.abs(moved).max() > 1e-3
+
+
+def _one_key_room(ctx, co, L, H, nsl):
+    """one target set with a smooth synthetic field pointing at a door on the right wall (device + oracle key)"""
+    kd = np.array([[L, H / 2, 0.6, 2.0]])
+    V = co.create_potential(ctx.X, ctx.Y, [], [], [[L / 2, H / 2, 0.4]], kd)
+    V[V < 0] = -100; V[V > 0] = 1
+    Xi, Yi = np.meshgrid(ctx.X[1:-1], ctx.Y[1:-1])
+    ux, uy = kd[0, 0] - Xi, kd[0, 1] - Yi
+    nrm = np.sqrt(ux ** 2 + uy ** 2) + 1e-9
+    vx, vy = np.repeat((ux / nrm)[None], nsl, 0), np.repeat((uy / nrm)[None], nsl, 0)
+    Vd = ctx.to_device(V)
+    tiles, vmin = ctx.wall_tiles(Vd)
+    return (dict(V=Vd, tiles=tiles, v_min=vmin, vx=ctx.to_device(vx), vy=ctx.to_device(vy), nt_opt=nsl + 1, doors=kd),
+            co.KeyData(V, vx, vy, nsl + 1, kd))
+
+
+def _run_both(ctx, co, prm, P, kdev, kcpu, cpu, vdes, steps, rng):
+    N = len(vdes)
+    dev = {k: ctx.to_device(v) for k, v in cpu.items()}
+    vd_dev, kid = ctx.to_device(vdes), np.zeros(N, dtype=np.int32)
+    kid_dev = ctx.to_device(kid)
+    redos = 0
+    for s in range(steps):
+        perm = rng.permutation(N)
+        noise = rng.normal(size=(int(cpu["status"].sum()), 2))
+        ex, rc = ctx.gcfm_step(prm, dev, vd_dev, kid_dev, [kdev], perm, noise, s)
+        redos += ctx.gcfm_last_redos()
+        ex2, bad, _ = co.gcfm_step(P, cpu, vdes, kid, [kcpu], ctx.X, ctx.Y, perm, noise, s)
+        assert rc == 0 and bad == 0
+        assert np.array_equal(ex, ex2), f"exit order differs at step {s}"
+        for k in ("x", "y", "vx", "vy", "time", "status"):
+            assert np.array_equal(dev[k].cpu().numpy(), cpu[k]), f"{k} differs at step {s}"
+    return redos
+
+
+def test_dense_jam_more_than_512_candidates_is_exact(cfg):
+    """8 ped/m^2: more agents within cutoff + 1 m of one agent than the shared-memory lists hold.  The reference has no
+    such limit (simulations.py:285-295 visits all pairs); the step is redone on the exact slow path (global-memory
+    candidate lists) and must equal the sequential CPU sweep bit for bit."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    L = H = 12.0
+    rng = np.random.RandomState(8)
+    ctx = _lib.Context(L, H, 0.05)
+    prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    kdev, kcpu = _one_key_room(ctx, co, L, H, 6)
+    pos = _random_crowd(rng, 1000, L, H, margin=0.6, min_dist=0.2)   # 1000 agents on 10.8 x 10.8 m = 8.6 ped/m^2
+    pos = pos[np.hypot(pos[:, 0] - L / 2, pos[:, 1] - H / 2) > 0.7]  # off the pillar
+    N = len(pos)
+    assert N > 900
+    cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=rng.normal(0, 0.4, N), vy=rng.normal(0, 0.4, N),
+               time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    redos = _run_both(ctx, co, prm, P, kdev, kcpu, cpu, rng.normal(1.34, 0.26, N), 3, rng)
+    assert redos >= 3          # every step overflowed the fast path and was redone
+    assert ctx.gcfm_last_pairs() > 100000
+    ctx.close()
+
+
+def test_displacement_beyond_search_margin_is_exact(cfg):
+    """agents that move more than 0.5 m per axis in one step (repulsions add to the velocity unclipped, and the position
+    update is not speed-limited: simulations.py:303,312-326): the candidate search is widened and the step redone."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    L, H = 30.0, 20.0
+    rng = np.random.RandomState(3)
+    ctx = _lib.Context(L, H, 0.05)
+    prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    kdev, kcpu = _one_key_room(ctx, co, L, H, 8)
+    N = 300
+    pos = _random_crowd(rng, N, L, H, margin=2.0)
+    pos = pos[np.hypot(pos[:, 0] - L / 2, pos[:, 1] - H / 2) > 1.0]
+    N = len(pos)
+    vx, vy = rng.normal(0, 0.5, N), rng.normal(0, 0.5, N)
+    fast = rng.choice(N, 12, replace=False)
+    vx[fast] = rng.choice([-1, 1], 12) * rng.uniform(30, 90, 12)     # 0.6 .. 1.8 m per step
+    cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=vx, vy=vy, time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    redos = _run_both(ctx, co, prm, P, kdev, kcpu, cpu, rng.normal(1.34, 0.26, N), 2, rng)
+    assert redos >= 1
+    ctx.close()
+
+
+def test_sampler_wraps_negative_indices_like_numpy(cfg):
+    """an agent at x < 0 or y < 0 makes the reference read vx_opt[t][-1, ...]: numpy wraps, no exception (App. C #7)"""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    L, H = 6.0, 4.0
+    rng = np.random.RandomState(1)
+    ctx = _lib.Context(L, H, 0.05)
+    prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    kdev, kcpu = _one_key_room(ctx, co, L, H, 4)
+    pts = np.array([[-0.02, 1.0], [1.0, -0.07], [-0.3, -0.01], [2.0, 2.0]])
+    N = len(pts)
+    for storage in ("velocity", "phi"):
+        cpu = dict(x=pts[:, 0].copy(), y=pts[:, 1].copy(), vx=np.zeros(N), vy=np.zeros(N), time=np.zeros(N),
+                   status=np.ones(N, dtype=np.uint8))
+        if storage == "velocity":
+            _run_both(ctx, co, prm, P, kdev, kcpu, cpu, np.full(N, 1.3), 1, rng)
+        else:
+            # same answer when the sampler differentiates phi samples on the fly: only the index rule is exercised
+            dev = {k: ctx.to_device(v) for k, v in cpu.items()}
+            phi = ctx.to_device(rng.uniform(1.0, 2.0, (6, ctx.Ny, ctx.Nx)))
+            k2 = dict(kdev, vx=None, vy=None, phi=phi, nt_opt=5)
+            _, rc = ctx.gcfm_step(prm, dev, ctx.to_device(np.full(N, 1.3)), ctx.to_device(np.zeros(N, dtype=np.int32)),
+                                  [k2], np.arange(N), np.zeros((N, 2)), 0)
+            assert rc == 0
+    ctx.close()
+
+
+def test_fp64_peak_microbenchmark(cfg):
+    from optimal_crowds_b200 import _lib
+    ctx = _lib.Context(6.0, 4.0, 0.05)
+    tf = ctx.fp64_peak()
+    assert 5.0 < tf < 80.0, tf   # B200: ~34 TFLOP/s measured (nominal 37-40)
+    ctx.close()
