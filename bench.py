@@ -79,13 +79,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, interval_ms=200):
+        self.index, self.rows, self.proc, self.interval_ms = index, [], None, int(interval_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -283,9 +283,9 @@ def parity_block(world, rank, note):
     def run(band):
         np.random.seed(5)
         with contextlib.redirect_stdout(io.StringIO()):
-            simu = simulations.simulation(room, 1.2, record=False, chunk_rows=32, band=band)
+            simu = simulations.simulation(room, 1.7, record=False, chunk_rows=32, band=band)
             simu._solve_all()
-            for _ in range(58):
+            for _ in range(80):
                 simu.step(simu.dt)
         return simu
 
@@ -299,9 +299,10 @@ def parity_block(world, rank, note):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     out["gcfm_bitwise"] = bool(flag[0].item() == 1)
     out["gcfm_exit_order"] = bool(flag[1].item() == 1)
-    out["gcfm_case"] = (f"{a.N} agents, 58 steps, {len(a._exit_order)} exits (per band: {exits_by_band.tolist()}), "
+    out["gcfm_case"] = (f"{a.N} agents, 80 steps, {len(a._exit_order)} exits (per band: {exits_by_band.tolist()}), "
                         f"band rows {own}")
     note(f"parity: {out}")
+    a._ctx.close(); b._ctx.close()
     return out
 
 
@@ -321,6 +322,12 @@ def run_slalom(args, world, rank, local_rank):
         if rank == 0:
             print(f"[bench {time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
+    if world > 1 and os.environ.get("OC_BENCH_PARITY_ONLY"):  # development aid: only the untimed parity block
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("OC_BENCH_WATCHDOG", "120")), exit=True)
+        par = parity_block(world, rank, note)
+        dist.destroy_process_group()
+        return 0 if all(v for k, v in par.items() if isinstance(v, bool)) else 1
     numa = pin_numa(local_rank)
     room = synthetic.slalom_room(nx, Ny, agents=args.agents * world)
     np.random.seed(1000)   # every rank of a row-decomposed run uses the same seed (replicated, deterministic sweep)
@@ -452,6 +459,8 @@ def run_slalom(args, world, rank, local_rank):
     peak, peak_src = load_peaks()
     dom = 0  # RK step kernels
     band_cells = nx * ny
+    if cls_bytes[dom] == 0:  # the row-band solver reports times only: 40 B/cell/attempt + 8 B/cell/emitted phi slice
+        cls_bytes[dom] = 40.0 * band_cells * ((nfev_total - 2 * K) // 6) + 8.0 * band_cells * round(args.T / 0.02) * K
     achieved = cls_bytes[dom] / (step_ms_max * 1e-3) / 1e9 if step_ms_max > 0 else 0.0
     p2p = bool(getattr(simu._ctx, "peer_memory", False))
     roof = {"bound": "hbm", "kernel": "hjb_stage_kernel<N,MODE> (RK45 stage: combination + stencil [+ y_new, error])"

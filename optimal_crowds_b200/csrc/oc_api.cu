@@ -82,6 +82,7 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     cudaFree(c->hjb_partial);
     cudaFree(c->hjb_scratch);
     cudaFree(c->dist_ws);
+    cudaFree(c->dist_halo);
     oc_dist_finalize(c);
     cudaFree(c->gcfm_ws);
     oc_gcfm_free_launch_state(c);

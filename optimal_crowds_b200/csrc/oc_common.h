@@ -36,6 +36,8 @@ struct oc_ctx {
     int rank = 0, nranks = 1;
     void *dist_ws = nullptr;
     size_t dist_ws_bytes = 0;
+    void *dist_halo = nullptr;      // staging of the deferred phi halo exchange (oc_hjb_dist.cu)
+    size_t dist_halo_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double gcfm_last_ms = 0.0;
     void *gcfm_stream = nullptr;

@@ -764,6 +764,7 @@ struct BatchRoom {
     bool rejected = false;
     int status = 1, t_eval_i = 0, n_out = 0, ia_lo = 0;
     double step_sum = 0.0;               // error sum delivered by the last CTA of the attempt
+    fused::Args fa{};                    // the attempt waiting in a bucket for its batched launch
     oc_hjb_stats st{};
 };
 
@@ -882,6 +883,33 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
         }
         return lo;
     };
+    // Batched launches: the step attempts that become ready during one polling sweep are grouped by their number of
+    // dense-output samples NE and launched together, up to fused::BATCH_MAX rooms per launch (blockIdx.z = room), instead
+    // of one launch per room: 512^2 rooms need ~10 us of device work per attempt, less than a launch round trip.  Only
+    // with phi output (velocity-only storage converts scratch slices on the room's own stream) and with the in-kernel
+    // final reduction; a room's arithmetic is unchanged (same kernel body, same chunking, same reduction order).
+    const bool batched = d_phi != nullptr && final_in_kernel && !getenv("OC_BATCH_PER_ROOM");
+    std::vector<BatchRoom *> buckets[fused::NE_MAX + 1];
+    std::vector<fused::BatchArgs> host_ba(1);
+    int bucket_launches = 0;
+    auto flush = [&]() -> int {
+        for (int ne = 0; ne <= fused::NE_MAX; ne++) {
+            auto &bk = buckets[ne];
+            for (size_t off = 0; off < bk.size(); off += fused::BATCH_MAX) {
+                const int nb = (int)std::min<size_t>(fused::BATCH_MAX, bk.size() - off);
+                for (int q = 0; q < nb; q++) {
+                    BatchRoom &r = *bk[off + q];
+                    fused::set_tensor_maps(r.fa, Ny, &r.s.maps);
+                    host_ba[0].a[q] = r.fa;
+                }
+                cudaStream_t st = ctx->batch_streams[(bucket_launches++) % n_streams];
+                OC_CUDA(fused::launch_batch(ne, host_ba[0], nb, dim3(fgx, fgy), st));
+                rooms[0].s.launches++;
+            }
+            bk.clear();
+        }
+        return OC_OK;
+    };
     // enqueue one step attempt of room r (fused kernel + reduction); returns false when the room has finished
     auto attempt = [&](BatchRoom &r) -> int {
         if (r.h_abs < r.min_step) { r.status = -1; r.phase = BatchRoom::DONE; return OC_OK; }
@@ -923,6 +951,11 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
                 fa.phi[ne] = d_phi ? r.phi + (size_t)kd * n : r.phi + (size_t)((r.t_eval_i - 1 - ia) % fused::NE_MAX) * n;
             }
             if (final_in_kernel) { final_reduce_args(ctx, (int)(&r - rooms.data()), fa); r.wait_seq = fa.seq; }
+            if (batched && ia < r.ia_lo) {  // all samples fit one launch (the rule): wait in the NE bucket
+                r.fa = fa;
+                buckets[ne].push_back(&r);
+                break;
+            }
             int rc = s.launch_fused(ne, fa);
             if (rc) return rc;
             if (!d_phi && ia >= r.ia_lo) {
@@ -1030,6 +1063,7 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
         rc = advance(rooms[b]);
         if (rooms[b].phase == BatchRoom::DONE) live--;
     }
+    if (!rc) rc = flush();
     unsigned long long idle = 0;
     while (live > 0 && !rc) {
         bool progressed = false;
@@ -1048,6 +1082,7 @@ extern "C" int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const 
             rc = advance(r);
             if (r.phase == BatchRoom::DONE) live--;
         }
+        if (!rc) rc = flush();  // one batched launch per NE class for everything that became ready in this sweep
         if (progressed) { idle = 0; continue; }
         if ((++idle & 0x3ffff) == 0) {  // nothing became ready for a long time: make sure no launch has failed
             for (int q = 0; q < n_streams && !rc; q++) {

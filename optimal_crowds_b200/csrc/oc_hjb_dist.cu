@@ -225,6 +225,22 @@ int oc_dist_allreduce_max_u64(oc_ctx *ctx, void *d_buf, size_t count, cudaStream
 // One cudaMalloc block per rank holds the four time-stepping arrays of its band (y, y_new, f, f_new: rows_store x Nx
 // each) and the inboxes of the cross-GPU error-sum exchange.  The block is exported through CUDA IPC; every rank maps
 // the blocks of all ranks (same layout everywhere, so a peer address is peer_base + local offset).
+// Deferred halo exchange of the emitted phi samples (distributed GCFM sampler: every slice carries one row of the band
+// above and 1 + xhi rows of the band below).  The rows are gathered from all nt slices into four contiguous buffers,
+// exchanged with ONE NCCL group per solve, and scattered back -- instead of one small NCCL group per accepted step,
+// which put ~50 us of launch latency on the critical path of every step.
+// pack = 1: staging <- slice rows ; pack = 0: slice rows <- staging.  rows [r0, r0 + nr) of every slice.
+__global__ void phi_halo_rows_kernel(double *__restrict__ phi, size_t slice, int nt, int Nx, int r0, int nr,
+                                     double *__restrict__ staging, int pack) {
+    const size_t per = (size_t)nr * Nx, total = per * nt;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = i / per, o = i - k * per;
+        double *p = phi + k * slice + (size_t)r0 * Nx + o;
+        if (pack) staging[i] = *p;
+        else *p = staging[i];
+    }
+}
+
 static size_t p2p_inbox_doubles() { return (size_t)2 * fused::P2P_MAX_RANKS * fused::P2P_INBOX_STRIDE; }
 
 extern "C" int oc_dist_p2p_export(oc_ctx *ctx, int band_rows, void *handle_out64) {
@@ -333,6 +349,8 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
     // GCFM sampler of an agent owned by this band reads up to two rows past it, oc_gcfm.cu)
     const int xhi = dist ? cfg->phi_extra_hi : 0;
     OC_ARG(xhi == 0 || xhi == 1, "phi_extra_hi must be 0 or 1");
+    // phi samples with GCFM halo rows and no velocity conversion: their halo rows are exchanged once, after the solve
+    const bool defer_phi_halo = dist && xhi && d_phi && !want_v && !getenv("OC_PHI_HALO_PER_STEP");
 
     // peer-memory mode: the band arrays live in the IPC-exported block, halos and error sums travel inside the step launch
     const bool use_p2p = dist && nranks > 1 && ctx->p2p_on && ctx->p2p_n_store == n_store && gy_f <= fused::P2P_INBOX_STRIDE - 2 &&
@@ -669,7 +687,7 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
         // the halo rows of the new y, f travelled with the error sums; only the halo rows of the emitted phi slices are
         // left: needed by the velocity conversion below and, with phi_extra_hi, by the distributed GCFM sampler
         if (dist && want_v && !phis.empty() && (rc = exchange({}, (int)phis.size(), phis.data()))) return rc;
-        if (dist && !want_v && xhi && d_phi) {
+        if (dist && !want_v && xhi && d_phi && !defer_phi_halo) {
             std::vector<double *> hp;
             for (int e = 0; e < n_emit; e++) hp.push_back(d_phi + (size_t)(nt - 1 - (t_eval_i - 1 - e)) * bands[0].phi_slice);
             if (!hp.empty() && (rc = exchange({}, (int)hp.size(), hp.data()))) return rc;
@@ -693,6 +711,40 @@ extern "C" int oc_hjb_solve_band(oc_ctx *ctx, const oc_band_cfg *cfg, const doub
         n_out += n_emit;
         t_eval_i = ia_lo;
         t = t_new;
+    }
+    if (defer_phi_halo && status == 0 && nranks > 1) {
+        // all nt samples are final now: one packed exchange of their halo rows (see phi_halo_rows_kernel)
+        Band &b = bands[0];
+        const int up = 1 + xhi;                       // rows I send up / receive from below
+        const size_t n_up = (size_t)nt * up * Nx, n_dn = (size_t)nt * Nx;
+        const size_t need = 2 * (n_up + n_dn) * sizeof(double);
+        if (ctx->dist_halo_bytes < need) {
+            if (ctx->dist_halo) cudaFree(ctx->dist_halo);
+            ctx->dist_halo = nullptr; ctx->dist_halo_bytes = 0;
+            if (cudaMalloc(&ctx->dist_halo, need) != cudaSuccess) {
+                cudaGetLastError();
+                oc::set_error("cannot allocate %zu bytes for the phi halo exchange", need);
+                return OC_ERR_NOMEM;
+            }
+            ctx->dist_halo_bytes = need;
+        }
+        double *s_up = (double *)ctx->dist_halo, *s_dn = s_up + n_up, *r_up = s_dn + n_dn, *r_dn = r_up + n_dn;
+        const int blocks = 592;
+        if (rank > 0) phi_halo_rows_kernel<<<blocks, 256, 0, st>>>(d_phi, b.phi_slice, nt, Nx, 1, up, s_up, 1);
+        if (rank + 1 < nranks) phi_halo_rows_kernel<<<blocks, 256, 0, st>>>(d_phi, b.phi_slice, nt, Nx, band_rows, 1, s_dn, 1);
+        OC_NCCL(g_nccl.GroupStart());
+        if (rank > 0) {
+            OC_NCCL(g_nccl.Send(s_up, n_up, ncclFloat64, rank - 1, comm, st));
+            OC_NCCL(g_nccl.Recv(r_up, n_dn, ncclFloat64, rank - 1, comm, st));
+        }
+        if (rank + 1 < nranks) {
+            OC_NCCL(g_nccl.Send(s_dn, n_dn, ncclFloat64, rank + 1, comm, st));
+            OC_NCCL(g_nccl.Recv(r_dn, n_up, ncclFloat64, rank + 1, comm, st));
+        }
+        OC_NCCL(g_nccl.GroupEnd());
+        if (rank > 0) phi_halo_rows_kernel<<<blocks, 256, 0, st>>>(d_phi, b.phi_slice, nt, Nx, 0, 1, r_up, 0);
+        if (rank + 1 < nranks) phi_halo_rows_kernel<<<blocks, 256, 0, st>>>(d_phi, b.phi_slice, nt, Nx, band_rows + 1, up, r_dn, 0);
+        launches += (rank > 0 ? 2 : 0) + (rank + 1 < nranks ? 2 : 0);
     }
     OC_CUDA(cudaEventRecord(ctx->ev1, st));
     OC_CUDA(cudaStreamSynchronize(st));

@@ -118,8 +118,8 @@ struct alignas(64) Args {
     unsigned long long *result_seq; // mapped host memory: set to `seq` after result[0] is visible
     unsigned long long seq;
     // Row-band solve over NVLink peer memory (template parameter P2P; oc_hjb_dist.cu): the halo exchange and the
-    // error-norm all-gather are part of this launch.  (a) A thread that stores a row of y_new / f_new lying within
-    // HY rows of a band edge stores it a second time, straight into the neighbouring GPU's halo rows.  (b) The last
+    // error-norm all-gather are part of this launch.  (a) A CTA whose chunk touches a band edge copies the rows of
+    // y_new / f_new lying within HY rows of that edge straight into the neighbouring GPU's halo rows when its row loop ends.  (b) The last
     // CTA writes this band's chunk-row sums into the inbox of every rank (peer stores, then a system fence, then the
     // sequence number), waits for the inboxes of all ranks, adds the sums in global chunk order and hands the total to
     // the host.  A rank that has seen every rank's sequence number also knows that every rank's kernel -- and with it
@@ -235,8 +235,8 @@ static_assert(sizeof(double2) * 2 * 3 * (BX + 2) >= sizeof(double) * MAX_FINAL_R
 
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-template <int NE, bool P2P = false, bool BULK = true>
-__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid_constant__ Args a) {
+template <int NE, bool P2P, bool BULK>
+__device__ __forceinline__ void hjb_fused_body(const Args &a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -447,15 +447,6 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid
             acc = ok ? fma(qq, qq, acc) : acc;
             st_if(a.ynew + g, un[6], ok);
             st_if(a.k7 + g, k7, ok);
-            if (P2P) {  // rows within HY of a band edge also go to the neighbour's halo rows (NVLink peer stores)
-                const bool up = ok && row < a.own0 + HY && a.peer_ynew[0] != nullptr;
-                const bool dn = ok && row >= a.own1 - HY && a.peer_ynew[1] != nullptr;
-                const int gu = (row - a.peer_row_base[0]) * a.Nx + gx, gd = (row - a.peer_row_base[1]) * a.Nx + gx;
-                st_if(a.peer_ynew[0] + gu, un[6], up);
-                st_if(a.peer_k7[0] + gu, k7, up);
-                st_if(a.peer_ynew[1] + gd, un[6], dn);
-                st_if(a.peer_k7[1] + gd, k7, dn);
-            }
 #pragma unroll
             for (int ee = 0; ee < NE; ee++) {
                 // rk.py:723-737: y_old + h * Q.p with Q = K^T P, regrouped per stage
@@ -493,6 +484,24 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid
       ph_base ^= 1u;  // every tile buffer is used once per unrolled body
     }
     if (!BULK) cp_async_wait<0>();
+    if (P2P && col_out) {
+        // Halo exchange over NVLink: the rows of y_new / f_new within HY of a band edge are copied into the neighbouring
+        // GPU's halo rows with peer stores.  Done here, after the row loop, by the thread that wrote them (it re-reads its
+        // own stores, L2 hits), so that the hot loop of the row-band variant is the single-GPU loop.  Speculative like
+        // the step itself: the rows of a rejected attempt are never read.
+        if (y0 == a.own0 && a.peer_ynew[0] != nullptr)
+            for (int row = a.own0; row < min(a.own0 + HY, y1); row++) {
+                const int g = (row - a.row_base) * a.Nx + gx, gp = (row - a.peer_row_base[0]) * a.Nx + gx;
+                a.peer_ynew[0][gp] = a.ynew[g];
+                a.peer_k7[0][gp] = a.k7[g];
+            }
+        if (y1 == a.own1 && a.peer_ynew[1] != nullptr)
+            for (int row = max(a.own1 - HY, y0); row < a.own1; row++) {
+                const int g = (row - a.row_base) * a.Nx + gx, gp = (row - a.peer_row_base[1]) * a.Nx + gx;
+                a.peer_ynew[1][gp] = a.ynew[g];
+                a.peer_k7[1][gp] = a.k7[g];
+            }
+    }
     // fixed-order CTA reduction of the error partial sum
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -582,6 +591,25 @@ __global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid
     }
 }
 
+template <int NE, bool P2P = false, bool BULK = true>
+__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_kernel(const __grid_constant__ Args a) {
+    hjb_fused_body<NE, P2P, BULK>(a);
+}
+
+// Ensembles (BASELINE configs[4]): the same step for up to BATCH_MAX independent rooms of one grid shape in ONE launch,
+// blockIdx.z = room.  Every room brings its own Args (its own step size, dense-output weights, arrays, ticket and result
+// slot: the rooms' RK45 controllers are independent), all in kernel-parameter space, so the per-room constants are
+// still uniform-register operands.  Rooms are grouped by their number of dense-output samples NE.
+constexpr int BATCH_MAX = 24;  // 24 x sizeof(Args) < the 32764-byte kernel-parameter limit
+struct BatchArgs {
+    Args a[BATCH_MAX];
+};
+static_assert(sizeof(BatchArgs) <= 32764, "kernel parameter space");
+template <int NE, bool BULK>
+__global__ void __launch_bounds__(BX, CTAS_PER_SM) hjb_fused_batch_kernel(const __grid_constant__ BatchArgs ba) {
+    hjb_fused_body<NE, false, BULK>(ba.a[blockIdx.z]);
+}
+
 // Launch of one step attempt.  BULK staging needs 16-byte aligned rows: an even number of columns and 16-byte aligned
 // field pointers (phi slices are only stored to, with 8-byte stores).
 inline bool bulk_ok(const Args &a) {
@@ -660,6 +688,30 @@ inline cudaError_t launch(int ne, const Args &a, dim3 grid, cudaStream_t st) {
     switch (ne) {
         OC_FUSED_CASE(0) OC_FUSED_CASE(1) OC_FUSED_CASE(2) OC_FUSED_CASE(3) OC_FUSED_CASE(4) OC_FUSED_CASE(5)
         default: return bulk ? launch_one<6, P2P, true>(a, grid, st) : launch_one<6, P2P, false>(a, grid, st);
+    }
+#undef OC_FUSED_CASE
+}
+
+// one launch for `nb` rooms (all with `ne` samples); every room must be TMA-capable or none
+template <int NE, bool BULK>
+inline cudaError_t launch_batch_one(const BatchArgs &ba, dim3 grid, cudaStream_t st) {
+    if (sizeof(Smem) > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hjb_fused_batch_kernel<NE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+    }
+    hjb_fused_batch_kernel<NE, BULK><<<grid, BX, sizeof(Smem), st>>>(ba);
+    return cudaSuccess;
+}
+inline cudaError_t launch_batch(int ne, const BatchArgs &ba, int nb, dim3 grid2d, cudaStream_t st) {
+    bool bulk = true;
+    for (int q = 0; q < nb; q++) bulk = bulk && bulk_ok(ba.a[q]);
+    const dim3 grid(grid2d.x, grid2d.y, nb);
+#define OC_FUSED_CASE(NE) \
+    case NE: return bulk ? launch_batch_one<NE, true>(ba, grid, st) : launch_batch_one<NE, false>(ba, grid, st);
+    switch (ne) {
+        OC_FUSED_CASE(0) OC_FUSED_CASE(1) OC_FUSED_CASE(2) OC_FUSED_CASE(3) OC_FUSED_CASE(4) OC_FUSED_CASE(5)
+        default: return bulk ? launch_batch_one<6, true>(ba, grid, st) : launch_batch_one<6, false>(ba, grid, st);
     }
 #undef OC_FUSED_CASE
 }

@@ -88,7 +88,7 @@ def ensemble_room(n: int = 512, agents: int = 1000) -> dict:
                           "c3": [L - 3.5, H / 2, 0.3]}}
 
 
-def parity_room(nx: int = 2048, ny: int = 512, bands: int = 2, per_box: int = 30) -> dict:
+def parity_room(nx: int = 2048, ny: int = 512, bands: int = 2, per_box: int = 20) -> dict:
     """Reduced room for the multi-GPU parity check of bench.py: one target set, and per row band a door with a small
     box of agents right next to it (so that agents leave within ~40 steps, in every band), a wall that straddles every
     internal band edge and a pillar -- everything a row-decomposed run can get wrong sits on or near a band edge."""
@@ -107,8 +107,9 @@ def parity_room(nx: int = 2048, ny: int = 512, bands: int = 2, per_box: int = 30
     for b in range(bands):
         yc = (b + 0.5) * bh
         for q, xc in enumerate((L * 0.25, L * 0.7)):
-            boxes[f"box_{b}_{q}"] = [xc - 1.4, yc, 2.0, 2.0, (per_box + 0.5) / 4.0] + names   # int(rho*w*h) == per_box
+            # 3 x 3 m at ~2.2 ped/m^2 (the reference's placement rule excludes ~0.4 m around an agent: it jams near 4)
+            boxes[f"box_{b}_{q}"] = [xc - 1.9, yc, 3.0, 3.0, (per_box + 0.5) / 9.0] + names   # int(rho*w*h) == per_box
         if b > 0:
-            boxes[f"edge_box_{b}"] = [L * 0.9 - 1.4, b * bh, 2.0, 2.0, (per_box + 0.5) / 4.0] + names
+            boxes[f"edge_box_{b}"] = [L * 0.9 - 1.9, b * bh, 3.0, 3.0, (per_box + 0.5) / 9.0] + names
     return {"room_length": L, "room_height": H, "initial_boxes": boxes, "targets": targets, "walls": walls,
             "holes": {}, "cylinders": cyl}
