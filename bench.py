@@ -199,7 +199,7 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-FP64_INST_PER_PAIR = 1130.0   # FP64-pipe warp instructions per lane of one pair_force call, measured with ncu
+FP64_INST_PER_PAIR = 733.0    # FP64-pipe warp instructions per lane of one pair_force call, measured with ncu
                               # (profiles/r2_gcfm_pair_fp64.md: sm__inst_executed_pipe_fp64 of pair_probe_kernel / pairs)
 
 

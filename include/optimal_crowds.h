@@ -63,6 +63,15 @@ int oc_ctx_set_int(oc_ctx *ctx, const char *key, int value);
  * copy; pageable memory is staged by the driver and has been read completely when the call returns. */
 int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void *stream);
 
+/* ------------------------------------------------------------------ crowd placement (host code, no CUDA)
+ * One initial box of simulation.__init__ (simulations.py:122-138): rejection-samples loc_N = int(rho*w*h) positions with
+ * the reference's exact use of numpy's legacy MT19937 stream and its node-mask occupancy rule.  box = cx,cy,w,h,rho;
+ * X (Nx), Y (Ny): linspace node coordinates; place_ped (Ny,Nx) float64 occupancy mask shared by all boxes, updated in
+ * place; mt_key (624 words) / mt_pos: np.random.get_state()[1:3], advanced in place.  Returns the number of trials
+ * (>= loc_N) or a negative oc_status. */
+long long oc_place_box(const double *box, const double *X, int Nx, const double *Y, int Ny, double *place_ped, double r_in,
+                       uint32_t *mt_key, int *mt_pos, double *xs, double *ys, int loc_N);
+
 /* ------------------------------------------------------------------ room rasteriser (K8)
  * Replaces simulation.create_potential (simulations.py:516-576) followed by the value remap of
  * optimals.__init__ (optimals.py:89-91) when remap != 0 (V<0 -> wall_value, V>0 -> target_value).

@@ -83,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box"]
 
 
 def load():
@@ -105,6 +105,8 @@ def load():
     lib.oc_gcfm_last_redos.argtypes = [C.c_void_p]
     lib.oc_state_pack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
     lib.oc_fp64_peak.argtypes = [C.c_void_p, dp]
+    lib.oc_place_box.restype = C.c_longlong
+    lib.oc_place_box.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(C.c_uint32), ip, dp, dp, C.c_int]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
     lib.oc_ctx_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.oc_ctx_destroy.restype = None
@@ -390,9 +392,9 @@ class Context:
         keys: list of dicts(V, tiles, v_min, vx, vy | phi, nt_opt, doors(np (n,4)))."""
         return self.gcfm_step_finish(self.gcfm_step_launch(prm, state, vdes, key_id, keys, perm, noise, simu_step))
 
-    def gcfm_step_launch(self, prm: GcfmParams, state, vdes, key_id, keys, perm, noise, simu_step):
-        """enqueue one step and return at once; pass the result to gcfm_step_finish()"""
-        N = state["x"].numel()
+    @staticmethod
+    def make_keys(keys):
+        """marshal the per-target-set descriptors (dicts, see optimals.field_key) once; returns (Key array, keep-alive)"""
         karr = (Key * len(keys))()
         keep = []
         for q, k in enumerate(keys):
@@ -406,12 +408,22 @@ class Context:
                           phi.data_ptr() if phi is not None else None, int(phi.shape[0]) if phi is not None else 0, 0,
                           float(k.get("mu", 5.0)), float(k.get("lim", 10e-3)), _hp(doors), len(doors),
                           int(k.get("phi_row0", 0)), int(k.get("phi_rows", 0)))
+        keep.append([k.get(n) for k in keys for n in ("V", "tiles", "vx", "vy", "phi")])  # tensors stay alive
+        return karr, keep
+
+    def gcfm_step_launch(self, prm: GcfmParams, state, vdes, key_id, keys, perm, noise, simu_step, stream=None):
+        """enqueue one step and return at once; pass the result to gcfm_step_finish().  `keys`: list of descriptor
+        dicts, or the result of make_keys() (marshalled once and reused by the run loop); `stream`: raw CUDA stream
+        handle (default: torch's current stream)"""
+        N = state["x"].numel()
+        karr, keep = keys if isinstance(keys, tuple) else self.make_keys(keys)
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 2)
         check(load().oc_gcfm_step_launch(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]),
                                          _dev(state["vx"]), _dev(state["vy"]), _dev(state["time"]),
-                                         _dev(state["status"]), _dev(vdes), _dev(key_id), karr, len(keys),
-                                         perm.ctypes.data_as(ip), _hp(noise), len(noise), int(simu_step), _stream()))
+                                         _dev(state["status"]), _dev(vdes), _dev(key_id), karr, len(karr),
+                                         perm.ctypes.data_as(ip), _hp(noise), len(noise), int(simu_step),
+                                         _stream() if stream is None else C.c_void_p(stream)))
         return (N, perm, noise, karr, keep)  # keeps the host buffers alive until the step has finished
 
     def gcfm_step_finish(self, pending):
@@ -433,12 +445,12 @@ class Context:
         """how often the last step was redone on the exact slow path (oc_gcfm_last_redos)"""
         return int(load().oc_gcfm_last_redos(self.h))
 
-    def state_pack(self, state, out):
+    def state_pack(self, state, out, stream=None):
         """out (N,4) <- packed (x, y, vx, vy): one row of the device-resident trajectory record"""
         N = state["x"].numel()
         assert out.is_contiguous() and out.numel() == 4 * N
         check(load().oc_state_pack(self.h, N, _dev(state["x"]), _dev(state["y"]), _dev(state["vx"]), _dev(state["vy"]),
-                                   _dev(out), _stream()))
+                                   _dev(out), _stream() if stream is None else C.c_void_p(stream)))
         return out
 
     def fp64_peak(self):

@@ -114,6 +114,91 @@ extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long b
 }
 
 // ------------------------------------------------------------------------------------------------
+// Crowd placement of one initial box (simulations.py:122-138) on the host, in C: the reference's rejection sampling with
+// its exact consumption of numpy's legacy MT19937 stream -- two uniform(lo, hi, 1) draws per trial, x first (:130-131) --
+// and its occupancy test on the node mask (:132,135), restricted to the window of nodes that can lie within r_in of
+// the trial.  The generator state (624 key words + position) is passed in and out, so that the Python host continues
+// with np.random exactly where the reference would be.  ~50 ns per trial instead of ~8 us in numpy: 100k agents are
+// placed in milliseconds.  No CUDA involved.
+namespace {
+struct Mt {
+    uint32_t *key;
+    int pos;
+    void gen() {  // numpy's mt19937_gen == the reference genrand
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAT = 0x9908b0dfu;
+        int i;
+        uint32_t y;
+        for (i = 0; i < 624 - 397; i++) {
+            y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
+        }
+        for (; i < 623; i++) {
+            y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
+        }
+        y = (key[623] & UPPER) | (key[0] & LOWER);
+        key[623] = key[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double next_double() {  // genrand_res53
+        const int32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+};
+}  // namespace
+
+extern "C" long long oc_place_box(const double *box, const double *X, int Nx, const double *Y, int Ny, double *place_ped,
+                                  double r_in, uint32_t *mt_key, int *mt_pos, double *xs, double *ys, int loc_N) {
+    if (!box || !X || !Y || !place_ped || !mt_key || !mt_pos || (loc_N > 0 && (!xs || !ys)) || Nx < 2 || Ny < 2 ||
+        *mt_pos < 0 || *mt_pos > 624) {
+        oc::set_error("bad argument: oc_place_box");
+        return OC_ERR_ARG;
+    }
+    Mt mt{mt_key, *mt_pos};
+    const double lox = box[0] - box[2] / 2, hix = box[0] + box[2] / 2, loy = box[1] - box[3] / 2, hiy = box[1] + box[3] / 2;
+    const double sx = hix - lox, sy = hiy - loy;  // legacy uniform: low + (high - low) * next_double
+    const double stepx = X[1] - X[0], stepy = Y[1] - Y[0];
+    long long trials = 0;
+    int placed = 0;
+    while (placed < loc_N) {
+        trials++;
+        const double x = lox + sx * mt.next_double();
+        const double y = loy + sy * mt.next_double();
+        const int j0 = std::max((int)std::floor((x - r_in) / stepx) - 2, 0), j1 = std::min((int)std::ceil((x + r_in) / stepx) + 3, Nx);
+        const int i0 = std::max((int)std::floor((y - r_in) / stepy) - 2, 0), i1 = std::min((int)std::ceil((y + r_in) / stepy) + 3, Ny);
+        bool taken = false;
+        for (int i = i0; i < i1 && !taken; i++) {
+            const double dy = Y[i] - y, dy2 = dy * dy;
+            for (int j = j0; j < j1; j++) {
+                const double dx = X[j] - x;
+                if (std::sqrt(dx * dx + dy2) < r_in && place_ped[(size_t)i * Nx + j] == 1.0) { taken = true; break; }
+            }
+        }
+        if (taken) continue;                                                  // simulations.py:132
+        for (int i = i0; i < i1; i++) {
+            const double dy = Y[i] - y, dy2 = dy * dy;
+            for (int j = j0; j < j1; j++) {
+                const double dx = X[j] - x;
+                if (std::sqrt(dx * dx + dy2) < r_in) place_ped[(size_t)i * Nx + j] = 1.0;   // :135
+            }
+        }
+        xs[placed] = x; ys[placed] = y;
+        placed++;
+    }
+    *mt_pos = mt.pos;
+    return trials;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 pipe peak of this GPU, measured: the roofline denominator of the GCFM pair forces (SURVEY.md section 8d asks
 // for a measured FP64 FMA peak; MEASURED_PEAKS.json only carries HBM and bf16 tensor figures).  8 independent DFMA
 // chains per thread, 16 warps per SM, ~10^9 FMAs: B200 sustains ~1.84 warp-DFMA per clock and SM (34 TFLOP/s).

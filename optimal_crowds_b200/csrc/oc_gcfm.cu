@@ -264,14 +264,26 @@ __device__ long long wall_argmin_warp(const double *__restrict__ X, const double
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int ttx = __shfl_sync(0xffffffffu, tx, src), tty = __shfl_sync(0xffffffffu, ty, src);
-                for (int c = lane; c < WT * WT; c += 32) {
-                    int iy = tty * WT + c / WT, ix = ttx * WT + (c % WT);
-                    if (iy < Ny && ix < Nx) {
-                        double v = V[(size_t)iy * Nx + ix];
-                        if (v < 0) {
-                            double ddx = X[ix] - x, ddy = Y[iy] - y;
-                            double key = sqrt(ddx * ddx + ddy * ddy) + v * 10e3;
-                            long long fi = (long long)iy * Nx + ix;
+                // the 8 potentials a lane looks at (nodes c = lane, lane + 32, ...: coalesced rows of the tile, ascending flat
+                // index inside a lane) are fetched with independent loads first: one memory round trip per tile instead of
+                // eight dependent ones
+                static_assert(WT * WT == 8 * 32, "tile scan: 8 nodes per lane");
+                {
+                    double vv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int c = lane + 32 * q, iy = tty * WT + c / WT, ix = ttx * WT + (c % WT);
+                        vv[q] = (iy < Ny && ix < Nx) ? __ldg(V + (size_t)iy * Nx + ix) : 0.0;
+                    }
+                    const int ix = ttx * WT + (lane % WT);
+                    const double ddx = (ix < Nx) ? X[ix] - x : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (vv[q] < 0) {
+                            const int iy = tty * WT + (lane + 32 * q) / WT;
+                            const double ddy = Y[iy] - y;
+                            const double key = sqrt(ddx * ddx + ddy * ddy) + vv[q] * 10e3;
+                            const long long fi = (long long)iy * Nx + ix;
                             if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
                         }
                     }
@@ -537,6 +549,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
     const double reach2 = reach * reach;
     const int span = (int)ceil(reach * inv_cs);
     const unsigned lt_mask = (1u << lane) - 1;
+    int pairs_total = 0;
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(&w.counters[0], 1);
@@ -599,9 +612,8 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             }
             nc += __popc(m);
         }
-        if (lane == 0) atomicMax(&w.counters[3], nc);
         if (nc > cap) {  // uniform across the warp
-            if (lane == 0) atomicOr(&w.counters[1], 2);
+            if (lane == 0) { atomicOr(&w.counters[1], 2); atomicMax(&w.counters[3], nc); }
             // too many neighbours for the lists: this attempt is void (flag; the host redoes the step with lists sized for
             // counters[3]); the agent still advances with the first `cap` candidates so that later agents do not wait forever
             nc = cap;
@@ -671,11 +683,29 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
             if (slot >= 0) { lfx[slot] = fx; lfy[slot] = fy; }  // the sort buffers are dead: proc/ord were extracted
         }
         __syncwarp();
-        // ---- D. ascending-j sum (simulations.py:285-295)
+        // ---- D. ascending-j sum (simulations.py:285-295).  Most slots hold +-0.0 (beyond the cutoff, or outside the field
+        // of view: k = 0).  Adding a zero never changes a bit of the running sum (it starts at +0.0 and can never become
+        // -0.0; x + (+-0.0) == x for every other x, NaN and inf included), so the zero terms are squeezed out in parallel
+        // first and only the remaining ones -- still in ascending-j order -- go through the sequential, order-sensitive
+        // additions.  proc[] is dead by now and receives the kept slots.
+        int nnz = 0;
+        for (int t0 = 0; t0 < nc; t0 += 32) {
+            const int t = t0 + lane;
+            int sl = 0;
+            bool nz = false;
+            if (t < nc) {
+                sl = ord[t];
+                nz = !(lfx[sl] == 0.0 && lfy[sl] == 0.0);   // NaN terms are kept
+            }
+            const unsigned mz = __ballot_sync(0xffffffffu, nz);
+            if (nz) proc[nnz + __popc(mz & lt_mask)] = (unsigned short)sl;
+            nnz += __popc(mz);
+        }
+        __syncwarp();
         double acc = 0.0;
         if (lane < 2) {  // lane 0 -> x component, lane 1 -> y component
             const double *src = lane == 0 ? lfx : lfy;
-            for (int t = 0; t < nc; t++) acc = acc + src[ord[t]];
+            for (int t = 0; t < nnz; t++) acc = acc + src[proc[t]];
         }
         const double rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1);
         if (lane == 0) {
@@ -698,7 +728,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
                 // (NaN displacements stay flagged with the largest margin: the host then gives up with an error)
                 atomicMax(reinterpret_cast<unsigned long long *>(w.counters + 4), (unsigned long long)__double_as_longlong(disp));
             }
-            if (n_pairs) atomicAdd(&w.counters[2], n_pairs);
+            pairs_total += n_pairs;  // (one atomic per warp at the end: an atomic here would sit in front of the fence below)
             bool out = false;
             for (int d = 0; d < n_doors; d++) {  // pedestrians.py:132-136
                 const double *door = w.doors + 4 * (door_off + d);
@@ -716,6 +746,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
         }
         __syncwarp();
     }
+    if (lane == 0 && pairs_total) atomicAdd(&w.counters[2], pairs_total);
 }
 
 // ordered compaction of the exit marks (by sweep position) into host-visible memory: out[0]=count, out[1..5]=counters[1..5]

@@ -137,8 +137,9 @@ class ensemble:
         # the members' sweeps run concurrently: each gets its share of the GPU's resident-CTA slots
         n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
         ctas = self.sweep_ctas or max(self.min_sweep_ctas, (n_sm * 4) // len(streams))
-        for s in sims:
+        for q, s in enumerate(sims):
             s._ctx.set_int("gcfm_sweep_ctas", ctas)
+            s._cuda_stream = streams[q % len(streams)].cuda_stream   # the member's steps run on its own stream
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         self.stats["cell_updates"] += self._solve_wave(sims)
@@ -155,8 +156,7 @@ class ensemble:
                 if self.record:
                     s.write_history(s.time)
                 self.stats["agent_steps"] += s.inside
-                with torch.cuda.stream(streams[q % len(streams)]):
-                    launched.append(s._step_launch(s.dt))
+                launched.append(s._step_launch(s.dt))
             tl1 = time.perf_counter()
             for q, l in zip(live, launched):
                 sims[q]._step_finish(l)

@@ -130,6 +130,7 @@ class simulation:
             self._gcfm_prm.own0, self._gcfm_prm.own1 = self._band
             if field_storage != "phi":
                 raise ValueError("band=True stores the field as phi samples: pass field_storage='phi'")
+        self._cuda_stream = None   # raw CUDA stream handle of this simulation's steps (None: torch's current stream)
         self._key_shard = None
         if shard_keys:
             import torch.distributed as tdist
@@ -262,7 +263,7 @@ class simulation:
             self._d_track.append(torch.empty((self.TRACK_CHUNK, max(self.N, 1), 4), dtype=torch.float64,
                                              device=self._ctx.torch_device))
         if self.N:
-            self._ctx.state_pack(self._state, self._d_track[blk][off])
+            self._ctx.state_pack(self._state, self._d_track[blk][off], stream=self._cuda_stream)
         self._n_rows += 1
 
     def _rows_upto(self, last):
@@ -299,7 +300,13 @@ class simulation:
         self._state["status"][i] = int(self._h_status[i])
 
     def _keys(self):
-        return [opt.field_key(self._doors[key]) for key, opt in self.targets.items()]
+        """marshalled per-target-set descriptors of oc_gcfm_step, rebuilt only when a field changed (a solve replaces
+        nt_opt and possibly the field tensors)"""
+        sig = tuple((o.nt_opt, id(o.d_phi), id(o.d_vx), id(o.d_V)) for o in self.targets.values())
+        if getattr(self, "_keys_sig", None) != sig:
+            self._keys_cache = _lib.Context.make_keys([opt.field_key(self._doors[key]) for key, opt in self.targets.items()])
+            self._keys_sig = sig
+        return self._keys_cache
 
     @property
     def _doors(self):
@@ -332,7 +339,7 @@ class simulation:
             # agent in sweep order == N calls of normal(size=2) (simulations.py:303)
             perm, noise = self._rng.draw(self.N, n_active)
             pending = self._ctx.gcfm_step_launch(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm,
-                                                 noise, self.simu_step)
+                                                 noise, self.simu_step, stream=self._cuda_stream)
             self._rng.lookahead(self.N, n_active)   # next step's draws while the GPU sweeps
         return dt, pending
 

@@ -4,7 +4,10 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from optimal_crowds_b200 import simulations, synthetic
 
-for agents, ny in ((12500, 2048), (50000, 2048), (100000, 2048)):
+cases = ((12500, 2048), (50000, 2048), (100000, 2048))
+if len(sys.argv) > 1:
+    cases = tuple((int(a), 2048) for a in sys.argv[1:])
+for agents, ny in cases:
     np.random.seed(0)
     t0 = time.time()
     with contextlib.redirect_stdout(io.StringIO()):

@@ -164,3 +164,35 @@ def test_history_frame_is_lazy():
     h = _Frame(lambda: rows.append(1) or [["p", "v", "door", 1.0]], lambda: calls.append(2) or np.zeros(1))
     assert not rows                                                    # the agents' rows are lazy too (device record)
     assert len(h) == 2 and rows == [1] and h[0][0] == "p" and rows == [1] and calls == [1]
+
+
+def test_c_crowd_placement_is_bit_identical_to_the_numpy_restatement():
+    """oc_place_box (C, liboc_b200.so) == _crowd.place_box_py (numpy, itself pinned to the reference by the golden
+    crowds): same positions, same occupancy mask, same MT19937 state afterwards -- for a RandomState and for the global
+    np.random module (simulations.py:122-140)."""
+    from optimal_crowds_b200 import _crowd, _lib, synthetic
+    for room, seed in ((synthetic.ensemble_room(512, 400), 3), (synthetic.metro_room(1024, 800), 11)):
+        Ny, Nx = _lib.grid_shape(room["room_length"], room["room_height"], 0.05)
+        X1, Y1 = np.linspace(0, room["room_length"], Nx), np.linspace(0, room["room_height"], Ny)
+        got = []
+        for fn in (_crowd.place_box_py, _crowd.place_box):
+            pp, rs = np.zeros((Ny, Nx)), np.random.RandomState(seed)
+            res = [fn(b, X1, Y1, pp, 0.2, rs) for b in room["initial_boxes"].values()]
+            got.append((res, pp, rs.get_state()))
+        for ra, rb in zip(got[0][0], got[1][0]):
+            for a, b in zip(ra, rb):
+                assert np.array_equal(a, b)
+        assert np.array_equal(got[0][1], got[1][1])
+        sa, sb = got[0][2], got[1][2]
+        assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+    room = synthetic.ensemble_room(512, 200)
+    Ny, Nx = _lib.grid_shape(room["room_length"], room["room_height"], 0.05)
+    X1, Y1 = np.linspace(0, room["room_length"], Nx), np.linspace(0, room["room_height"], Ny)
+    box = list(room["initial_boxes"].values())[0]
+    st0 = np.random.get_state()
+    try:
+        np.random.seed(9); a = _crowd.place_box(box, X1, Y1, np.zeros((Ny, Nx)), 0.2, np.random); s1 = np.random.get_state()
+        np.random.seed(9); b = _crowd.place_box_py(box, X1, Y1, np.zeros((Ny, Nx)), 0.2, np.random); s2 = np.random.get_state()
+    finally:
+        np.random.set_state(st0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(s1[1], s2[1]) and s1[2:] == s2[2:]
