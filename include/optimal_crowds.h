@@ -137,6 +137,9 @@ int oc_hjb_solve(oc_ctx *ctx, const double *d_V, const double *d_m, const oc_hjb
  * n_rooms device pointers held in HOST memory; d_phi or (d_vx and d_vy) may be NULL.  stats: n_rooms entries.
  * prm->fused, forced_h and profile are ignored (always the stage-fused kernel, free-running controller).
  * Returns OC_ERR_STEP_TOO_SMALL if any room's integration stopped early (its stats.status == -1). */
+/* Chunk height (prm->chunk_rows) that balances halo recomputation against wave quantisation for `copies` rooms solved
+ * side by side; the default of a single solve is oc_hjb_plan_chunk_rows(ctx, 1). */
+int oc_hjb_plan_chunk_rows(oc_ctx *ctx, int copies);
 int oc_hjb_solve_batch(oc_ctx *ctx, int n_rooms, const double *const *d_V, const double *const *d_m,
                        const oc_hjb_params *prm, double T, const double *t_eval, int nt, double *const *d_phi,
                        double *const *d_vx, double *const *d_vy, oc_hjb_stats *stats, void *stream);

@@ -83,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows"]
 
 
 def load():
@@ -105,6 +105,7 @@ def load():
     lib.oc_gcfm_last_redos.argtypes = [C.c_void_p]
     lib.oc_state_pack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
     lib.oc_fp64_peak.argtypes = [C.c_void_p, dp]
+    lib.oc_hjb_plan_chunk_rows.argtypes = [C.c_void_p, C.c_int]
     lib.oc_place_box.restype = C.c_longlong
     lib.oc_place_box.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(C.c_uint32), ip, dp, dp, C.c_int]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
@@ -367,6 +368,12 @@ class Context:
         return [{"stats": st[q].asdict(), "phi": out_phi[q] if out_phi is not None else None,
                  "vx": out_vx[q] if out_vx is not None else None, "vy": out_vy[q] if out_vx is not None else None,
                  "rc": rc if st[q].status == -1 else 0} for q in range(B)]
+
+    def plan_chunk_rows(self, copies=1):
+        """chunk height the fused solver picks for `copies` rooms of this grid side by side (oc_hjb_plan_chunk_rows)"""
+        rc = int(load().oc_hjb_plan_chunk_rows(self.h, int(copies)))
+        check(min(rc, 0))
+        return rc
 
     def hjb_rhs(self, phi, V, m, prm: HjbParams):
         out = self.empty(self.Ny, self.Nx)

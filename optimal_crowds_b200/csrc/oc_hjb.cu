@@ -432,6 +432,16 @@ extern "C" int oc_hjb_rhs(oc_ctx *ctx, const double *d_phi, const double *d_V, c
     return OC_OK;
 }
 
+// rows per CTA chunk the stage-fused kernel would choose for `copies` independent solves of this context's grid running
+// side by side (ensembles).  A caller that wants member results independent of the batch size fixes prm->chunk_rows
+// to this value for the stand-alone solve too (the chunking defines the order of the error-norm sum).
+extern "C" int oc_hjb_plan_chunk_rows(oc_ctx *ctx, int copies) {
+    if (!ctx || copies < 1) return OC_ERR_ARG;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    return fused::plan_chunk_rows(ctx->Nx, ctx->Ny, n_sm, copies, 0);
+}
+
 extern "C" int oc_hjb_vels(oc_ctx *ctx, const double *d_phi, const oc_hjb_params *prm, double *d_vx, double *d_vy,
                            void *stream) {
     OC_ARG(ctx && d_phi && prm && d_vx && d_vy, "NULL argument");

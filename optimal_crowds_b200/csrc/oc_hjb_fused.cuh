@@ -72,6 +72,7 @@ constexpr int NE_MAX = 6;           // dense-output samples per launch
 // each chunk recomputes.  `rows` = rows of the band, `copies` = bands launched back to back on this GPU.
 inline int plan_chunk_rows(int Nx, int rows, int n_sm, int copies, int must_divide) {
     static const int cand[] = {16, 32, 48, 64, 96, 128, 160, 192, 224, 256, 320, 384, 448, 512, 640, 768, 1024, 2048};
+    constexpr int UNROLL = 12;  // rows per unrolled loop body of the kernel (see below)
     const long long slots = (long long)n_sm * CTAS_PER_SM;
     const int gx = (Nx + VX - 1) / VX;
     double best = 1e300;
@@ -80,7 +81,9 @@ inline int plan_chunk_rows(int Nx, int rows, int n_sm, int copies, int must_divi
         if (must_divide && rows % c) continue;
         const int cc = c < rows ? c : rows;
         const long long blocks = (long long)gx * ((rows + cc - 1) / cc) * copies;
-        const double cost = (double)((blocks + slots - 1) / slots) * (cc + 2 * HY);
+        // a CTA walks its chunk + 2 HY halo rows in whole unrolled bodies of UNROLL rows
+        const int walked = (cc + 2 * HY + UNROLL - 1) / UNROLL * UNROLL;
+        const double cost = (double)((blocks + slots - 1) / slots) * walked;
         if (cost < best) { best = cost; rc = cc; }
     }
     return rc;

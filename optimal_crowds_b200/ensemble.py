@@ -69,7 +69,11 @@ class ensemble:
 
     def __init__(self, rooms, T, seeds, recompute=False, field_storage="phi", chunk_rows=0, rank=0, world=1,
                  memory_budget=None, max_wave=256, record=False, verbose=False):
-        self.T, self.recompute, self.field_storage, self.chunk_rows = T, recompute, field_storage, int(chunk_rows)
+        # chunk_rows: 0 = every room chunked as if it were alone (members are then bit-identical to stand-alone runs with
+        # default settings, whatever the wave size); n > 0 = fixed; "wave" = planned for the wave size (fastest)
+        self.chunk_plan_for_wave = chunk_rows == "wave"
+        self.T, self.recompute, self.field_storage = T, recompute, field_storage
+        self.chunk_rows = 0 if self.chunk_plan_for_wave else int(chunk_rows)
         self.seeds = list(seeds)
         if isinstance(rooms, (list, tuple)):
             if len(rooms) != len(self.seeds):
@@ -82,6 +86,7 @@ class ensemble:
         self.memory_budget, self.max_wave = memory_budget, max_wave
         self.record, self.verbose = record, verbose
         self.min_sweep_ctas, self.sweep_ctas = 8, 0   # sweep grid per member: automatic share of the GPU, or fixed
+        self.chunk_rows_used = self.chunk_rows
         self.results = {}
         self.members = {}          # member index -> simulation (kept only when record=True)
         self.stats = dict(hjb_ms=0.0, gcfm_ms=0.0, build_ms=0.0, agent_steps=0, cell_updates=0, waves=0, launch_ms=0.0,
@@ -111,6 +116,13 @@ class ensemble:
                 if nt - 1 > o._n_slices:
                     raise IndexError("re-solve asks for more slices than the field was allocated for")
             prm = opts[0]._prm
+            if self.chunk_plan_for_wave:
+                # chunk height planned for the whole wave (a 512^2 room alone would be cut into 16-row chunks to fill the
+                # GPU; 64 rooms side by side fill it with 64-row chunks and recompute far fewer halo rows).  The chunking
+                # fixes the error-norm summation order: a stand-alone run reproduces a member bit for bit when it is
+                # given the same chunk_rows (ensemble.chunk_rows_used).
+                self.chunk_rows_used = first._ctx.plan_chunk_rows(len(sims))
+                prm.chunk_rows = self.chunk_rows_used
             vel = self.field_storage == "velocity"
             res = first._ctx.hjb_solve_batch([o.d_V for o in opts], d_ms, prm, self.T, nt,
                                              out_phi=None if vel else [o.d_phi for o in opts],

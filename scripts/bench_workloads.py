@@ -205,7 +205,7 @@ def run_ensemble(args, world, rank, local_rank):
     ctx.close()
 
     def one_pass():
-        ens = ensemble.ensemble(room, T, list(range(n_rooms)), rank=rank, world=world, max_wave=128)
+        ens = ensemble.ensemble(room, T, list(range(n_rooms)), rank=rank, world=world, max_wave=128, chunk_rows="wave")
         t0 = time.perf_counter()
         res = ens.run(gather=False)
         torch.cuda.synchronize()

@@ -69,3 +69,19 @@ def test_sharding_and_waves_do_not_change_results(in_repo_cwd):
         assert np.array_equal(parts[i]["final"], whole[i]["final"])
         assert np.array_equal(parts[i]["exit_order"], whole[i]["exit_order"])
         assert whole[i]["N"] == 12
+
+
+def test_wave_planned_chunking_matches_standalone_with_the_same_chunk_rows(in_repo_cwd):
+    """chunk_rows="wave": the chunk height is planned for the wave (fewer halo rows recomputed); a member then equals the
+    stand-alone run that is given the same chunk_rows"""
+    from optimal_crowds_b200 import ensemble, simulations
+    seeds = [5, 6, 7, 8]
+    ens = ensemble.ensemble("room_test", 2.0, seeds, chunk_rows="wave")
+    res = ens.run()
+    assert ens.chunk_rows_used > 0
+    np.random.seed(seeds[2])
+    with contextlib.redirect_stdout(io.StringIO()):
+        one = simulations.simulation("room_test", 2.0, record=False, chunk_rows=ens.chunk_rows_used)
+        one.run()
+    assert np.array_equal(res[2]["final"], one._h_now) and np.array_equal(res[2]["times"], one._h_timev)
+    assert res[2]["hjb"]["door_1"]["nfev"] == one.targets["door_1"].last_stats["nfev"]
