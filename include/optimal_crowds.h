@@ -72,6 +72,12 @@ int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long bytes, void 
 long long oc_place_box(const double *box, const double *X, int Nx, const double *Y, int Ny, double *place_ped, double r_in,
                        uint32_t *mt_key, int *mt_pos, double *xs, double *ys, int loc_N);
 
+/* The random numbers of one GCFM step from numpy's legacy MT19937 stream (host code): the permutation of
+ * simulations.py:271 and one normal pair per agent inside (:303).  mt_key/mt_pos/has_gauss/cached_gauss =
+ * np.random.get_state()[1:5], advanced in place; perm (N ints) and noise (n_active,2) are outputs. */
+int oc_rng_step_draw(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N, int n_active, int *perm,
+                     double *noise);
+
 /* ------------------------------------------------------------------ room rasteriser (K8)
  * Replaces simulation.create_potential (simulations.py:516-576) followed by the value remap of
  * optimals.__init__ (optimals.py:89-91) when remap != 0 (V<0 -> wall_value, V>0 -> target_value).
@@ -264,6 +270,23 @@ int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d
                         const oc_key *keys, int n_keys, const int *perm, const double *noise, int n_noise,
                         int simu_step, void *stream);
 int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit);
+
+/* Batched step for ensembles of independent rooms (BASELINE configs[4]): ONE launch per kernel for all n members
+ * (blockIdx.y = member) instead of 7 launches per member, and the members' per-step randomness drawn in C from their own
+ * legacy MT19937 states (mt_key[m]: 624 words; mt_pos, has_gauss, cached_gauss: arrays of n = get_state()[2:5]; all
+ * advanced in place) exactly as oc_rng_step_draw / the reference would.  Every member keeps its own context (workspace,
+ * grid); all on one device.  Arrays are indexed by member: ctxs, prms, Ns, the SoA state pointers, keys / n_keys,
+ * n_active (agents inside at step start) and simu_step.  sweep_ctas: CTAs of the sweep per member (0 = 8).
+ * _finish waits, returns every member's exit log (exit_log[m]: capacity Ns[m]) and status rc_out[m] (OC_OK or
+ * OC_ERR_SAMPLER_RANGE as oc_gcfm_step); members whose fast attempt was void are redone on the exact slow path.
+ * Results are bit-identical to stepping every member with oc_gcfm_step. */
+int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gcfm_params *const *prms, const int *Ns,
+                              double *const *x, double *const *y, double *const *vx, double *const *vy,
+                              double *const *tim, uint8_t *const *status, const double *const *vdes,
+                              const int *const *key, const oc_key *const *keys, const int *n_keys,
+                              uint32_t *const *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss,
+                              const int *n_active, const int *simu_step, int sweep_ctas, void *stream);
+int oc_gcfm_step_multi_finish(int n, oc_ctx *const *ctxs, int *const *exit_log, int *n_exit, int *rc_out);
 
 /* CUDA-event time (ms) of the last oc_gcfm_step on this context (H2D of perm/noise, all kernels, exit-log copy). */
 double oc_gcfm_last_ms(oc_ctx *ctx);

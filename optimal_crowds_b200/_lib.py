@@ -83,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows", "oc_rng_step_draw", "oc_gcfm_step_multi_launch", "oc_gcfm_step_multi_finish"]
 
 
 def load():
@@ -106,6 +106,11 @@ def load():
     lib.oc_state_pack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
     lib.oc_fp64_peak.argtypes = [C.c_void_p, dp]
     lib.oc_hjb_plan_chunk_rows.argtypes = [C.c_void_p, C.c_int]
+    vpp_ = C.POINTER(C.c_void_p)
+    lib.oc_gcfm_step_multi_launch.argtypes = [C.c_int, vpp_, vpp_, ip] + [vpp_] * 9 + [ip, vpp_, ip, ip, dp, ip, ip,
+                                                                                     C.c_int, C.c_void_p]
+    lib.oc_gcfm_step_multi_finish.argtypes = [C.c_int, vpp_, vpp_, ip, ip]
+    lib.oc_rng_step_draw.argtypes = [C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, ip, dp]
     lib.oc_place_box.restype = C.c_longlong
     lib.oc_place_box.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(C.c_uint32), ip, dp, dp, C.c_int]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]
@@ -489,6 +494,81 @@ class Context:
         check(load().oc_density(self.h, N, _dev(x), _dev(y), _dev(status), float(sigma), Cn, _dev(Vglobal), _dev(d),
                                 _stream()))
         return d
+
+
+class GcfmBatch:
+    """Batched GCFM steps of several simulations on one GPU (oc_gcfm_step_multi_*): marshals the members' pointers once
+    and keeps their legacy MT19937 states in numpy arrays that the C side advances (ensemble.py).  ``members``: list of
+    dicts with ctx (Context), prm (GcfmParams), state, vdes, key_id, keys (Context.make_keys result), rng (RandomState)."""
+
+    def __init__(self, members, sweep_ctas=8):
+        self.members = members
+        self.sweep_ctas = int(sweep_ctas)
+        W = len(members)
+        self.mt_key = np.empty((W, 624), dtype=np.uint32)
+        self.mt_pos = np.empty(W, dtype=np.int32)
+        self.has_gauss = np.empty(W, dtype=np.int32)
+        self.cached = np.empty(W, dtype=np.float64)
+        for q, m in enumerate(members):
+            st = m["rng"].get_state()
+            assert st[0] == "MT19937"
+            self.mt_key[q], self.mt_pos[q], self.has_gauss[q], self.cached[q] = st[1], st[2], st[3], st[4]
+        self.maxN = max(m["state"]["x"].numel() for m in members)
+        self.exit_log = np.empty((W, max(self.maxN, 1)), dtype=np.int32)
+        self._live = None
+
+    def _bind(self, live):
+        """compact pointer arrays of the live members (rebuilt when the live set or a member's keys changed)"""
+        n = len(live)
+        vp = lambda: (C.c_void_p * n)()
+        a = dict(ctx=vp(), prm=vp(), x=vp(), y=vp(), vx=vp(), vy=vp(), tim=vp(), status=vp(), vdes=vp(), key=vp(),
+                 keys=vp(), mt=vp(), elog=vp())
+        a["N"] = np.empty(n, dtype=np.int32); a["nk"] = np.empty(n, dtype=np.int32)
+        for i, q in enumerate(live):
+            m = self.members[q]
+            st = m["state"]
+            a["ctx"][i] = m["ctx"].h.value if hasattr(m["ctx"].h, "value") else m["ctx"].h
+            a["prm"][i] = C.addressof(m["prm"])
+            for name, t in (("x", st["x"]), ("y", st["y"]), ("vx", st["vx"]), ("vy", st["vy"]), ("tim", st["time"]),
+                            ("status", st["status"]), ("vdes", m["vdes"]), ("key", m["key_id"])):
+                a[name][i] = t.data_ptr()
+            karr = m["keys"][0]
+            a["keys"][i] = C.addressof(karr); a["nk"][i] = len(karr)
+            a["N"][i] = st["x"].numel()
+            a["mt"][i] = self.mt_key[q].ctypes.data
+            a["elog"][i] = self.exit_log[q].ctypes.data
+        a["pos"] = np.empty(n, dtype=np.int32); a["hg"] = np.empty(n, dtype=np.int32); a["cg"] = np.empty(n)
+        a["n_exit"] = np.zeros(n, dtype=np.int32); a["rc"] = np.zeros(n, dtype=np.int32)
+        self._live, self._a = list(live), a
+
+    def launch(self, live, n_active, simu_step, stream=None, rebind=False):
+        if rebind or self._live != list(live):
+            self._bind(live)
+        a, idx = self._a, np.asarray(live, dtype=np.intp)
+        a["pos"][:], a["hg"][:], a["cg"][:] = self.mt_pos[idx], self.has_gauss[idx], self.cached[idx]
+        na = np.ascontiguousarray(n_active, dtype=np.int32); ss = np.ascontiguousarray(simu_step, dtype=np.int32)
+        I = lambda v: v.ctypes.data_as(ip)
+        check(load().oc_gcfm_step_multi_launch(len(live), a["ctx"], a["prm"], I(a["N"]), a["x"], a["y"], a["vx"], a["vy"],
+                                               a["tim"], a["status"], a["vdes"], a["key"], a["keys"], I(a["nk"]), a["mt"],
+                                               I(a["pos"]), I(a["hg"]), _hp(a["cg"]), I(na), I(ss), self.sweep_ctas,
+                                               _stream() if stream is None else C.c_void_p(stream)))
+        self.mt_pos[idx], self.has_gauss[idx], self.cached[idx] = a["pos"], a["hg"], a["cg"]
+        self._keep = (na, ss)
+
+    def finish(self):
+        """-> list of (exit ids in sweep order, rc) for the live members of the last launch"""
+        a, n = self._a, len(self._live)
+        I = lambda v: v.ctypes.data_as(ip)
+        rc = load().oc_gcfm_step_multi_finish(n, a["ctx"], a["elog"], I(a["n_exit"]), I(a["rc"]))
+        check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
+        return [(self.exit_log[q, :a["n_exit"][i]].copy() if a["n_exit"][i] else self.exit_log[q, :0], int(a["rc"][i]))
+                for i, q in enumerate(self._live)]
+
+    def write_back_rng(self):
+        """hand the advanced generator states back to the members' RandomState objects"""
+        for q, m in enumerate(self.members):
+            m["rng"].set_state(("MT19937", self.mt_key[q].copy(), int(self.mt_pos[q]), int(self.has_gauss[q]),
+                                float(self.cached[q])))
 
 
 def gcfm_params(cfg: dict, room_length: float, room_height: float, Ny: int, Nx: int) -> GcfmParams:

@@ -47,7 +47,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
-        subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"], check=True)
+        subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"], check=True)
     return LIB
 
 

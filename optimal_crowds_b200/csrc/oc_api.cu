@@ -5,6 +5,7 @@
 
 #include "oc_common.h"
 #include "oc_math.h"
+#include "oc_rng.h"
 
 namespace oc {
 static thread_local char g_err[1024] = "";
@@ -86,6 +87,8 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     oc_dist_finalize(c);
     cudaFree(c->gcfm_ws);
     oc_gcfm_free_launch_state(c);
+    if (c->multi_pinned) cudaFreeHost(c->multi_pinned);
+    cudaFree(c->multi_dev);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->gcfm_pinned) cudaFreeHost(c->gcfm_pinned);
     cudaFree(c->fr_ticket);
@@ -120,42 +123,6 @@ extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long b
 // the trial.  The generator state (624 key words + position) is passed in and out, so that the Python host continues
 // with np.random exactly where the reference would be.  ~50 ns per trial instead of ~8 us in numpy: 100k agents are
 // placed in milliseconds.  No CUDA involved.
-namespace {
-struct Mt {
-    uint32_t *key;
-    int pos;
-    void gen() {  // numpy's mt19937_gen == the reference genrand
-        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAT = 0x9908b0dfu;
-        int i;
-        uint32_t y;
-        for (i = 0; i < 624 - 397; i++) {
-            y = (key[i] & UPPER) | (key[i + 1] & LOWER);
-            key[i] = key[i + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
-        }
-        for (; i < 623; i++) {
-            y = (key[i] & UPPER) | (key[i + 1] & LOWER);
-            key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
-        }
-        y = (key[623] & UPPER) | (key[0] & LOWER);
-        key[623] = key[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
-        pos = 0;
-    }
-    uint32_t next32() {
-        if (pos == 624) gen();
-        uint32_t y = key[pos++];
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        return y;
-    }
-    double next_double() {  // genrand_res53
-        const int32_t a = next32() >> 5, b = next32() >> 6;
-        return (a * 67108864.0 + b) / 9007199254740992.0;
-    }
-};
-}  // namespace
-
 extern "C" long long oc_place_box(const double *box, const double *X, int Nx, const double *Y, int Ny, double *place_ped,
                                   double r_in, uint32_t *mt_key, int *mt_pos, double *xs, double *ys, int loc_N) {
     if (!box || !X || !Y || !place_ped || !mt_key || !mt_pos || (loc_N > 0 && (!xs || !ys)) || Nx < 2 || Ny < 2 ||
@@ -163,7 +130,7 @@ extern "C" long long oc_place_box(const double *box, const double *X, int Nx, co
         oc::set_error("bad argument: oc_place_box");
         return OC_ERR_ARG;
     }
-    Mt mt{mt_key, *mt_pos};
+    ocrng::Mt mt{mt_key, *mt_pos, 0, 0.0};
     const double lox = box[0] - box[2] / 2, hix = box[0] + box[2] / 2, loy = box[1] - box[3] / 2, hiy = box[1] + box[3] / 2;
     const double sx = hix - lox, sy = hiy - loy;  // legacy uniform: low + (high - low) * next_double
     const double stepx = X[1] - X[0], stepy = Y[1] - Y[0];
@@ -196,6 +163,20 @@ extern "C" long long oc_place_box(const double *box, const double *X, int Nx, co
     }
     *mt_pos = mt.pos;
     return trials;
+}
+
+// The randomness of one GCFM step, drawn from a legacy MT19937 state exactly as the reference does (simulations.py:271:
+// np.random.choice(np.arange(N), N, replace=False); :303: one np.random.normal(size=2) per agent inside, in sweep order).
+// State = np.random.get_state()[1:5], advanced in place.  perm: N ints; noise: (n_active, 2) doubles.
+extern "C" int oc_rng_step_draw(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N, int n_active,
+                                int *perm, double *noise) {
+    OC_ARG(mt_key && mt_pos && has_gauss && cached_gauss && perm && (n_active == 0 || noise) && N >= 0 && n_active >= 0 &&
+           *mt_pos >= 0 && *mt_pos <= 624, "oc_rng_step_draw");
+    ocrng::Mt mt{mt_key, *mt_pos, *has_gauss, *cached_gauss};
+    mt.permutation(N, perm);
+    for (int q = 0; q < 2 * n_active; q++) noise[q] = mt.gauss();
+    *mt_pos = mt.pos; *has_gauss = mt.has_gauss; *cached_gauss = mt.gauss_;
+    return OC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

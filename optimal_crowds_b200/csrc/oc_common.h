@@ -48,6 +48,10 @@ struct oc_ctx {
     int gcfm_tag = 0;                 // generation of the sweep's done-flags (they live in this context's workspace)
     int gcfm_redos = 0;               // slow-path redos of the last step
     long long gcfm_last_pairs = 0;    // interacting pairs evaluated by the last step
+    std::vector<char> gcfm_keys_sig;  // batched step: the target-set descriptors last uploaded (KeyDev records + doors)
+    void *gcfm_keys_dev = nullptr;    //   and where they were uploaded to
+    void *multi_pinned = nullptr, *multi_dev = nullptr;  // batched step: staging arena (perm, noise, member records)
+    size_t multi_bytes = 0;
     int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
     int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
     // in-kernel final reduction of the fused step (oc_hjb_fused.cuh): ticket counters on the device, results in

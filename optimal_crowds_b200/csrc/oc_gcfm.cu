@@ -18,10 +18,12 @@
 #include <cmath>
 #include <cstdint>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "oc_common.h"
 #include "oc_math.h"
+#include "oc_rng.h"
 #include "oc_vels.h"
 
 namespace {
@@ -365,10 +367,10 @@ __global__ void tile_ring_kernel(const uint8_t *__restrict__ occ, int ntx, int n
 }
 
 // rank = inverse permutation; snapshot; bin histogram
-__global__ void setup_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ vx, const double *__restrict__ vy,
-                             const double *__restrict__ tim, const uint8_t *__restrict__ status, Ws w, double inv_cs,
-                             int nbx, int nby) {
+__device__ __forceinline__ void setup_body(int N, const double *__restrict__ x, const double *__restrict__ y,
+                                           const double *__restrict__ vx, const double *__restrict__ vy,
+                                           const double *__restrict__ tim, const uint8_t *__restrict__ status, const Ws &w,
+                                           double inv_cs, int nbx, int nby) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     w.rank[w.perm[i]] = i;
@@ -386,7 +388,7 @@ __global__ void setup_kernel(int N, const double *__restrict__ x, const double *
 }
 
 // single-block inclusive scan in place over a[0..n) (a[0] must be 0 => exclusive offsets)
-__global__ void __launch_bounds__(1024) scan_kernel(int *a, int n) {
+__device__ __forceinline__ void scan_body(int *a, int n) {
     __shared__ int tot[1024];
     int t = threadIdx.x;
     int per = (n + 1023) / 1024;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(int *a, int n) {
     for (int i = lo; i < hi; i++) { run += a[i]; a[i] = run; }
 }
 
-__global__ void scatter_kernel(int N, Ws w) {
+__device__ __forceinline__ void scatter_body(int N, const Ws &w) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N || !w.status0[i]) return;
     int b = w.agent_bin[i];
@@ -434,7 +436,7 @@ __global__ void restore_kernel(int N, Ws w, double *__restrict__ x, double *__re
 
 // nzidx[agent] = number of agents active at step start that precede it in the sweep (simulations.py:303
 // draws one normal pair per active agent in sweep order).  Single block.
-__global__ void __launch_bounds__(1024) noise_index_kernel(int N, Ws w) {
+__device__ __forceinline__ void noise_index_body(int N, const Ws &w) {
     __shared__ int tot[1024];
     int t = threadIdx.x;
     int per = (N + 1023) / 1024;
@@ -459,10 +461,10 @@ __global__ void __launch_bounds__(1024) noise_index_kernel(int N, Ws w) {
 
 // K5: per-agent terms that depend only on the agent's own old state: desired velocity (sampler) and wall
 // force.  One warp per agent.
-__global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, Ws w,
-                                                      const double *__restrict__ X, const double *__restrict__ Y,
-                                                      const double *__restrict__ vdes, const int *__restrict__ key_id,
-                                                      int simu_step) {
+__device__ __forceinline__ void prepare_body(const oc_gcfm_params &p, int N, const Ws &w,
+                                             const double *__restrict__ X, const double *__restrict__ Y,
+                                             const double *__restrict__ vdes, const int *__restrict__ key_id,
+                                             int simu_step) {
     int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= N || !w.status0[i]) return;
     const int lane = threadIdx.x & 31;
@@ -529,11 +531,11 @@ __device__ __forceinline__ void warp_sort_u64(unsigned long long *a, int n, int 
 // The sweep is a chain of dependencies (an agent needs the new state of every earlier neighbour), so what matters is
 // the time from "my last dependency published" to "I publish": with this ordering it is ONE batch of pair forces plus
 // the sum, instead of all remaining batches plus the sort.
-__global__ void __launch_bounds__(SWEEP_WARPS * 32)
-sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y,
-             double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
-             uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
-             double inv_cs, int nbx, int nby, unsigned poll_ns, double margin, int cap, unsigned char *glists) {
+__device__ __forceinline__ void
+sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, double *__restrict__ y,
+           double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
+           uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
+           double inv_cs, int nbx, int nby, unsigned poll_ns, double margin, int cap, unsigned char *glists) {
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj (ints), proc, ord
@@ -750,7 +752,7 @@ sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__re
 }
 
 // ordered compaction of the exit marks (by sweep position) into host-visible memory: out[0]=count, out[1..5]=counters[1..5]
-__global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
+__device__ __forceinline__ void exit_compact_body(int N, const Ws &w, int *__restrict__ out) {
     __shared__ int tot[1024];
     int t = threadIdx.x;
     int per = (N + 1023) / 1024;
@@ -770,6 +772,86 @@ __global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__
         if (w.exit_mark[r]) out[OUT_HDR + run++] = w.exit_mark[r] - 1;
     if (t == 1023) out[0] = tot[1023];
     if (t < 5) out[1 + t] = w.counters[1 + t];  // flags, pairs, largest candidate count, largest displacement (2 ints)
+}
+
+// ---- kernel entry points.  Single room: arguments by value.  Ensembles (BASELINE configs[4]): ONE launch per kernel for
+// all members of a wave, blockIdx.y = member, every member described by a GcfmMember record in device memory -- the
+// members' sweeps then run side by side without one stream (and one of the 32 hardware queues) per member, and a step
+// of 128 members costs 8 launches instead of 128 x 7.
+struct GcfmMember {
+    oc_gcfm_params prm;
+    Ws w;
+    double *x, *y, *vx, *vy, *tim;
+    uint8_t *status;
+    const double *vdes, *X, *Y;
+    const int *key;
+    int *out;          // host-visible step result (exit log)
+    int N, simu_step, tag, nbx, nby, nbins;
+    double inv_cs;
+    unsigned poll_ns;
+};
+
+__global__ void setup_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ vx, const double *__restrict__ vy,
+                             const double *__restrict__ tim, const uint8_t *__restrict__ status, Ws w, double inv_cs,
+                             int nbx, int nby) {
+    setup_body(N, x, y, vx, vy, tim, status, w, inv_cs, nbx, nby);
+}
+__global__ void __launch_bounds__(1024) scan_kernel(int *a, int n) { scan_body(a, n); }
+__global__ void scatter_kernel(int N, Ws w) { scatter_body(N, w); }
+__global__ void __launch_bounds__(1024) noise_index_kernel(int N, Ws w) { noise_index_body(N, w); }
+__global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X,
+                                                      const double *__restrict__ Y, const double *__restrict__ vdes,
+                                                      const int *__restrict__ key_id, int simu_step) {
+    prepare_body(p, N, w, X, Y, vdes, key_id, simu_step);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
+             double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
+             const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, double inv_cs, int nbx, int nby,
+             unsigned poll_ns, double margin, int cap, unsigned char *glists) {
+    sweep_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, inv_cs, nbx, nby, poll_ns, margin, cap, glists);
+}
+__global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
+    exit_compact_body(N, w, out);
+}
+
+// batched variants: blockIdx.y = member
+__global__ void clear_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i <= m.nbins; i += stride) { m.w.bin_start[i] = 0; m.w.bin_cursor[i] = 0; }
+    for (int i = t0; i < m.N; i += stride) m.w.exit_mark[i] = 0;
+    if (t0 < 8) m.w.counters[t0] = 0;
+}
+__global__ void setup_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    setup_body(m.N, m.x, m.y, m.vx, m.vy, m.tim, m.status, m.w, m.inv_cs, m.nbx, m.nby);
+}
+__global__ void __launch_bounds__(1024) scan_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    scan_body(m.w.bin_start, m.nbins + 1);
+}
+__global__ void scatter_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    scatter_body(m.N, m.w);
+}
+__global__ void __launch_bounds__(1024) noise_index_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    noise_index_body(m.N, m.w);
+}
+__global__ void __launch_bounds__(128) prepare_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    prepare_body(m.prm, m.N, m.w, m.X, m.Y, m.vdes, m.key, m.simu_step);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    sweep_body(m.prm, m.N, m.w, m.x, m.y, m.vx, m.vy, m.tim, m.status, m.vdes, m.key, m.tag, m.inv_cs, m.nbx, m.nby,
+               m.poll_ns, DISP_MARGIN, CAND_CAP, nullptr);
+}
+__global__ void __launch_bounds__(1024) exit_compact_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    exit_compact_body(m.N, m.w, m.out);
 }
 
 // unit-probe kernels ---------------------------------------------------------------------------------
@@ -1110,13 +1192,13 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     return OC_OK;
 }
 
-extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
+static int gcfm_finish_member(oc_ctx *ctx, int *exit_log, int *n_exit, bool synced, bool timed) {
     OC_ARG(ctx && ctx->gcfm_pending && ctx->gcfm_last, "no GCFM step in flight");
     OC_CUDA(cudaSetDevice(ctx->device));
     ctx->gcfm_pending = false;
     cudaStream_t st = (cudaStream_t)ctx->gcfm_stream;
     GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
-    OC_CUDA(cudaStreamSynchronize(st));  // host-visible exit log
+    if (!synced) OC_CUDA(cudaStreamSynchronize(st));  // host-visible exit log
     const int *pinned = (const int *)ctx->gcfm_pinned;
     // Exact slow path (rare).  The fast attempt keeps at most CAND_CAP candidates per agent in shared memory and
     // searches them within cutoff + DISP_MARGIN of the agent's old position.  An attempt that met more candidates, or
@@ -1154,11 +1236,11 @@ extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
         if (tag < 0) return tag;
         int rc = gcfm_launch_sweep(ctx, L, st, tag, margin, cap, true);
         if (rc) return rc;
-        OC_CUDA(cudaEventRecord(ctx->ev1, st));
+        if (timed) OC_CUDA(cudaEventRecord(ctx->ev1, st));
         OC_CUDA(cudaStreamSynchronize(st));
         ctx->gcfm_redos = redo + 1;
     }
-    {
+    if (timed) {
         float ms = 0;
         OC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->gcfm_last_ms = ms;
@@ -1173,6 +1255,156 @@ extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
         return OC_ERR_SAMPLER_RANGE;
     }
     return OC_OK;
+}
+
+extern "C" int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit) {
+    return gcfm_finish_member(ctx, exit_log, n_exit, false, true);
+}
+
+// ------------------------------------------------------------------------------------------------ batched step (ensembles)
+// One GCFM step of n independent members (each with its own context, crowd, fields and legacy RNG stream) with ONE launch
+// per kernel (blockIdx.y = member).  The host part -- per member: the step's permutation and normal pairs from the
+// member's MT19937 state (oc_rng.h: numpy's legacy stream, simulations.py:271,303), the staging of both, the member
+// record -- runs in C; perm / noise of all members travel in one host-to-device copy.
+extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gcfm_params *const *prms, const int *Ns,
+                                         double *const *x, double *const *y, double *const *vx, double *const *vy,
+                                         double *const *tim, uint8_t *const *status, const double *const *vdes,
+                                         const int *const *key, const oc_key *const *keys, const int *n_keys,
+                                         uint32_t *const *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss,
+                                         const int *n_active, const int *simu_step, int sweep_ctas, void *stream) {
+    OC_ARG(n >= 1 && ctxs && prms && Ns && x && y && vx && vy && tim && status && vdes && key && keys && n_keys && mt_key &&
+           mt_pos && has_gauss && cached_gauss && n_active && simu_step, "NULL argument");
+    oc_ctx *c0 = ctxs[0];
+    OC_CUDA(cudaSetDevice(c0->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // ---- staging arena: per member perm (N ints, padded to 8 bytes) + noise (2 n_active doubles)
+    std::vector<size_t> off(n + 1, 0);
+    int max_N = 0;
+    for (int m = 0; m < n; m++) {
+        OC_ARG(ctxs[m] && ctxs[m]->device == c0->device && Ns[m] >= 1 && n_active[m] >= 0 && n_active[m] <= Ns[m] &&
+               prms[m]->own1 <= prms[m]->own0 && prms[m]->key_mod == 0, "bad member");
+        off[m + 1] = off[m] + (((size_t)Ns[m] * sizeof(int) + 7) / 8) * 8 + (size_t)2 * n_active[m] * sizeof(double);
+        max_N = std::max(max_N, Ns[m]);
+    }
+    const size_t arena = off[n] + 64, rec_bytes = sizeof(GcfmMember) * (size_t)n;
+    if (c0->multi_bytes < arena + rec_bytes) {
+        if (c0->multi_pinned) cudaFreeHost(c0->multi_pinned);
+        if (c0->multi_dev) cudaFree(c0->multi_dev);
+        c0->multi_pinned = c0->multi_dev = nullptr; c0->multi_bytes = 0;
+        const size_t cap = (arena + rec_bytes) * 2;
+        OC_CUDA(cudaMallocHost(&c0->multi_pinned, cap));
+        OC_CUDA(cudaMalloc(&c0->multi_dev, cap));
+        c0->multi_bytes = cap;
+    }
+    char *hp = (char *)c0->multi_pinned, *dp = (char *)c0->multi_dev;
+    GcfmMember *recs = reinterpret_cast<GcfmMember *>(hp + ((arena + 63) / 64) * 64);
+    GcfmMember *recs_dev = reinterpret_cast<GcfmMember *>(dp + ((arena + 63) / 64) * 64);
+    OC_CUDA(cudaEventRecord(c0->ev0, st));
+    int max_bins = 0;
+    for (int m = 0; m < n; m++) {
+        oc_ctx *ctx = ctxs[m];
+        const oc_gcfm_params *prm = prms[m];
+        const int N = Ns[m];
+        OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
+        const double reach = prm->cutoff + DISP_MARGIN, inv_cs = 2.0 / reach;
+        const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
+                  nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
+        const int nbins = nbx * nby;
+        int n_doors = 0;
+        for (int k = 0; k < n_keys[m]; k++) n_doors += keys[m][k].n_doors;
+        if (!ctx->gcfm_last) ctx->gcfm_last = new GcfmLaunch();
+        GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
+        int *pinned = nullptr;
+        int rc = gcfm_workspace(ctx, N, n_keys[m], n_doors, nbins, L.w, &pinned, st);
+        if (rc) return rc;
+        L.prm = *prm; L.N = N; L.n_keys = n_keys[m]; L.n_doors = n_doors; L.nbins_alloc = nbins;
+        L.x = x[m]; L.y = y[m]; L.vx = vx[m]; L.vy = vy[m]; L.tim = tim[m]; L.status = status[m]; L.vdes = vdes[m];
+        L.key = key[m]; L.pinned = pinned;
+        // target-set descriptors: uploaded only when they changed (a re-solve changes nt_opt)
+        std::vector<char> sig(sizeof(KeyDev) * n_keys[m] + sizeof(double) * 4 * std::max(n_doors, 1), 0);
+        KeyDev *hk = reinterpret_cast<KeyDev *>(sig.data());
+        double *hd = reinterpret_cast<double *>(sig.data() + sizeof(KeyDev) * n_keys[m]);
+        int doff = 0;
+        for (int k = 0; k < n_keys[m]; k++) {
+            const oc_key &kk = keys[m][k];
+            OC_ARG(kk.d_V && kk.d_wall_tiles && (!kk.d_vx == !kk.d_vy), "bad key");
+            hk[k] = KeyDev{kk.d_V, kk.d_wall_tiles, kk.d_vx, kk.d_vy, kk.d_vx ? nullptr : kk.d_phi, kk.nt_opt,
+                           kk.d_vx ? kk.n_slices : 0, doff, kk.n_doors, (kk.d_vx || !kk.d_phi) ? 0 : kk.n_phi, kk.v_min * 10e3,
+                           kk.mu, kk.lim, kk.phi_row0, kk.phi_rows};
+            for (int d = 0; d < 4 * kk.n_doors; d++) hd[4 * (size_t)doff + d] = kk.doors[d];
+            doff += kk.n_doors;
+        }
+        if (ctx->gcfm_keys_sig != sig || ctx->gcfm_keys_dev != (void *)L.w.keys) {
+            ctx->gcfm_keys_sig = sig;   // the vector stays alive: pageable source of the asynchronous copies below
+            ctx->gcfm_keys_dev = (void *)L.w.keys;
+            OC_CUDA(cudaMemcpyAsync(L.w.keys, ctx->gcfm_keys_sig.data(), sizeof(KeyDev) * n_keys[m], cudaMemcpyHostToDevice, st));
+            OC_CUDA(cudaMemcpyAsync(L.w.doors, ctx->gcfm_keys_sig.data() + sizeof(KeyDev) * n_keys[m],
+                                    sizeof(double) * 4 * std::max(n_doors, 1), cudaMemcpyHostToDevice, st));
+        }
+        // (this step's randomness is drawn below, by a few host threads, straight into the staging arena)
+        L.w.perm = reinterpret_cast<int *>(dp + off[m]);
+        L.w.noise = reinterpret_cast<double *>(dp + off[m] + (((size_t)N * sizeof(int) + 7) / 8) * 8);
+        if (++ctx->gcfm_tag >= 0x3fffffff) ctx->gcfm_tag = 1;
+        GcfmMember &r = recs[m];
+        r.prm = *prm; r.w = L.w; r.x = x[m]; r.y = y[m]; r.vx = vx[m]; r.vy = vy[m]; r.tim = tim[m]; r.status = status[m];
+        r.vdes = vdes[m]; r.X = ctx->d_X; r.Y = ctx->d_Y; r.key = key[m]; r.out = pinned; r.N = N;
+        r.simu_step = simu_step[m]; r.tag = ctx->gcfm_tag; r.nbx = nbx; r.nby = nby; r.nbins = nbins; r.inv_cs = inv_cs;
+        r.poll_ns = (unsigned)ctx->gcfm_poll_ns;
+        max_bins = std::max(max_bins, nbins);
+        ctx->gcfm_stream = st;
+        ctx->gcfm_pending = true;
+    }
+    {   // the members' streams are independent: draw them in parallel (simulations.py:271,303 per member)
+        const int n_thr = std::max(1, std::min({n, 8, (int)std::thread::hardware_concurrency()}));
+        auto work = [&](int t) {
+            for (int m = t; m < n; m += n_thr) {
+                const int N = Ns[m];
+                int *perm_h = reinterpret_cast<int *>(hp + off[m]);
+                double *noise_h = reinterpret_cast<double *>(hp + off[m] + (((size_t)N * sizeof(int) + 7) / 8) * 8);
+                ocrng::Mt mt{mt_key[m], mt_pos[m], has_gauss[m], cached_gauss[m]};
+                mt.permutation(N, perm_h);
+                for (int q = 0; q < 2 * n_active[m]; q++) noise_h[q] = mt.gauss();
+                mt_pos[m] = mt.pos; has_gauss[m] = mt.has_gauss; cached_gauss[m] = mt.gauss_;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
+    OC_CUDA(cudaMemcpyAsync(dp, hp, ((arena + 63) / 64) * 64 + rec_bytes, cudaMemcpyHostToDevice, st));
+    OC_CUDA(cudaFuncSetAttribute(sweep_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    const int nb = (max_N + 255) / 256;
+    const int ctas = std::max(1, std::min(sweep_ctas > 0 ? sweep_ctas : 8, (max_N + SWEEP_WARPS - 1) / SWEEP_WARPS));
+    clear_multi_kernel<<<dim3(std::max(1, std::min(8, (std::max(max_N, max_bins) + 255) / 256)), n), 256, 0, st>>>(recs_dev);
+    setup_multi_kernel<<<dim3(nb, n), 256, 0, st>>>(recs_dev);
+    scan_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
+    scatter_multi_kernel<<<dim3(nb, n), 256, 0, st>>>(recs_dev);
+    noise_index_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
+    prepare_multi_kernel<<<dim3((max_N * 32 + 127) / 128, n), 128, 0, st>>>(recs_dev);
+    sweep_multi_kernel<<<dim3(ctas, n), SWEEP_WARPS * 32, SWEEP_SMEM, st>>>(recs_dev);
+    exit_compact_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
+    oc::count_launch(8);
+    OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaEventRecord(c0->ev1, st));
+    return OC_OK;
+}
+
+extern "C" int oc_gcfm_step_multi_finish(int n, oc_ctx *const *ctxs, int *const *exit_log, int *n_exit, int *rc_out) {
+    OC_ARG(n >= 1 && ctxs && exit_log && n_exit && rc_out && ctxs[0] && ctxs[0]->gcfm_pending, "no batched GCFM step in flight");
+    oc_ctx *c0 = ctxs[0];
+    OC_CUDA(cudaSetDevice(c0->device));
+    OC_CUDA(cudaStreamSynchronize((cudaStream_t)c0->gcfm_stream));
+    float ms = 0;
+    OC_CUDA(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
+    int worst = OC_OK;
+    for (int m = 0; m < n; m++) {
+        // (a member whose fast attempt was void is redone alone on the exact slow path, like a single step)
+        rc_out[m] = gcfm_finish_member(ctxs[m], exit_log[m], &n_exit[m], true, false);
+        if (rc_out[m] != OC_OK && rc_out[m] != OC_ERR_SAMPLER_RANGE) worst = rc_out[m];
+    }
+    c0->gcfm_last_ms = ms;
+    return worst;
 }
 
 extern "C" double oc_gcfm_last_ms(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_ms : 0.0; }

@@ -68,7 +68,7 @@ class ensemble:
     statistics per target set)."""
 
     def __init__(self, rooms, T, seeds, recompute=False, field_storage="phi", chunk_rows=0, rank=0, world=1,
-                 memory_budget=None, max_wave=256, record=False, verbose=False):
+                 memory_budget=None, max_wave=256, record=False, verbose=False, batched_steps=True):
         # chunk_rows: 0 = every room chunked as if it were alone (members are then bit-identical to stand-alone runs with
         # default settings, whatever the wave size); n > 0 = fixed; "wave" = planned for the wave size (fastest)
         self.chunk_plan_for_wave = chunk_rows == "wave"
@@ -85,6 +85,9 @@ class ensemble:
         self.mine = shard(len(self.seeds), rank, world)
         self.memory_budget, self.max_wave = memory_budget, max_wave
         self.record, self.verbose = record, verbose
+        # True: the GCFM steps of a wave run as batched launches with the randomness drawn in C (oc_gcfm_step_multi_*);
+        # False: member by member on their own streams with numpy draws.  Identical results (tests/test_gpu_ensemble.py).
+        self.batched_steps = bool(batched_steps)
         self.min_sweep_ctas, self.sweep_ctas = 8, 0   # sweep grid per member: automatic share of the GPU, or fixed
         self.chunk_rows_used = self.chunk_rows
         self.results = {}
@@ -157,24 +160,55 @@ class ensemble:
         self.stats["cell_updates"] += self._solve_wave(sims)
         t2 = time.perf_counter()
         live = list(range(len(sims)))
+        batch = None
+        if self.batched_steps:
+            # one launch per kernel for the whole wave (blockIdx.y = member) and the members' randomness drawn in C from
+            # their own MT19937 states: same kernels and same streams of random numbers as the member-by-member path
+            main = torch.cuda.current_stream().cuda_stream
+            for s in sims:
+                s._cuda_stream = main
+            # a room's sweep is a dependency chain with ~5 agents runnable at a time (1000 agents, depth ~200): a few warps per
+            # room suffice, and every CTA slot given to one room is a slot another room of the wave cannot use
+            ctas_b = self.sweep_ctas or max(2, min(8, (n_sm * 4) // len(sims)))
+            batch = _lib.GcfmBatch([dict(ctx=s._ctx, prm=s._gcfm_prm, state=s._state, vdes=s._d_vdes, key_id=s._d_key,
+                                         keys=s._keys(), rng=s._np_random) for s in sims], sweep_ctas=ctas_b)
         while live:
             first = sims[live[0]]
+            rebind = False
             if self.recompute and first.simu_step % first.recompute_step == 0 and first.simu_step > 0:
                 self.stats["cell_updates"] += self._solve_wave([sims[q] for q in live])
-            launched = []
+                rebind = True
             tl0 = time.perf_counter()
-            for q in live:
-                s = sims[q]
-                if self.record:
-                    s.write_history(s.time)
-                self.stats["agent_steps"] += s.inside
-                launched.append(s._step_launch(s.dt))
-            tl1 = time.perf_counter()
-            for q, l in zip(live, launched):
-                sims[q]._step_finish(l)
+            if batch is not None:
+                if rebind:
+                    for q in live:
+                        batch.members[q]["keys"] = sims[q]._keys()
+                for q in live:
+                    s = sims[q]
+                    if self.record:
+                        s.write_history(s.time)
+                    self.stats["agent_steps"] += s.inside
+                batch.launch(live, [sims[q].inside for q in live], [sims[q].simu_step for q in live], stream=main,
+                             rebind=rebind)
+                tl1 = time.perf_counter()
+                for q, (exits, rc) in zip(live, batch.finish()):
+                    sims[q]._step_finish((sims[q].dt, ("batched", exits, rc)))
+            else:
+                launched = []
+                for q in live:
+                    s = sims[q]
+                    if self.record:
+                        s.write_history(s.time)
+                    self.stats["agent_steps"] += s.inside
+                    launched.append(s._step_launch(s.dt))
+                tl1 = time.perf_counter()
+                for q, l in zip(live, launched):
+                    sims[q]._step_finish(l)
             self.stats["launch_ms"] += (tl1 - tl0) * 1e3
             self.stats["finish_ms"] += (time.perf_counter() - tl1) * 1e3
             live = [q for q in live if (sims[q].inside > 0) and (sims[q].time < sims[q].T)]   # simulations.py:427
+        if batch is not None:
+            batch.write_back_rng()
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         for i, s in zip(wave, sims):

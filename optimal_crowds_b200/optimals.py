@@ -99,7 +99,10 @@ class optimals:
             rows = self.Ny if self.band is None else self.band[1] - self.band[0] + 3
             self.d_phi = torch.empty((n_slices + 1, rows, self.Nx), dtype=torch.float64, device=self.d_V.device)
         self._h_vx = self._h_vy = None
-        self._d_m = None
+        self._d_m = None            # two device buffers for host densities (double-buffered uploads)
+        self._d_m_flip = 0
+        self._prefetched = None
+        self._copy_stream = None
         self.phi_T = np.zeros((self.Ny, self.Nx), dtype=float).reshape(self.Nx * self.Ny) + 1  # optimals.py:83,93
         self.last_stats = None
 
@@ -146,6 +149,38 @@ class optimals:
             key.update(phi_row0=self.band[0] - 1, phi_rows=self.band[1] - self.band[0] + 3)
         return key
 
+    # ---- host density input ----------------------------------------------------------------------------
+    def _band_rows_of(self, m):
+        """the rows of a host density array this process needs: (Ny,Nx), flat, or already band shaped"""
+        mh = np.asarray(m, dtype=np.float64)
+        if self.band is not None and mh.size == (self.band[1] - self.band[0]) * self.Nx:
+            return mh.reshape(-1, self.Nx)                                 # already this rank's rows
+        mh = mh.reshape(self.Ny, self.Nx)
+        return mh[self.band[0]:self.band[1]] if self.band is not None else mh
+
+    def _m_buffer(self, shape, which):
+        if self._d_m is None:
+            self._d_m = [None, None]
+        if self._d_m[which] is None or tuple(self._d_m[which].shape) != tuple(shape):
+            self._d_m[which] = self._ctx.empty(*shape)
+        return self._d_m[which]
+
+    def prefetch_density(self, m):
+        """Start the host -> device copy of the density a LATER ``compute_optimal_velocity(t, m)`` will be given (same
+        numpy array, page-locked for a truly asynchronous copy) on a side stream, into the buffer the current solve does
+        not use: the upload of the next solve's input overlaps the running solve (double-buffered input).  Optional; a
+        solve whose density was not announced uploads it itself."""
+        import torch
+        mh = self._band_rows_of(m)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        buf = self._m_buffer(mh.shape, self._d_m_flip ^ 1)
+        with torch.cuda.stream(self._copy_stream):
+            keep = self._ctx.upload(mh, buf)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._prefetched = ((mh.__array_interface__["data"][0], mh.shape), buf, ev, keep)
+
     def V_host(self):
         return self.V if self.V is not None else self.d_V.cpu().numpy()
 
@@ -166,20 +201,18 @@ class optimals:
         if m is None or (np.isscalar(m) and m == 0):
             d_m = None
         elif isinstance(m, np.ndarray):
-            # host density -> persistent device buffer; the solve below synchronises the stream, which also
-            # covers the (asynchronous) copy from a page-locked source.  A row-decomposed field only needs (and only
-            # uploads) the rows of its band.
-            mh = np.asarray(m, dtype=np.float64)
-            if self.band is not None and mh.size == (self.band[1] - self.band[0]) * self.Nx:
-                mh = mh.reshape(-1, self.Nx)            # already this rank's rows
+            # host density -> device buffer; the solve below synchronises the stream, which also covers the
+            # (asynchronous) copy from a page-locked source.  A row-decomposed field only needs (and only uploads) the
+            # rows of its band.  An array announced with prefetch_density() is already on its way (or there).
+            mh = self._band_rows_of(m)
+            pf, self._prefetched = self._prefetched, None
+            if pf is not None and pf[0] == (mh.__array_interface__["data"][0], mh.shape):
+                torch.cuda.current_stream().wait_event(pf[2])
+                d_m = pf[1]
+                self._d_m_flip ^= 1
             else:
-                mh = mh.reshape(self.Ny, self.Nx)
-                if self.band is not None:
-                    mh = mh[self.band[0]:self.band[1]]
-            if self._d_m is None:
-                self._d_m = self._ctx.empty(*mh.shape)
-            _keep = self._ctx.upload(mh, self._d_m)
-            d_m = self._d_m
+                d_m = self._m_buffer(mh.shape, self._d_m_flip)
+                _keep = self._ctx.upload(mh, d_m)
         else:
             d_m = m if (self.band is not None and m.shape[0] == self.band[1] - self.band[0]) else m.reshape(self.Ny, self.Nx)
         if nt - 1 > self._n_slices:

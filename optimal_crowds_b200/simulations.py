@@ -346,7 +346,8 @@ class simulation:
     def _step_finish(self, launched, verbose=False):
         dt, pending = launched
         if pending is not None:
-            exits, rc = self._ctx.gcfm_step_finish(pending)
+            # ("batched", exits, rc): the step ran inside a batched launch of an ensemble wave and has finished already
+            exits, rc = pending[1:] if pending[0] == "batched" else self._ctx.gcfm_step_finish(pending)
             if rc == _lib.OC_ERR_SAMPLER_RANGE:
                 raise IndexError("agent position outside the velocity field's index range "
                                  "(numpy raises IndexError in the reference's sampler too: optimals.py:247)")

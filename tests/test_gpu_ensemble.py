@@ -85,3 +85,15 @@ def test_wave_planned_chunking_matches_standalone_with_the_same_chunk_rows(in_re
         one.run()
     assert np.array_equal(res[2]["final"], one._h_now) and np.array_equal(res[2]["times"], one._h_timev)
     assert res[2]["hjb"]["door_1"]["nfev"] == one.targets["door_1"].last_stats["nfev"]
+
+
+def test_batched_and_member_by_member_steps_agree(in_repo_cwd):
+    """oc_gcfm_step_multi_* (one launch per kernel for the wave, randomness drawn in C from the members' MT19937 states)
+    == stepping every member with oc_gcfm_step and numpy draws, bit for bit, incl. a periodic re-solve"""
+    from optimal_crowds_b200 import ensemble
+    seeds = [21, 22, 23, 24, 25]
+    a = ensemble.ensemble("exit_opposite", 2.5, seeds, recompute=True, batched_steps=True).run()
+    b = ensemble.ensemble("exit_opposite", 2.5, seeds, recompute=True, batched_steps=False).run()
+    for i in range(len(seeds)):
+        assert np.array_equal(a[i]["final"], b[i]["final"]) and np.array_equal(a[i]["times"], b[i]["times"])
+        assert np.array_equal(a[i]["exit_order"], b[i]["exit_order"]) and a[i]["steps"] == b[i]["steps"]

@@ -298,3 +298,26 @@ def test_plotting_methods_execute_under_stub_matplotlib(in_repo_cwd, monkeypatch
         opt = list(a.targets.values())[0]
         opt.nt_opt = 3
         opt.draw_optimal_velocity()
+
+
+def test_prefetched_density_gives_the_same_field(in_repo_cwd):
+    """optimals.prefetch_density(m) only moves the upload of m ahead of time (double-buffered): same field, bit for bit;
+    a solve that gets a different array than the announced one uploads it itself"""
+    import torch
+    a, _ = _run("room_test", 1.0, False, 0, max_steps=0)
+    opt = list(a.targets.values())[0]
+    rng = np.random.RandomState(2)
+    m1 = torch.from_numpy(rng.uniform(0, 1, (a.Ny, a.Nx))).pin_memory().numpy()
+    m2 = torch.from_numpy(rng.uniform(0, 1, (a.Ny, a.Nx))).pin_memory().numpy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt.compute_optimal_velocity(0.0, m1); ref1 = opt.d_phi.clone()
+        opt.compute_optimal_velocity(0.0, m2); ref2 = opt.d_phi.clone()
+        opt.prefetch_density(m1)
+        opt.compute_optimal_velocity(0.0, m1); got1 = opt.d_phi.clone()
+        opt.prefetch_density(m2)
+        opt.prefetch_density(m1)                      # announcing again simply replaces the announcement
+        opt.compute_optimal_velocity(0.0, m2); got2 = opt.d_phi.clone()   # not the announced array: plain upload
+        opt.prefetch_density(m2)
+        opt.compute_optimal_velocity(0.0, m2); got3 = opt.d_phi.clone()
+    assert torch.equal(ref1, got1) and torch.equal(ref2, got2) and torch.equal(ref2, got3)
+    assert not torch.equal(ref1, ref2)
