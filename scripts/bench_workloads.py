@@ -185,7 +185,7 @@ def run_metro(args, world, rank, local_rank):
                          "roofline": {"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
                                       "achieved": pairs * bench.FP64_INST_PER_PAIR * 2.0 / g_dev / 1e12,
                                       "frac": pairs * bench.FP64_INST_PER_PAIR * 2.0 / g_dev / 1e12 / fp64_peak}}}
-        print(json.dumps(line), flush=True)
+        bench.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -262,7 +262,7 @@ def run_ensemble(args, world, rank, local_rank):
                 "cpu_baseline": cpu,
                 "gcfm": {"metric": "gcfm_agent_steps_per_s", "value": ast_ / (gcfm_ms * 1e-3), "unit": "agent-steps/s",
                          "e2e_value": ast_ / (wall_ms * 1e-3), "members": n_rooms, "fp64_peak_tflops": fp64_peak}}
-        print(json.dumps(line), flush=True)
+        bench.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
