@@ -77,6 +77,11 @@ long long oc_place_box(const double *box, const double *X, int Nx, const double 
  * np.random.get_state()[1:5], advanced in place; perm (N ints) and noise (n_active,2) are outputs. */
 int oc_rng_step_draw(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N, int n_active, int *perm,
                      double *noise);
+/* The same, plus n_ckpt snapshots of the generator state as it is after n_active - q pairs (q = 0 .. n_ckpt-1; snapshot q:
+ * ckpt_key + 624 q, ckpt_pos[q], ckpt_has[q], ckpt_cached[q]): look-ahead draws for an upper bound of agents. */
+int oc_rng_step_draw_ckpt(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N, int n_active,
+                          int *perm, double *noise, int n_ckpt, uint32_t *ckpt_key, int *ckpt_pos, int *ckpt_has,
+                          double *ckpt_cached);
 
 /* ------------------------------------------------------------------ room rasteriser (K8)
  * Replaces simulation.create_potential (simulations.py:516-576) followed by the value remap of

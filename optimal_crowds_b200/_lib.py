@@ -83,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows", "oc_rng_step_draw", "oc_gcfm_step_multi_launch", "oc_gcfm_step_multi_finish"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows", "oc_rng_step_draw", "oc_rng_step_draw_ckpt", "oc_gcfm_step_multi_launch", "oc_gcfm_step_multi_finish"]
 
 
 def load():
@@ -111,6 +111,8 @@ def load():
                                                                                      C.c_int, C.c_void_p]
     lib.oc_gcfm_step_multi_finish.argtypes = [C.c_int, vpp_, vpp_, ip, ip]
     lib.oc_rng_step_draw.argtypes = [C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, ip, dp]
+    lib.oc_rng_step_draw_ckpt.argtypes = [C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, ip, dp, C.c_int,
+                                          C.POINTER(C.c_uint32), ip, ip, dp]
     lib.oc_place_box.restype = C.c_longlong
     lib.oc_place_box.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(C.c_uint32), ip, dp, dp, C.c_int]
     lib.oc_wall_tiles_bytes.argtypes = [C.c_void_p]

@@ -170,11 +170,22 @@ extern "C" long long oc_place_box(const double *box, const double *X, int Nx, co
 // State = np.random.get_state()[1:5], advanced in place.  perm: N ints; noise: (n_active, 2) doubles.
 extern "C" int oc_rng_step_draw(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N, int n_active,
                                 int *perm, double *noise) {
+    return oc_rng_step_draw_ckpt(mt_key, mt_pos, has_gauss, cached_gauss, N, n_active, perm, noise, 0, nullptr, nullptr,
+                                 nullptr, nullptr);
+}
+
+// The same draw with snapshots of the generator state as it is after n_active - q pairs, q = 0 .. n_ckpt-1: a caller that
+// draws a step's randomness ahead of time for an UPPER BOUND of agents (nobody leaves) can later continue the stream
+// exactly where the reference would be once the true count (n_active - q) is known (look-ahead RNG of the run loop).
+extern "C" int oc_rng_step_draw_ckpt(uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int N,
+                                     int n_active, int *perm, double *noise, int n_ckpt, uint32_t *ckpt_key,
+                                     int *ckpt_pos, int *ckpt_has, double *ckpt_cached) {
     OC_ARG(mt_key && mt_pos && has_gauss && cached_gauss && perm && (n_active == 0 || noise) && N >= 0 && n_active >= 0 &&
-           *mt_pos >= 0 && *mt_pos <= 624, "oc_rng_step_draw");
+           *mt_pos >= 0 && *mt_pos <= 624 && n_ckpt >= 0 && (n_ckpt == 0 || (ckpt_key && ckpt_pos && ckpt_has && ckpt_cached)),
+           "oc_rng_step_draw");
     ocrng::Mt mt{mt_key, *mt_pos, *has_gauss, *cached_gauss};
     mt.permutation(N, perm);
-    for (int q = 0; q < 2 * n_active; q++) noise[q] = mt.gauss();
+    mt.gauss_fill(noise, 2ll * n_active, n_ckpt, ckpt_key, ckpt_pos, ckpt_has, ckpt_cached);
     *mt_pos = mt.pos; *has_gauss = mt.has_gauss; *cached_gauss = mt.gauss_;
     return OC_OK;
 }

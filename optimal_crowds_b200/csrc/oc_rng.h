@@ -7,8 +7,12 @@
 //   gauss()          legacy_gauss: polar Box-Muller with one cached value (has_gauss / cached_gaussian of get_state())
 // Pinned against numpy itself by tests/test_cpu_host.py (bit-identical draws and generator state).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace ocrng {
 
@@ -79,6 +83,75 @@ struct Mt {
         gauss_ = f * x1;
         has_gauss = 1;
         return f * x2;
+    }
+    // n consecutive gauss() values into out[], same values and same final state as n calls.  The generator is advanced
+    // sequentially (the rejection test needs only x1, x2), the expensive part -- f = sqrt(-2 log(r2) / r2) -- is evaluated
+    // afterwards, by several threads for large n.  ckpt (optional): snapshots of the generator state as it is after
+    // value number n - 2q, q = 0 .. n_ckpt-1 (q-th snapshot: key at ckpt_key + 624 q, ...), for a caller that drew more
+    // values than it turns out to need (look-ahead of the GCFM step: values come in pairs, n even).
+    void gauss_fill(double *out, long long n, int n_ckpt = 0, uint32_t *ckpt_key = nullptr, int *ckpt_pos = nullptr,
+                    int *ckpt_has = nullptr, double *ckpt_cached = nullptr) {
+        long long idx = 0;
+        const int had = has_gauss;
+        const double had_val = gauss_;
+        if (n > 0 && has_gauss) { out[idx++] = gauss_; has_gauss = 0; gauss_ = 0.0; }
+        const long long rem = n - idx, n_ev = (rem + 1) / 2;
+        std::vector<double> X1(n_ev), X2(n_ev), R2(n_ev);
+        // snapshot q is wanted after value n - 2q = after event e_q = (n - 2q - idx + 1) / 2 - 1 (or the start state)
+        auto snap = [&](int q) {
+            if (!ckpt_key) return;
+            std::memcpy(ckpt_key + (size_t)624 * q, key, 624 * sizeof(uint32_t));
+            ckpt_pos[q] = pos;
+        };
+        std::vector<long long> ev_of(n_ckpt, -2);
+        for (int q = 0; q < n_ckpt; q++) {
+            const long long v = n - 2ll * q;            // values drawn at that point
+            if (v < 0) continue;
+            ev_of[q] = (v <= idx) ? -1 : (v - idx + 1) / 2 - 1;
+            if (ev_of[q] == -1) snap(q);                // the state before any new event (only the cached value was used)
+        }
+        for (long long e = 0; e < n_ev; e++) {
+            double x1, x2, r2;
+            do {
+                x1 = 2.0 * next_double() - 1.0;
+                x2 = 2.0 * next_double() - 1.0;
+                r2 = x1 * x1 + x2 * x2;
+            } while (r2 >= 1.0 || r2 == 0.0);
+            X1[e] = x1; X2[e] = x2; R2[e] = r2;
+            for (int q = 0; q < n_ckpt; q++)
+                if (ev_of[q] == e) snap(q);
+        }
+        auto fill = [&](long long e0, long long e1) {
+            for (long long e = e0; e < e1; e++) {
+                const double f = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]);
+                out[idx + 2 * e] = f * X2[e];
+                if (idx + 2 * e + 1 < n) out[idx + 2 * e + 1] = f * X1[e];
+            }
+        };
+        const int n_thr = n_ev >= 8192 ? std::max(1, std::min(8, (int)std::thread::hardware_concurrency())) : 1;
+        if (n_thr > 1) {
+            std::vector<std::thread> pool;
+            const long long per = (n_ev + n_thr - 1) / n_thr;
+            for (int t = 1; t < n_thr; t++) pool.emplace_back(fill, std::min(n_ev, t * per), std::min(n_ev, (t + 1) * per));
+            fill(0, std::min(n_ev, per));
+            for (auto &th : pool) th.join();
+        } else {
+            fill(0, n_ev);
+        }
+        // cache flag / value as they are after v values (v = n for the generator itself, n - 2q for the snapshots)
+        auto cached_after = [&](long long v, int *has, double *cv) {
+            if (v == 0) { *has = had; *cv = had_val; return; }
+            if (v <= idx || (v - idx) % 2 == 0) { *has = 0; *cv = 0.0; return; }
+            const long long e = (v - idx + 1) / 2 - 1;      // the event whose second value is still cached
+            *has = 1;
+            *cv = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]) * X1[e];
+        };
+        cached_after(n, &has_gauss, &gauss_);
+        for (int q = 0; q < n_ckpt; q++) {
+            const long long v = n - 2ll * q;
+            if (v < 0 || !ckpt_key) continue;
+            cached_after(v, &ckpt_has[q], &ckpt_cached[q]);
+        }
     }
 };
 

@@ -98,7 +98,7 @@ def test_step_randomness_lookahead_is_stream_exact():
     from optimal_crowds_b200._rng import StepRandomness
     N = 9000
     rng_exits = np.random.RandomState(99)
-    exits = [0, 0, 3, 0, 1500, 7, 0, 0, 1, 400, 0, 1000, 90, 0, 0]   # incl. exits beyond every checkpoint but the first
+    exits = [0, 0, 3, 0, 1500, 7, 0, 0, 1, 400, 0, 1000, 90, 63, 0]   # incl. more exits in one step than snapshots are kept
     # reference sequence
     np.random.seed(42)
     ref, n = [], N
@@ -124,7 +124,8 @@ def test_step_randomness_lookahead_is_stream_exact():
         n -= e
     end = np.random.get_state()
     assert end[2] == end_ref[2] and np.array_equal(end[1], end_ref[1]) and end[3:] == end_ref[3:]
-    assert sr.hits >= len(exits) - 3 and sr.misses >= 2          # first step + the step after the foreign draw
+    # misses: the first step, the step after the foreign draw, and the steps after >= N_CKPT (64) exits (4 of them)
+    assert sr.hits == len(exits) - 6 and sr.misses == 6
 
 
 def test_member_rng_is_the_seeded_global_stream():
@@ -196,3 +197,36 @@ def test_c_crowd_placement_is_bit_identical_to_the_numpy_restatement():
     finally:
         np.random.set_state(st0)
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(s1[1], s2[1]) and s1[2:] == s2[2:]
+
+
+def test_c_legacy_rng_equals_numpy_draws_and_state():
+    """oc_rng_step_draw_ckpt (csrc/oc_rng.h: MT19937, masked-rejection intervals, Fisher-Yates from the top, polar
+    Box-Muller with its cached value; transform threaded for large counts) == RandomState.choice(arange(N), N, False) +
+    normal(size=(n, 2)), bit for bit, incl. the generator state afterwards and the look-ahead snapshots"""
+    import ctypes as C
+    from optimal_crowds_b200 import _lib
+    lib = _lib.load()
+    U = C.POINTER(C.c_uint32)
+    for seed in range(24):
+        rs = np.random.RandomState(seed)
+        if seed % 3 == 0:
+            rs.normal(size=3)                       # leaves a cached gaussian in the state
+        N = int(np.random.RandomState(seed + 99).randint(1, 30000 if seed % 6 == 0 else 2500))
+        na = int(N * 0.8)
+        st = rs.get_state()
+        key = st[1].copy(); pos = C.c_int(st[2]); hg = C.c_int(st[3]); cg = C.c_double(st[4])
+        perm = np.empty(N, dtype=np.int32); noise = np.empty((na, 2))
+        nck = min(40, na + 1)
+        ck = np.zeros((nck, 624), dtype=np.uint32); cp = np.zeros(nck, dtype=np.int32)
+        ch = np.zeros(nck, dtype=np.int32); cc = np.zeros(nck)
+        rc = lib.oc_rng_step_draw_ckpt(key.ctypes.data_as(U), C.byref(pos), C.byref(hg), C.byref(cg), N, na,
+                                       perm.ctypes.data_as(_lib.ip), _lib._hp(noise), nck, ck.ctypes.data_as(U),
+                                       cp.ctypes.data_as(_lib.ip), ch.ctypes.data_as(_lib.ip), _lib._hp(cc))
+        ref = np.random.RandomState(); ref.set_state(st)
+        p2 = ref.choice(np.arange(N), N, replace=False); n2 = ref.normal(size=(na, 2)); s2 = ref.get_state()
+        assert rc == 0 and np.array_equal(perm, p2) and np.array_equal(noise, n2)
+        assert np.array_equal(key, s2[1]) and (pos.value, hg.value, cg.value) == (s2[2], s2[3], s2[4])
+        for q in (0, 1, nck - 1):                   # snapshot q = the state after na - q pairs
+            r3 = np.random.RandomState(); r3.set_state(st)
+            r3.choice(np.arange(N), N, replace=False); r3.normal(size=(na - q, 2)); s3 = r3.get_state()
+            assert np.array_equal(ck[q], s3[1]) and (int(cp[q]), int(ch[q]), float(cc[q])) == (s3[2], s3[3], s3[4])
