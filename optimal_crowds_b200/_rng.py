@@ -53,6 +53,8 @@ class StepRandomness:
     N_CKPT = 64     # the look-ahead survives up to N_CKPT - 1 exits in one step
     MIN_N = 2048    # below this numpy's own draws cost less than moving the generator state in and out
 
+    _pool = None   # one helper thread for all simulations of the process (the C draw releases the GIL)
+
     def __init__(self, lookahead: bool = True, rng=np.random):
         # rng: the global ``np.random`` module (reference behaviour) or a ``np.random.RandomState`` of an ensemble member
         self.rng = rng
@@ -63,6 +65,8 @@ class StepRandomness:
     def draw(self, N: int, n_active: int):
         """(perm, noise) of the step that starts now; the generator ends where the reference's would."""
         sp, self._spec = self._spec, None
+        if sp is not None and "future" in sp:     # the look-ahead is drawn by the helper thread: collect it
+            sp["perm"], sp["Z"], _, sp["ck"] = sp.pop("future").result()
         if N < self.MIN_N:
             perm = self.rng.choice(np.arange(N), N, replace=False)
             noise = self.rng.normal(size=(n_active, 2)) if n_active else np.zeros((0, 2))
@@ -90,5 +94,10 @@ class StepRandomness:
         if state0[0] != "MT19937":
             return
         n_ckpt = min(self.N_CKPT, n_upper + 1)
-        perm, Z, _, ck = _c_draw(state0, N, n_upper, n_ckpt)
-        self._spec = dict(N=N, n_spec=n_upper, state0=state0, perm=perm, Z=Z, ck=ck, n_ckpt=n_ckpt)
+        if StepRandomness._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            StepRandomness._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="oc-rng")
+        # drawn from a COPY of the state on the helper thread, concurrently with the rest of the step's host work and the
+        # GPU sweep (ctypes releases the GIL for the C call)
+        fut = StepRandomness._pool.submit(_c_draw, state0, N, n_upper, n_ckpt)
+        self._spec = dict(N=N, n_spec=n_upper, state0=state0, future=fut, n_ckpt=n_ckpt)

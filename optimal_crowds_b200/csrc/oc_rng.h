@@ -11,7 +11,6 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
-#include <thread>
 #include <vector>
 
 namespace ocrng {
@@ -84,9 +83,8 @@ struct Mt {
         has_gauss = 1;
         return f * x2;
     }
-    // n consecutive gauss() values into out[], same values and same final state as n calls.  The generator is advanced
-    // sequentially (the rejection test needs only x1, x2), the expensive part -- f = sqrt(-2 log(r2) / r2) -- is evaluated
-    // afterwards, by several threads for large n.  ckpt (optional): snapshots of the generator state as it is after
+    // n consecutive gauss() values into out[], same values and same final state as n calls (the generator is advanced
+    // first -- the rejection test needs only x1, x2 -- then f = sqrt(-2 log(r2) / r2) is evaluated).  ckpt (optional): snapshots of the generator state as it is after
     // value number n - 2q, q = 0 .. n_ckpt-1 (q-th snapshot: key at ckpt_key + 624 q, ...), for a caller that drew more
     // values than it turns out to need (look-ahead of the GCFM step: values come in pairs, n even).
     void gauss_fill(double *out, long long n, int n_ckpt = 0, uint32_t *ckpt_key = nullptr, int *ckpt_pos = nullptr,
@@ -110,6 +108,9 @@ struct Mt {
             ev_of[q] = (v <= idx) ? -1 : (v - idx + 1) / 2 - 1;
             if (ev_of[q] == -1) snap(q);                // the state before any new event (only the cached value was used)
         }
+        long long first_ck_ev = n_ev;
+        for (int q = 0; q < n_ckpt; q++)
+            if (ev_of[q] >= 0) first_ck_ev = std::min(first_ck_ev, ev_of[q]);
         for (long long e = 0; e < n_ev; e++) {
             double x1, x2, r2;
             do {
@@ -118,25 +119,16 @@ struct Mt {
                 r2 = x1 * x1 + x2 * x2;
             } while (r2 >= 1.0 || r2 == 0.0);
             X1[e] = x1; X2[e] = x2; R2[e] = r2;
-            for (int q = 0; q < n_ckpt; q++)
-                if (ev_of[q] == e) snap(q);
+            if (e >= first_ck_ev)   // the snapshots sit at the last n_ckpt events
+                for (int q = 0; q < n_ckpt; q++)
+                    if (ev_of[q] == e) snap(q);
         }
-        auto fill = [&](long long e0, long long e1) {
-            for (long long e = e0; e < e1; e++) {
-                const double f = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]);
-                out[idx + 2 * e] = f * X2[e];
-                if (idx + 2 * e + 1 < n) out[idx + 2 * e + 1] = f * X1[e];
-            }
-        };
-        const int n_thr = n_ev >= 8192 ? std::max(1, std::min(8, (int)std::thread::hardware_concurrency())) : 1;
-        if (n_thr > 1) {
-            std::vector<std::thread> pool;
-            const long long per = (n_ev + n_thr - 1) / n_thr;
-            for (int t = 1; t < n_thr; t++) pool.emplace_back(fill, std::min(n_ev, t * per), std::min(n_ev, (t + 1) * per));
-            fill(0, std::min(n_ev, per));
-            for (auto &th : pool) th.join();
-        } else {
-            fill(0, n_ev);
+        // the transform, one event at a time (measured: helper threads / OpenMP teams cost more per call than the ~0.3 ms
+        // they could save at 12.5 k pairs; the run loop overlaps this whole function with the GPU step instead)
+        for (long long e = 0; e < n_ev; e++) {
+            const double f = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]);
+            out[idx + 2 * e] = f * X2[e];
+            if (idx + 2 * e + 1 < n) out[idx + 2 * e + 1] = f * X1[e];
         }
         // cache flag / value as they are after v values (v = n for the generator itself, n - 2q for the snapshots)
         auto cached_after = [&](long long v, int *has, double *cv) {

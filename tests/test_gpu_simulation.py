@@ -321,3 +321,28 @@ def test_prefetched_density_gives_the_same_field(in_repo_cwd):
         opt.compute_optimal_velocity(0.0, m2); got3 = opt.d_phi.clone()
     assert torch.equal(ref1, got1) and torch.equal(ref2, got2) and torch.equal(ref2, got3)
     assert not torch.equal(ref1, ref2)
+
+
+def test_c_drawn_and_lookahead_randomness_do_not_change_a_run():
+    """3000 agents (above StepRandomness.MIN_N): per-step randomness through the C restatement of numpy's legacy stream,
+    with and without look-ahead, == numpy's own draws: same trajectories, same generator state afterwards"""
+    from optimal_crowds_b200 import _rng, simulations, synthetic
+    room = synthetic.slalom_room(1024, 512, agents=3000, pitch=6.0, door_pitch=12.0)
+    outs = []
+    for mode in ("numpy", "c", "c+lookahead"):
+        np.random.seed(17)
+        old = _rng.StepRandomness.MIN_N
+        _rng.StepRandomness.MIN_N = 10 ** 9 if mode == "numpy" else 2048
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                s = simulations.simulation(room, 0.5, record=False, lookahead=(mode == "c+lookahead"))
+                s._solve_all()
+                for _ in range(12):
+                    s.step(s.dt)
+        finally:
+            _rng.StepRandomness.MIN_N = old
+        outs.append((np.array(s._h_now), np.random.get_state(), s._rng.hits))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0])
+        assert np.array_equal(o[1][1], outs[0][1][1]) and o[1][2:] == outs[0][1][2:]
+    assert outs[2][2] >= 10 and outs[1][2] == 0
