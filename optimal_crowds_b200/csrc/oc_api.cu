@@ -70,6 +70,28 @@ extern "C" int oc_ctx_set_int(oc_ctx *ctx, const char *key, int value) {
         ctx->gcfm_poll_ns = value;
         return OC_OK;
     }
+    if (!strcmp(key, "gcfm_margin_mm")) {
+        OC_ARG(value >= 20 && value <= 1000, "gcfm_margin_mm out of range (20..1000)");
+        ctx->gcfm_margin_mm = value;
+        ctx->gcfm_margin_hold = 0;
+        return OC_OK;
+    }
+    if (!strcmp(key, "gcfm_fov_cull")) {
+        ctx->gcfm_fov_cull = value != 0;
+        return OC_OK;
+    }
+    if (!strcmp(key, "gcfm_ws_pair")) {
+        ctx->gcfm_ws_pair = value != 0;
+        return OC_OK;
+    }
+    if (!strcmp(key, "gcfm_split")) {
+        ctx->gcfm_split = value != 0;
+        return OC_OK;
+    }
+    if (!strcmp(key, "gcfm_overlap")) {
+        ctx->gcfm_overlap = value != 0;
+        return OC_OK;
+    }
     oc::set_error("unknown option '%s'", key);
     return OC_ERR_ARG;
 }
@@ -97,6 +119,9 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     if (c->batch_pinned) cudaFreeHost(c->batch_pinned);
     for (auto s : c->batch_streams) cudaStreamDestroy(s);
     for (auto e : c->batch_events) cudaEventDestroy(e);
+    if (c->gcfm_side) cudaStreamDestroy(c->gcfm_side);
+    if (c->gcfm_ev_fork) cudaEventDestroy(c->gcfm_ev_fork);
+    if (c->gcfm_ev_join) cudaEventDestroy(c->gcfm_ev_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;

@@ -54,6 +54,14 @@ struct oc_ctx {
     size_t multi_bytes = 0;
     int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
     int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
+    int gcfm_margin_mm = 250;  // oc_ctx_set_int("gcfm_margin_mm"): displacement margin (2 x per-axis bound) of the fast attempt
+    int gcfm_margin_hold = 0;  // steps left on the full margin after a step that exceeded the small one
+    int gcfm_fov_cull = 1;     // oc_ctx_set_int("gcfm_fov_cull"): drop candidates that cannot enter the field of view
+    int gcfm_overlap = 1;      // oc_ctx_set_int("gcfm_overlap"): wall search / sampler on a side stream next to the cell list
+    int gcfm_ws_pair = 1;      // oc_ctx_set_int("gcfm_ws_pair"): wall search scans two tiles per memory round trip
+    int gcfm_split = 1;        // oc_ctx_set_int("gcfm_split"): two-kernel sweep (candidate lists, then the dependency chain)
+    cudaStream_t gcfm_side = nullptr;
+    cudaEvent_t gcfm_ev_fork = nullptr, gcfm_ev_join = nullptr;
     // in-kernel final reduction of the fused step (oc_hjb_fused.cuh): ticket counters on the device, results in
     // mapped page-locked host memory (slot b: value at [2b], sequence number at [2b+1])
     unsigned *fr_ticket = nullptr;

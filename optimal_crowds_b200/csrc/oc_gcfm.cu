@@ -59,6 +59,11 @@ struct Ws {  // device workspace carved out of ctx->gcfm_ws
     double *doors;                          // flattened door rectangles of all keys
     int *perm, *rank, *nzidx, *flags, *exit_mark, *agent_bin, *cell_agents, *bin_start, *bin_cursor;
     uint8_t *status0;
+    long long *wall_ind;  // flat index of the nearest wall node (wall_search_kernel -> agent_terms_kernel)
+    // two-kernel sweep: per agent the candidate list in processing order, (agent j, position in the summation order),
+    // LIST_CAP entries; (candidates, of which later in the sweep); (|v|, a_i, b_i, beta_i) of pedestrians.py:242-243,267
+    int2 *lst, *lhdr;
+    double4 *ell;
     double *time0;   // per-agent clock at step start (restored when a step is redone on the exact slow path)
     KeyDev *keys;
     // [0] ticket [1] flags: bit0 sampler range, bit1 list overflow, bit2 displacement > margin [2] interacting pairs
@@ -225,86 +230,186 @@ __device__ void wall_force_from_node(const oc_gcfm_params &p, const AgentEllipse
 
 // K4: exact np.argmin(sqrt((X-x)^2+(Y-y)^2) + V*10e3) (pedestrians.py:311-313), one warp per agent.
 // Only nodes with V<0 can win (their offset is <= -|pot|*1e4, the host checks that this exceeds the room
-// diagonal).  Rings of WT x WT node tiles around the agent are scanned, skipping tiles without wall
-// nodes, until no node outside the scanned square can reach the best key.  Returns the flat index
-// (first index among equal keys, like np.argmin) on every lane.
+// diagonal).  Returns the flat index (first index among equal keys, like np.argmin) on every lane.
+//
+// Search (round 2, v2).  tiles[] holds per WT x WT node tile 1 + the ring distance (in tiles) to the nearest tile with a
+// wall node, so the rings below that distance are skipped.  Phase 1 scans the first ring that holds wall nodes, which
+// gives an upper bound `wbest` of the minimum key.  Phase 2 then determines in ONE step the last ring K that can still
+// hold a node with a key <= wbest (the rounded distance to anything outside the square of radius K exceeds it) and
+// scans the tiles of rings k+1..K that (a) hold wall nodes and (b) whose nearest possible node is not farther than
+// wbest -- occupancy bytes of up to 128 tiles per memory round trip, two tiles (16 independent loads per lane) per round
+// trip of the node scan.  The result is the global argmin whatever superset of the necessary tiles is scanned, so the
+// pruning only has to be conservative: for a node of a tile, |X[ix] - x| >= gx := max(X[ix0] - x, x - X[ix1], 0) in
+// floating point as well (rounding is monotonic), hence its computed distance is >= sqrt(gx*gx + gy*gy) evaluated with
+// the same operations, and its key >= that + off_min (the most negative potential x 10e3).
+template <bool PAIR>
+struct WallSearch {
+    const double *__restrict__ X, *__restrict__ Y, *__restrict__ V;
+    const uint8_t *__restrict__ tiles;
+    int Ny, Nx, ntx, nty, lane;
+    double x, y, off_min;
+    double best, wbest;
+    long long best_i;
+
+    __device__ __forceinline__ double tile_lb(int ttx, int tty) const {
+        const int ix0 = ttx * WT, ix1 = min(ix0 + WT - 1, Nx - 1), iy0 = tty * WT, iy1 = min(iy0 + WT - 1, Ny - 1);
+        const double gx = fmax(fmax(X[ix0] - x, x - X[ix1]), 0.0), gy = fmax(fmax(Y[iy0] - y, y - Y[iy1]), 0.0);
+        return sqrt(gx * gx + gy * gy);
+    }
+    // strict: a node with an equal key and a lower flat index would win the tie
+    __device__ __forceinline__ bool cannot_win(double lb) const { return wbest < lb * (1.0 - 0x1p-50) + off_min; }
+    __device__ __forceinline__ void load_tile(int ttx, int tty, double (&vv)[8]) const {
+        static_assert(WT * WT == 8 * 32, "tile scan: 8 nodes per lane");
+        // nodes c = lane, lane + 32, ...: coalesced rows of the tile, ascending flat index inside a lane
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int c = lane + 32 * q, iy = tty * WT + c / WT, ix = ttx * WT + (c % WT);
+            vv[q] = (iy < Ny && ix < Nx) ? __ldg(V + (size_t)iy * Nx + ix) : 0.0;
+        }
+    }
+    __device__ __forceinline__ void eval_tile(int ttx, int tty, const double (&vv)[8]) {
+        const int ix = ttx * WT + (lane % WT);
+        const double ddx = (ix < Nx) ? X[ix] - x : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (vv[q] < 0) {
+                const int iy = tty * WT + (lane + 32 * q) / WT;
+                const double ddy = Y[iy] - y;
+                const double key = sqrt(ddx * ddx + ddy * ddy) + vv[q] * 10e3;
+                const long long fi = (long long)iy * Nx + ix;
+                if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
+            }
+        }
+    }
+    __device__ __forceinline__ void refresh_wbest() {
+        double wb = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+        wbest = wb;
+    }
+    // position r on ring k (border of the (2k+1)^2 tile square around (tcx, tcy)) -> tile
+    __device__ __forceinline__ static void ring_tile(int tcx, int tcy, int k, int r, int &tx, int &ty) {
+        const int side = 2 * k + 1;
+        if (k == 0) { tx = tcx; ty = tcy; }
+        else if (r < side) { tx = tcx - k + r; ty = tcy - k; }
+        else if (r < 2 * side) { tx = tcx - k + (r - side); ty = tcy + k; }
+        else if (r < 2 * side + (side - 2)) { tx = tcx - k; ty = tcy - k + 1 + (r - 2 * side); }
+        else { tx = tcx + k; ty = tcy - k + 1 + (r - 2 * side - (side - 2)); }
+    }
+    // scan the tiles of rings ka..kb that hold wall nodes and can still win
+    __device__ void scan_rings(int tcx, int tcy, int ka, int kb) {
+        int total = 0;
+        for (int k = ka; k <= kb; k++) total += (k == 0) ? 1 : 8 * k;
+        constexpr int U = 2;
+        for (int base = 0; base < total; base += 32 * U) {
+            int tx[U], ty[U];
+            double lb[U];
+            bool cand[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                int t = base + 32 * u + lane, k = ka;
+                tx[u] = ty[u] = -1;
+                if (t < total) {
+                    while (t >= ((k == 0) ? 1 : 8 * k)) { t -= (k == 0) ? 1 : 8 * k; k++; }
+                    ring_tile(tcx, tcy, k, t, tx[u], ty[u]);
+                }
+                cand[u] = tx[u] >= 0 && tx[u] < ntx && ty[u] >= 0 && ty[u] < nty && tiles[ty[u] * ntx + tx[u]] == 1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                lb[u] = 0.0;
+                if (cand[u]) {
+                    lb[u] = tile_lb(tx[u], ty[u]);
+                    cand[u] = !cannot_win(lb[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                unsigned todo = __ballot_sync(0xffffffffu, cand[u]);
+                while (todo) {
+                    // up to two tiles per memory round trip; a tile that the bound found meanwhile rules out is dropped
+                    int ax = -1, ay = -1, bx = -1, by = -1;
+                    while (todo && (PAIR ? bx < 0 : ax < 0)) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const double l = __shfl_sync(0xffffffffu, lb[u], src);
+                        const int sx_ = __shfl_sync(0xffffffffu, tx[u], src), sy_ = __shfl_sync(0xffffffffu, ty[u], src);
+                        if (cannot_win(l)) continue;
+                        if (ax < 0) { ax = sx_; ay = sy_; } else { bx = sx_; by = sy_; }
+                    }
+                    if (ax < 0) break;
+                    double va[8];
+                    load_tile(ax, ay, va);
+                    if (PAIR) {
+                        double vb[8];
+                        if (bx >= 0) load_tile(bx, by, vb);
+                        eval_tile(ax, ay, va);
+                        if (bx >= 0) eval_tile(bx, by, vb);
+                    } else {
+                        eval_tile(ax, ay, va);
+                    }
+                    refresh_wbest();
+                }
+            }
+        }
+    }
+};
+
+template <bool PAIR>
 __device__ long long wall_argmin_warp(const double *__restrict__ X, const double *__restrict__ Y,
                                       const double *__restrict__ V, const uint8_t *__restrict__ tiles, int Ny,
                                       int Nx, double x, double y, double off_min) {
-    const int lane = threadIdx.x & 31;
-    const int ntx = (Nx + WT - 1) / WT, nty = (Ny + WT - 1) / WT;
+    WallSearch<PAIR> ws;
+    ws.X = X; ws.Y = Y; ws.V = V; ws.tiles = tiles; ws.Ny = Ny; ws.Nx = Nx;
+    ws.lane = threadIdx.x & 31;
+    ws.ntx = (Nx + WT - 1) / WT; ws.nty = (Ny + WT - 1) / WT;
+    ws.x = x; ws.y = y; ws.off_min = off_min;
+    ws.best = INFINITY; ws.wbest = INFINITY; ws.best_i = (long long)Ny * Nx;
+    const int ntx = ws.ntx, nty = ws.nty, lane = ws.lane;
     // tile containing the node nearest to (x,y); any centre is correct, a near one is fast
     const double sx = X[1] - X[0], sy = Y[1] - Y[0];
     int cx = (int)fmin(fmax(x / sx, 0.0), (double)(Nx - 1)), cy = (int)fmin(fmax(y / sy, 0.0), (double)(Ny - 1));
     const int tcx = cx / WT, tcy = cy / WT;
-    double best = INFINITY;
-    long long best_i = (long long)Ny * Nx;
     const int kmax = max(max(tcx, ntx - 1 - tcx), max(tcy, nty - 1 - tcy));
     // tiles[t] = 1 + (ring distance, in tiles, from t to the nearest tile holding a wall node, capped at RING_CAP):
     // the rings below that distance are known to be empty and are skipped (no memory round trips for them)
-    const int k0 = min((int)tiles[tcy * ntx + tcx] - 1, kmax);
-    for (int k = max(k0, 0); k <= kmax; k++) {
-        const int ty_lo = tcy - k, ty_hi = tcy + k, tx_lo = tcx - k, tx_hi = tcx + k;
-        // ring k = border of the (2k+1)^2 tile square.  The occupancy bytes of 32 ring tiles are fetched at once
-        // (one lane each) and only the occupied ones are scanned: the ring costs one memory round trip instead
-        // of one per tile.
-        const int side = 2 * k + 1;
-        const int ring_n = (k == 0) ? 1 : 8 * k;
-        for (int rbase = 0; rbase < ring_n; rbase += 32) {
-            const int r = rbase + lane;
-            int tx = -1, ty = -1;
-            if (r < ring_n) {
-                if (k == 0) { tx = tcx; ty = tcy; }
-                else if (r < side) { tx = tx_lo + r; ty = ty_lo; }
-                else if (r < 2 * side) { tx = tx_lo + (r - side); ty = ty_hi; }
-                else if (r < 2 * side + (side - 2)) { tx = tx_lo; ty = ty_lo + 1 + (r - 2 * side); }
-                else { tx = tx_hi; ty = ty_lo + 1 + (r - 2 * side - (side - 2)); }
-            }
-            const bool occ = tx >= 0 && tx < ntx && ty >= 0 && ty < nty && tiles[ty * ntx + tx] == 1;
-            unsigned todo = __ballot_sync(0xffffffffu, occ);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int ttx = __shfl_sync(0xffffffffu, tx, src), tty = __shfl_sync(0xffffffffu, ty, src);
-                // the 8 potentials a lane looks at (nodes c = lane, lane + 32, ...: coalesced rows of the tile, ascending flat
-                // index inside a lane) are fetched with independent loads first: one memory round trip per tile instead of
-                // eight dependent ones
-                static_assert(WT * WT == 8 * 32, "tile scan: 8 nodes per lane");
-                {
-                    double vv[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int c = lane + 32 * q, iy = tty * WT + c / WT, ix = ttx * WT + (c % WT);
-                        vv[q] = (iy < Ny && ix < Nx) ? __ldg(V + (size_t)iy * Nx + ix) : 0.0;
-                    }
-                    const int ix = ttx * WT + (lane % WT);
-                    const double ddx = (ix < Nx) ? X[ix] - x : 0.0;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (vv[q] < 0) {
-                            const int iy = tty * WT + (lane + 32 * q) / WT;
-                            const double ddy = Y[iy] - y;
-                            const double key = sqrt(ddx * ddx + ddy * ddy) + vv[q] * 10e3;
-                            const long long fi = (long long)iy * Nx + ix;
-                            if (key < best || (key == best && fi < best_i)) { best = key; best_i = fi; }
-                        }
-                    }
-                }
-            }
+    int k = max(min((int)tiles[tcy * ntx + tcx] - 1, kmax), 0);
+    // (one call site of scan_rings for both phases: the scan is inlined once)
+    int ka = k, kb = k;
+    bool last = false;
+    for (;;) {
+        ws.scan_rings(tcx, tcy, ka, kb);
+        if (last || kb >= kmax) break;
+        if (!(ws.wbest < INFINITY)) {  // ---- phase 1: ring by ring until one holds a wall node
+            ka = kb = kb + 1;
+            continue;
         }
-        // lower bound of the distance to any node outside the scanned square
-        double lb = INFINITY;
-        int ix_lo = tx_lo * WT - 1, ix_hi = (tx_hi + 1) * WT, iy_lo = ty_lo * WT - 1, iy_hi = (ty_hi + 1) * WT;
-        if (ix_lo >= 0) lb = fmin(lb, x - X[ix_lo]);
-        if (ix_hi < Nx) lb = fmin(lb, X[ix_hi] - x);
-        if (iy_lo >= 0) lb = fmin(lb, y - Y[iy_lo]);
-        if (iy_hi < Ny) lb = fmin(lb, Y[iy_hi] - y);
-        double wbest = best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wbest = fmin(wbest, __shfl_xor_sync(0xffffffffu, wbest, o));
-        // strict: an outside node with an equal key and a lower flat index would win the tie
-        if (lb == INFINITY || wbest < lb * (1.0 - 0x1p-50) + off_min) break;
+        // ---- phase 2: last ring K that can hold a node with a key <= wbest.  ring_lb(kk) = lower bound of the distance
+        // to any node outside the square of radius kk (32 radii per round trip, one per lane)
+        int K = kmax;
+        for (int k2 = kb; k2 <= kmax; k2 += 32) {
+            const int kk = k2 + lane;
+            bool stop = false;
+            if (kk <= kmax) {
+                double lb = INFINITY;
+                const int ix_lo = (tcx - kk) * WT - 1, ix_hi = (tcx + kk + 1) * WT, iy_lo = (tcy - kk) * WT - 1,
+                          iy_hi = (tcy + kk + 1) * WT;
+                if (ix_lo >= 0) lb = fmin(lb, x - X[ix_lo]);
+                if (ix_hi < Nx) lb = fmin(lb, X[ix_hi] - x);
+                if (iy_lo >= 0) lb = fmin(lb, y - Y[iy_lo]);
+                if (iy_hi < Ny) lb = fmin(lb, Y[iy_hi] - y);
+                stop = lb == INFINITY || ws.cannot_win(lb);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) { K = k2 + __ffs(m) - 1; break; }
+        }
+        if (K <= kb) break;
+        ka = kb + 1;
+        kb = K;
+        last = true;
     }
+    double best = ws.best;
+    long long best_i = ws.best_i;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -381,6 +486,7 @@ __device__ __forceinline__ void setup_body(int N, const double *__restrict__ x, 
     uint8_t s = status[i];
     w.status0[i] = s;
     w.time0[i] = tim[i];
+    if (s && !(fabs(vxi) < 16.0 && fabs(vyi) < 16.0)) w.counters[6] = 1;  // `wild`: the sweep then culls nothing
     int bx = min(max((int)floor(xi * inv_cs), 0), nbx - 1), by = min(max((int)floor(yi * inv_cs), 0), nby - 1);
     int b = by * nbx + bx;
     w.agent_bin[i] = b;
@@ -427,7 +533,7 @@ __global__ void restore_kernel(int N, Ws w, double *__restrict__ x, double *__re
     x[i] = s.x; y[i] = s.y; vx[i] = s.z; vy[i] = s.w;
     tim[i] = w.time0[i];
     status[i] = w.status0[i];
-    if (i == 0) {  // the sampler-range flag (bit 0, set by prepare_kernel) survives a redo; everything else restarts
+    if (i == 0) {  // the sampler-range flag (bit 0, set by agent_terms_kernel) survives a redo; everything else restarts
         w.counters[0] = 0;
         w.counters[1] &= 1;
         for (int q = 2; q < 8; q++) w.counters[q] = 0;
@@ -459,43 +565,56 @@ __device__ __forceinline__ void noise_index_body(int N, const Ws &w) {
     }
 }
 
-// K5: per-agent terms that depend only on the agent's own old state: desired velocity (sampler) and wall
-// force.  One warp per agent.
-__device__ __forceinline__ void prepare_body(const oc_gcfm_params &p, int N, const Ws &w,
-                                             const double *__restrict__ X, const double *__restrict__ Y,
-                                             const double *__restrict__ vdes, const int *__restrict__ key_id,
-                                             int simu_step) {
-    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// K5: per-agent terms that depend only on the agent's own old state: desired velocity (sampler) and wall force.
+// Two kernels: the nearest-wall search with one WARP per agent (memory-latency bound: few registers, many resident
+// warps), then sampler + wall force with one THREAD per agent (round 1 ran them on lane 0 of the search warp).
+__device__ __forceinline__ bool agent_owned(const oc_gcfm_params &p, int key, double yi) {
+    // key-sharded run: the rank that solved this agent's target set evaluates it
+    if (p.key_mod > 0 && key % p.key_mod != p.key_rem) return false;
+    if (p.own1 > p.own0) {  // row-decomposed run: the rank whose band holds the sampled rows
+        const int orow = sampler_owner_row(p, yi);
+        if (orow < p.own0 || orow >= p.own1) return false;
+    }
+    return true;
+}
+template <bool PAIR>
+__device__ __forceinline__ void wall_search_body(const oc_gcfm_params &p, int N, const Ws &w,
+                                                 const double *__restrict__ X, const double *__restrict__ Y,
+                                                 const int *__restrict__ key_id) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= N || !w.status0[i]) return;
-    const int lane = threadIdx.x & 31;
-    const KeyDev k = w.keys[key_id[i]];
-    double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i];
-    if (p.key_mod > 0 && key_id[i] % p.key_mod != p.key_rem) {
-        // key-sharded run: the rank that solved this agent's target set evaluates it -- all-zero bits for the merge
-        if (lane == 0) { w.des_x[i] = 0.0; w.des_y[i] = 0.0; w.wfx[i] = 0.0; w.wfy[i] = 0.0; }
+    const int key = key_id[i];
+    const double xi = w.x0[i], yi = w.y0[i];
+    if (!agent_owned(p, key, yi)) return;
+    const KeyDev *k = w.keys + key;
+    const long long ind = wall_argmin_warp<PAIR>(X, Y, k->V, k->tiles, p.Ny, p.Nx, xi, yi, k->off_min);
+    if ((threadIdx.x & 31) == 0) w.wall_ind[i] = ind;
+}
+__device__ __forceinline__ void agent_terms_body(const oc_gcfm_params &p, int N, const Ws &w,
+                                                 const double *__restrict__ X, const double *__restrict__ Y,
+                                                 const double *__restrict__ vdes, const int *__restrict__ key_id,
+                                                 int simu_step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !w.status0[i]) return;
+    const int key = key_id[i];
+    const double xi = w.x0[i], yi = w.y0[i], vxi = w.vx0[i], vyi = w.vy0[i];
+    if (!agent_owned(p, key, yi)) {  // all-zero bits for the bit-exact merge over the ranks
+        w.des_x[i] = 0.0; w.des_y[i] = 0.0; w.wfx[i] = 0.0; w.wfy[i] = 0.0;
         return;
     }
-    if (p.own1 > p.own0) {
-        // row-decomposed run: another rank owns this agent -- leave all-zero bits for the bit-exact merge
-        const int orow = sampler_owner_row(p, yi);
-        if (orow < p.own0 || orow >= p.own1) {
-            if (lane == 0) { w.des_x[i] = 0.0; w.des_y[i] = 0.0; w.wfx[i] = 0.0; w.wfy[i] = 0.0; }
-            return;
-        }
-    }
-    long long ind = wall_argmin_warp(X, Y, k.V, k.tiles, p.Ny, p.Nx, xi, yi, k.off_min);
-    if (lane == 0) {
-        double ux, uy;
-        int bad = choose_velocity(p, k, xi, yi, simu_step, ux, uy);
-        if (bad) atomicOr(&w.counters[1], 1);
-        w.des_x[i] = vdes[i] * ux;  // simulations.py:281
-        w.des_y[i] = vdes[i] * uy;
-        AgentEllipse ei = ellipse_of(p, vxi, vyi, vdes[i]);
-        double fx, fy;
-        wall_force_from_node(p, ei, xi, yi, vxi, vyi, X[ind % p.Nx], Y[ind / p.Nx], fx, fy);
-        w.wfx[i] = fx;
-        w.wfy[i] = fy;
-    }
+    const KeyDev k = w.keys[key];
+    long long ind = w.wall_ind[i];
+    if (ind < 0 || ind >= (long long)p.Ny * p.Nx) ind = 0;  // no comparable key at all (NaN position): np.argmin gives 0
+    double ux, uy;
+    const int bad = choose_velocity(p, k, xi, yi, simu_step, ux, uy);
+    if (bad) atomicOr(&w.counters[1], 1);
+    w.des_x[i] = vdes[i] * ux;  // simulations.py:281
+    w.des_y[i] = vdes[i] * uy;
+    const AgentEllipse ei = ellipse_of(p, vxi, vyi, vdes[i]);
+    double fx, fy;
+    wall_force_from_node(p, ei, xi, yi, vxi, vyi, X[ind % p.Nx], Y[ind / p.Nx], fx, fy);
+    w.wfx[i] = fx;
+    w.wfy[i] = fy;
 }
 
 // ascending bitonic sort of a[0..n) (64-bit keys, n <= m2 = power of two, a[n..m2) is overwritten with padding) by one warp
@@ -517,54 +636,44 @@ __device__ __forceinline__ void warp_sort_u64(unsigned long long *a, int n, int 
         }
 }
 
-// K6: the sweep (simulations.py:271-332).  Per agent (one warp):
-//  A. gather the candidates -- agents whose OLD position is within cutoff + margin of i's old position -- from the
-//     cell list into shared memory (no waiting: only the immutable snapshot is read);
-//  B. two sorts, still without waiting: the PROCESSING order (candidates later in the sweep first -- they are in
-//     their snapshot state -- then the earlier ones by ascending sweep rank, i.e. roughly in the order in which they
-//     will publish) and the SUMMATION order (ascending agent index, `for j in range(N)`, simulations.py:287);
-//  C. forces, 32 candidates at a time in processing order: an earlier candidate must have finished (acquire on its
-//     done-flag, which also carries its inside/exited status), then its NEW packed state is read.  Cutoff test and
-//     pair force (simulations.py:291-295) go to the candidate's slot, +0.0 if it does not interact (adding +0.0 to
-//     the running sum changes no bit: the sum starts at +0.0 and can never become -0.0);
-//  D. ascending-j sum, Euler step, exit test, publish.
-// The sweep is a chain of dependencies (an agent needs the new state of every earlier neighbour), so what matters is
-// the time from "my last dependency published" to "I publish": with this ordering it is ONE batch of pair forces plus
-// the sum, instead of all remaining batches plus the sort.
-__device__ __forceinline__ void
-sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, double *__restrict__ y,
-           double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
-           uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
-           double inv_cs, int nbx, int nby, unsigned poll_ns, double margin, int cap, unsigned char *glists) {
-    extern __shared__ __align__(16) unsigned char sweep_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj (ints), proc, ord
-    // (16-bit slot indices).  Fast path: `cap` = CAND_CAP slots in shared memory; exact slow path (glists != NULL): `cap`
-    // slots per warp in global memory, sized from the candidate count the refused fast attempt measured
-    unsigned char *base = glists ? glists + ((size_t)blockIdx.x * SWEEP_WARPS + wid) * cap * SWEEP_SLOT_BYTES
-                                 : sweep_smem + (size_t)wid * CAND_CAP * SWEEP_SLOT_BYTES;
-    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + cap;
-    int *ckk = reinterpret_cast<int *>(lfy + cap), *cj = ckk + cap;
-    unsigned short *proc = reinterpret_cast<unsigned short *>(cj + cap), *ord = proc + cap;
-    unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(lfx), *sort_b = reinterpret_cast<unsigned long long *>(lfy);
-    const double reach = p.cutoff + margin;
-    const double reach2 = reach * reach;
-    const int span = (int)ceil(reach * inv_cs);
-    const unsigned lt_mask = (1u << lane) - 1;
-    int pairs_total = 0;
-    for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(&w.counters[0], 1);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= N) break;
-        const int i = w.perm[r];
-        if (!w.status0[i]) continue;  // simulations.py:277
-        const double4 si = w.snap4[i];
-        const double xi = si.x, yi = si.y, vxi = si.z, vyi = si.w, vd = vdes[i];
-        const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
+// Candidate search of one agent (stage A of the sweep), shared by the one-kernel sweep and the two-kernel path.
+struct CandSearch {
+    int span;
+    double rho_s, reach2, sin_fov, cos_fov;
+    bool cull_ok;
+    __device__ __forceinline__ CandSearch(const oc_gcfm_params &p, const Ws &w, double margin, double inv_cs, int fov_cull) {
+        const double reach = p.cutoff + margin;
+        const int span = (int)ceil(reach * inv_cs);
+        // No agent moves more than margin/2 per axis in one step (checked below; a violation voids the attempt), i.e. not
+        // more than rho = margin/sqrt(2).  A candidate can therefore only come within the cutoff if its OLD position is
+        // within cutoff + rho of i's old position ...
+        const double rho_s = margin * 0.70710678118654757 * (1.0 + 1e-6) + 1e-12;
+        const double reach_c = p.cutoff + rho_s + 1e-9, reach2 = reach_c * reach_c;
+        // ... and can only be inside i's field of view (k > 0, pedestrians.py:259-262) if the direction to its old position
+        // is within the half-angle of the field of view plus the angle asin(rho/d) that a disc of radius rho subtends.  A
+        // candidate outside contributes exactly -+0.0 whatever its new state is (k = 0 and exp(.) finite), so it is neither
+        // waited for nor evaluated.  Only applied when every quantity involved is tame, so that 0 * exp(.) cannot be NaN:
+        // setup_kernel's `wild` flag (counters[6]: some |velocity component| >= 16 m/s or NaN) is clear, the semi-axes are
+        // positive and bounded (q <= max(a, b), a <= a_min + 23 tau_a, b in [b_min, b_max] for v_des > 0) and
+        // (q_i + q_j)/eta stays below the overflow threshold of exp; otherwise every candidate within reach is kept.
+        const double sin_fov = sqrt(fmax(1.0 - p.cos_fov * p.cos_fov, 0.0));
+        const bool cull_ok = fov_cull && w.counters[6] == 0 && p.cos_fov < 0.0 && p.cos_fov > -1.0 && p.v_max <= 16.0 &&
+                             p.a_min > 0.0 && p.tau_a >= 0.0 && p.b_min > 0.0 && p.b_max >= p.b_min &&
+                             2.0 * (p.a_min + 23.0 * p.tau_a) + 2.0 * p.b_max < 600.0 * p.eta;
+        this->span = span; this->rho_s = rho_s; this->reach2 = reach2; this->sin_fov = sin_fov; this->cos_fov = p.cos_fov;
+        this->cull_ok = cull_ok;
+    }
+    // fills ckk / cj / the two sort-key lists for agent i (sweep rank r); returns the number of candidates kept (<= cap;
+    // on overflow the attempt is flagged void and the list truncated)
+    __device__ __forceinline__ int gather(const oc_gcfm_params &p, const Ws &w, int i, int r, double xi, double yi,
+                                          double vxi, double vyi, double vd, double ni, int nbx, int nby, int cap,
+                                          int *ckk, int *cj, unsigned long long *sort_a, unsigned long long *sort_b) const {
+        const int lane = threadIdx.x & 31;
+        const unsigned lt_mask = (1u << lane) - 1;
+        const bool do_cull = cull_ok && ni < 32.0 && vd > 0.0;  // (false for a NaN speed; v_des > 0 keeps b_i, b_j in [b_min, b_max])
         // ---- A. candidates.  Each of the (2 span + 1) bin rows is one contiguous range of the cell list; lanes fetch the
         // range bounds in parallel, then the concatenated ranges are scanned 32 entries at a time.
-        int nc = 0, n_later = 0;
+        int nc = 0;
         const int b = w.agent_bin[i];
         const int bix = b % nbx, biy = b / nbx;
         const int by0 = max(biy - span, 0), nrows = min(biy + span, nby - 1) - by0 + 1;
@@ -595,9 +704,24 @@ sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, 
             if (kk >= 0) {
                 const double2 pj = *reinterpret_cast<const double2 *>(w.cell_state + kk);  // (x, y)
                 const double ox = pj.x - xi, oy = pj.y - yi;
-                if (ox * ox + oy * oy < reach2) {
-                    jr = w.cell_jr[kk];
-                    keep = jr.x != i;  // j != i (simulations.py:291)
+                const double d2 = ox * ox + oy * oy;
+                if (d2 < reach2) {
+                    bool cull = false;
+                    if (do_cull) {
+                        if (ni == 0.0) cull = true;  // k = 0 (pedestrians.py:259-261)
+                        else {
+                            const double d = sqrt(d2), sn = rho_s / d;
+                            if (sn < 0.999 * sin_fov) {  // fov half-angle + asin(sn) stays below pi
+                                const double cs = sqrt(1.0 - sn * sn);
+                                const double cos_lim = p.cos_fov * cs - sin_fov * sn;  // cos(fov half-angle + asin(sn))
+                                cull = (vxi * ox + vyi * oy) / (ni * d) < cos_lim - 1e-9;
+                            }
+                        }
+                    }
+                    if (!cull) {
+                        jr = w.cell_jr[kk];
+                        keep = jr.x != i;  // j != i (simulations.py:291)
+                    }
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -620,6 +744,57 @@ sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, 
             // counters[3]); the agent still advances with the first `cap` candidates so that later agents do not wait forever
             nc = cap;
         }
+        return nc;
+    }
+};
+
+// K6: the sweep (simulations.py:271-332).  Per agent (one warp):
+//  A. gather the candidates -- agents whose OLD position is within cutoff + margin of i's old position -- from the
+//     cell list into shared memory (no waiting: only the immutable snapshot is read);
+//  B. two sorts, still without waiting: the PROCESSING order (candidates later in the sweep first -- they are in
+//     their snapshot state -- then the earlier ones by ascending sweep rank, i.e. roughly in the order in which they
+//     will publish) and the SUMMATION order (ascending agent index, `for j in range(N)`, simulations.py:287);
+//  C. forces, 32 candidates at a time in processing order: an earlier candidate must have finished (acquire on its
+//     done-flag, which also carries its inside/exited status), then its NEW packed state is read.  Cutoff test and
+//     pair force (simulations.py:291-295) go to the candidate's slot, +0.0 if it does not interact (adding +0.0 to
+//     the running sum changes no bit: the sum starts at +0.0 and can never become -0.0);
+//  D. ascending-j sum, Euler step, exit test, publish.
+// The sweep is a chain of dependencies (an agent needs the new state of every earlier neighbour), so what matters is
+// the time from "my last dependency published" to "I publish": with this ordering it is ONE batch of pair forces plus
+// the sum, instead of all remaining batches plus the sort.
+__device__ __forceinline__ void
+sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, double *__restrict__ y,
+           double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim,
+           uint8_t *__restrict__ status, const double *__restrict__ vdes, const int *__restrict__ key_id, int tag,
+           double inv_cs, int nbx, int nby, unsigned poll_ns, double margin, int cap, unsigned char *glists,
+           int fov_cull) {
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // per warp: fx, fy (doubles; reused as the 64-bit sort buffers before the forces exist), ckk, cj (ints), proc, ord
+    // (16-bit slot indices).  Fast path: `cap` = CAND_CAP slots in shared memory; exact slow path (glists != NULL): `cap`
+    // slots per warp in global memory, sized from the candidate count the refused fast attempt measured
+    unsigned char *base = glists ? glists + ((size_t)blockIdx.x * SWEEP_WARPS + wid) * cap * SWEEP_SLOT_BYTES
+                                 : sweep_smem + (size_t)wid * CAND_CAP * SWEEP_SLOT_BYTES;
+    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + cap;
+    int *ckk = reinterpret_cast<int *>(lfy + cap), *cj = ckk + cap;
+    unsigned short *proc = reinterpret_cast<unsigned short *>(cj + cap), *ord = proc + cap;
+    unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(lfx), *sort_b = reinterpret_cast<unsigned long long *>(lfy);
+    const CandSearch cs_(p, w, margin, inv_cs, fov_cull);
+    const unsigned lt_mask = (1u << lane) - 1;
+    int pairs_total = 0;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&w.counters[0], 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= N) break;
+        const int i = w.perm[r];
+        if (!w.status0[i]) continue;  // simulations.py:277
+        const double4 si = w.snap4[i];
+        const double xi = si.x, yi = si.y, vxi = si.z, vyi = si.w, vd = vdes[i];
+        const AgentEllipse ei = ellipse_of(p, vxi, vyi, vd);
+        // ---- A. candidates
+        int n_later = 0;
+        const int nc = cs_.gather(p, w, i, r, xi, yi, vxi, vyi, vd, ei.ni, nbx, nby, cap, ckk, cj, sort_a, sort_b);
         __syncwarp();
         // everything the final Euler step needs that does not depend on the neighbours is fetched now, so that no global
         // load sits between "last dependency published" and "I publish"
@@ -736,15 +911,197 @@ sweep_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, 
                 const double *door = w.doors + 4 * (door_off + d);
                 if (fabs(nx_ - door[0]) < door[2] * 0.5 && fabs(ny_ - door[1]) < door[3] * 0.5) out = true;
             }
+            // publish first: the release store orders the two 16-byte stores of the new state before the flag; everything
+            // that only the host / the next kernel reads is written afterwards, off the dependency chain
             w.live4[i] = make_double4(nx_, ny_, nvx, nvy);
+            st_release(&w.flags[i], tag * 2 + (out ? 0 : 1));
             x[i] = nx_; y[i] = ny_; vx[i] = nvx; vy[i] = nvy;
             tim[i] = tim_i + p.dt;  // pedestrians.py:191
             if (out) {
                 status[i] = 0;
                 w.exit_mark[r] = i + 1;  // simulations.py:331-332, ordered by sweep position
             }
-            __threadfence();
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && pairs_total) atomicAdd(&w.counters[2], pairs_total);
+}
+
+// ---- two-kernel form of the sweep (the default fast path).  The candidate search, its two sorts and the agent's own
+// ellipse need only the step-start snapshot, so cand_kernel does them for all agents at once -- fully parallel, next to
+// the wall search on the side stream -- and leaves per agent a list in PROCESSING order of (candidate, position in the
+// SUMMATION order).  chain_kernel is then the dependency chain only: wait, pair force, ordered sum, Euler step, publish.
+// Its body is less than half of the one-kernel sweep's instructions (which overflowed the 32 KB instruction cache level
+// behind L0: ncu `no_instruction` was a quarter of all stall cycles), and it needs neither sort buffers nor cell lists.
+constexpr int LIST_CAP = CAND_CAP;
+constexpr size_t CAND_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * (2 * sizeof(unsigned long long) + 2 * sizeof(int) + sizeof(unsigned short));
+constexpr size_t CHAIN_SMEM = (size_t)SWEEP_WARPS * CAND_CAP * (2 * sizeof(double) + sizeof(unsigned short));
+
+__device__ __forceinline__ void cand_body(const oc_gcfm_params &p, int N, const Ws &w, const double *__restrict__ vdes,
+                                          double inv_cs, int nbx, int nby, double margin, int fov_cull) {
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * SWEEP_WARPS + wid;
+    if (i >= N || !w.status0[i]) return;
+    unsigned char *base = sweep_smem + (size_t)wid * (CAND_SMEM / SWEEP_WARPS);
+    unsigned long long *sort_a = reinterpret_cast<unsigned long long *>(base), *sort_b = sort_a + CAND_CAP;
+    int *ckk = reinterpret_cast<int *>(sort_b + CAND_CAP), *cj = ckk + CAND_CAP;
+    unsigned short *pos_of = reinterpret_cast<unsigned short *>(cj + CAND_CAP);
+    const CandSearch cs_(p, w, margin, inv_cs, fov_cull);
+    const int r = w.rank[i];
+    const double4 si = w.snap4[i];
+    const double vd = vdes[i];
+    const AgentEllipse ei = ellipse_of(p, si.z, si.w, vd);
+    const int nc = cs_.gather(p, w, i, r, si.x, si.y, si.z, si.w, vd, ei.ni, nbx, nby, CAND_CAP, ckk, cj, sort_a, sort_b);
+    __syncwarp();
+    if (nc > 1) {
+        warp_sort_u64(sort_a, nc, lane);
+        warp_sort_u64(sort_b, nc, lane);
+    }
+    for (int t = lane; t < nc; t += 32) pos_of[(unsigned short)sort_b[t]] = (unsigned short)t;  // slot -> summation position
+    __syncwarp();
+    int n_later = 0;
+    int2 *out = w.lst + (size_t)i * LIST_CAP;
+    for (int t0 = 0; t0 < nc; t0 += 32) {
+        const int t = t0 + lane;
+        bool is_later = false;
+        if (t < nc) {
+            const unsigned long long ka = sort_a[t];
+            const int slot = (unsigned short)ka;
+            out[t] = make_int2(cj[slot], pos_of[slot]);
+            is_later = (ka >> 32) == 0;  // key 0 <=> later in the sweep: no waiting
+        }
+        n_later += __popc(__ballot_sync(0xffffffffu, is_later));
+    }
+    if (lane == 0) {
+        w.lhdr[i] = make_int2(nc, n_later);
+        w.ell[i] = make_double4(ei.ni, ei.a_i, ei.b_i, ei.beta_i);
+    }
+}
+
+__device__ __forceinline__ void
+chain_body(const oc_gcfm_params &p, int N, const Ws &w, double *__restrict__ x, double *__restrict__ y,
+           double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
+           const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, unsigned poll_ns, double margin) {
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *base = sweep_smem + (size_t)wid * (CHAIN_SMEM / SWEEP_WARPS);
+    double *lfx = reinterpret_cast<double *>(base), *lfy = lfx + CAND_CAP;  // forces by summation position
+    unsigned short *nzl = reinterpret_cast<unsigned short *>(lfy + CAND_CAP);  // positions of the non-zero terms
+    const unsigned lt_mask = (1u << lane) - 1;
+    int pairs_total = 0;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&w.counters[0], 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= N) break;
+        const int i = w.perm[r];
+        if (!w.status0[i]) continue;  // simulations.py:277
+        const int2 hdr = w.lhdr[i];
+        const int nc = hdr.x, n_later = hdr.y;
+        const double4 si = w.snap4[i];
+        const double xi = si.x, yi = si.y, vxi = si.z, vyi = si.w, vd = vdes[i];
+        const double4 el = w.ell[i];
+        AgentEllipse ei;
+        ei.ni = el.x; ei.a_i = el.y; ei.b_i = el.z; ei.beta_i = el.w;
+        const int2 *lst = w.lst + (size_t)i * LIST_CAP;
+        // everything the final Euler step needs that does not depend on the neighbours is fetched now, so that no global
+        // load sits between "last dependency published" and "I publish"
+        double nz_x = 0.0, nz_y = 0.0, wf_x = 0.0, wf_y = 0.0, de_x = 0.0, de_y = 0.0, tim_i = 0.0;
+        int door_off = 0, n_doors = 0;
+        if (lane == 0) {
+            const int nz = w.nzidx[i];
+            nz_x = w.noise[2 * nz]; nz_y = w.noise[2 * nz + 1];
+            wf_x = w.wfx[i]; wf_y = w.wfy[i];
+            de_x = w.des_x[i]; de_y = w.des_y[i];
+            tim_i = tim[i];
+            const KeyDev *kp = w.keys + key_id[i];
+            door_off = kp->door_off; n_doors = kp->n_doors;
+        }
+        // ---- forces in processing order (later candidates first: snapshot state, no waiting), stored by summation position
+        int n_pairs = 0;
+        for (int base_c = 0; base_c < nc; base_c += 32) {
+            const int c = base_c + lane;
+            double fx = 0.0, fy = 0.0;
+            int pos = -1;
+            bool hit = false;
+            if (c < nc) {
+                const int2 e = lst[c];
+                const int j = e.x;
+                pos = e.y;
+                double4 sj;
+                bool alive = true;
+                if (c >= n_later) {  // earlier in the sweep: needs j's NEW state
+                    int f;
+                    while (((f = ld_acquire(&w.flags[j])) >> 1) != tag) __nanosleep(poll_ns);
+                    alive = (f & 1) != 0;
+                    const double2 a = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j));
+                    const double2 bb = __ldcg(reinterpret_cast<const double2 *>(w.live4 + j) + 1);
+                    sj = make_double4(a.x, a.y, bb.x, bb.y);
+                } else {  // later: still in its old state
+                    sj = w.snap4[j];
+                }
+                if (alive) {
+                    const double ddx = sj.x - xi, ddy = sj.y - yi;
+                    if (sqrt(ddx * ddx + ddy * ddy) < p.cutoff) {  // pedestrians.py:354, simulations.py:291
+                        pair_force(p, ei, xi, yi, vxi, vyi, vd, sj.x, sj.y, sj.z, sj.w, fx, fy);
+                        hit = true;
+                    } else { fx = 0.0; fy = 0.0; }
+                }
+            }
+            n_pairs += __popc(__ballot_sync(0xffffffffu, hit));
+            if (pos >= 0) { lfx[pos] = fx; lfy[pos] = fy; }
+        }
+        __syncwarp();
+        // ---- ascending-j sum (simulations.py:285-295); exact zeros are squeezed out first (see the one-kernel sweep)
+        int nnz = 0;
+        for (int t0 = 0; t0 < nc; t0 += 32) {
+            const int t = t0 + lane;
+            const bool nz = t < nc && !(lfx[t] == 0.0 && lfy[t] == 0.0);  // NaN terms are kept
+            const unsigned mz = __ballot_sync(0xffffffffu, nz);
+            if (nz) nzl[nnz + __popc(mz & lt_mask)] = (unsigned short)t;
+            nnz += __popc(mz);
+        }
+        __syncwarp();
+        double acc = 0.0;
+        if (lane < 2) {  // lane 0 -> x component, lane 1 -> y component
+            const double *src = lane == 0 ? lfx : lfy;
+            for (int t = 0; t < nnz; t++) acc = acc + src[nzl[t]];
+        }
+        const double rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1);
+        if (lane == 0) {
+            double cx = vxi + p.half_noise * nz_x + rx + wf_x;  // simulations.py:303
+            double cy = vyi + p.half_noise * nz_y + ry + wf_y;
+            double ax = (de_x - cx) / p.relaxation, ay = (de_y - cy) / p.relaxation;  // :307-308
+            double nx_ = xi + cx * p.dt + 0.5 * ax * p.dt2;  // :314-315
+            double ny_ = yi + cy * p.dt + 0.5 * ay * p.dt2;
+            double nvx = cx + ax * p.dt, nvy = cy + ay * p.dt;  // :316-317
+            double nr = sqrt(nvx * nvx + nvy * nvy);            // :321
+            if (!(nr < p.v_max)) {                              // :323-326
+                double sc = p.v_max / nr;
+                nvx = nvx * sc;
+                nvy = nvy * sc;
+            }
+            // the candidate search of every agent assumed that nobody moves more than margin/2 per axis in one step
+            const double disp = fmax(fabs(nx_ - xi), fabs(ny_ - yi));
+            if (!(disp <= margin * 0.5)) {
+                atomicOr(&w.counters[1], 4);
+                atomicMax(reinterpret_cast<unsigned long long *>(w.counters + 4), (unsigned long long)__double_as_longlong(disp));
+            }
+            pairs_total += n_pairs;
+            bool out = false;
+            for (int d = 0; d < n_doors; d++) {  // pedestrians.py:132-136
+                const double *door = w.doors + 4 * (door_off + d);
+                if (fabs(nx_ - door[0]) < door[2] * 0.5 && fabs(ny_ - door[1]) < door[3] * 0.5) out = true;
+            }
+            w.live4[i] = make_double4(nx_, ny_, nvx, nvy);
             st_release(&w.flags[i], tag * 2 + (out ? 0 : 1));
+            x[i] = nx_; y[i] = ny_; vx[i] = nvx; vy[i] = nvy;
+            tim[i] = tim_i + p.dt;  // pedestrians.py:191
+            if (out) {
+                status[i] = 0;
+                w.exit_mark[r] = i + 1;  // simulations.py:331-332, ordered by sweep position
+            }
         }
         __syncwarp();
     }
@@ -789,6 +1146,8 @@ struct GcfmMember {
     int N, simu_step, tag, nbx, nby, nbins;
     double inv_cs;
     unsigned poll_ns;
+    int fov_cull;
+    double margin;  // displacement margin of this member's fast attempt
 };
 
 __global__ void setup_kernel(int N, const double *__restrict__ x, const double *__restrict__ y,
@@ -800,17 +1159,36 @@ __global__ void setup_kernel(int N, const double *__restrict__ x, const double *
 __global__ void __launch_bounds__(1024) scan_kernel(int *a, int n) { scan_body(a, n); }
 __global__ void scatter_kernel(int N, Ws w) { scatter_body(N, w); }
 __global__ void __launch_bounds__(1024) noise_index_kernel(int N, Ws w) { noise_index_body(N, w); }
-__global__ void __launch_bounds__(128) prepare_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X,
-                                                      const double *__restrict__ Y, const double *__restrict__ vdes,
-                                                      const int *__restrict__ key_id, int simu_step) {
-    prepare_body(p, N, w, X, Y, vdes, key_id, simu_step);
+// PAIR: two tiles per round trip of the node scan (96 registers, 5 CTAs/SM) or one (80 registers, 6 CTAs/SM)
+template <bool PAIR>
+__global__ void __launch_bounds__(128, PAIR ? 5 : 6)
+wall_search_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X, const double *__restrict__ Y,
+                   const int *__restrict__ key_id) {
+    wall_search_body<PAIR>(p, N, w, X, Y, key_id);
+}
+__global__ void __launch_bounds__(128) agent_terms_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X,
+                                                          const double *__restrict__ Y, const double *__restrict__ vdes,
+                                                          const int *__restrict__ key_id, int simu_step) {
+    agent_terms_body(p, N, w, X, Y, vdes, key_id, simu_step);
 }
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
              double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
              const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, double inv_cs, int nbx, int nby,
-             unsigned poll_ns, double margin, int cap, unsigned char *glists) {
-    sweep_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, inv_cs, nbx, nby, poll_ns, margin, cap, glists);
+             unsigned poll_ns, double margin, int cap, unsigned char *glists, int fov_cull) {
+    sweep_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, inv_cs, nbx, nby, poll_ns, margin, cap, glists,
+               fov_cull);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+cand_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ vdes, double inv_cs, int nbx, int nby, double margin,
+            int fov_cull) {
+    cand_body(p, N, w, vdes, inv_cs, nbx, nby, margin, fov_cull);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+chain_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
+             double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
+             const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, unsigned poll_ns, double margin) {
+    chain_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, poll_ns, margin);
 }
 __global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
     exit_compact_body(N, w, out);
@@ -840,14 +1218,27 @@ __global__ void __launch_bounds__(1024) noise_index_multi_kernel(const GcfmMembe
     const GcfmMember &m = ms[blockIdx.y];
     noise_index_body(m.N, m.w);
 }
-__global__ void __launch_bounds__(128) prepare_multi_kernel(const GcfmMember *__restrict__ ms) {
+template <bool PAIR>
+__global__ void __launch_bounds__(128, PAIR ? 5 : 6) wall_search_multi_kernel(const GcfmMember *__restrict__ ms) {
     const GcfmMember &m = ms[blockIdx.y];
-    prepare_body(m.prm, m.N, m.w, m.X, m.Y, m.vdes, m.key, m.simu_step);
+    wall_search_body<PAIR>(m.prm, m.N, m.w, m.X, m.Y, m.key);
+}
+__global__ void __launch_bounds__(128) agent_terms_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    agent_terms_body(m.prm, m.N, m.w, m.X, m.Y, m.vdes, m.key, m.simu_step);
 }
 __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_multi_kernel(const GcfmMember *__restrict__ ms) {
     const GcfmMember &m = ms[blockIdx.y];
     sweep_body(m.prm, m.N, m.w, m.x, m.y, m.vx, m.vy, m.tim, m.status, m.vdes, m.key, m.tag, m.inv_cs, m.nbx, m.nby,
-               m.poll_ns, DISP_MARGIN, CAND_CAP, nullptr);
+               m.poll_ns, m.margin, CAND_CAP, nullptr, m.fov_cull);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) cand_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    cand_body(m.prm, m.N, m.w, m.vdes, m.inv_cs, m.nbx, m.nby, m.margin, m.fov_cull);
+}
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) chain_multi_kernel(const GcfmMember *__restrict__ ms) {
+    const GcfmMember &m = ms[blockIdx.y];
+    chain_body(m.prm, m.N, m.w, m.x, m.y, m.vx, m.vy, m.tim, m.status, m.vdes, m.key, m.tag, m.poll_ns, m.margin);
 }
 __global__ void __launch_bounds__(1024) exit_compact_multi_kernel(const GcfmMember *__restrict__ ms) {
     const GcfmMember &m = ms[blockIdx.y];
@@ -863,7 +1254,7 @@ wall_probe_kernel(oc_gcfm_params p, int N, const double *__restrict__ X, const d
                   double *__restrict__ fy, long long *__restrict__ ind_out) {
     int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= N) return;
-    long long ind = wall_argmin_warp(X, Y, V, tiles, p.Ny, p.Nx, px[i], py[i], off_min);
+    long long ind = wall_argmin_warp<true>(X, Y, V, tiles, p.Ny, p.Nx, px[i], py[i], off_min);
     if ((threadIdx.x & 31) == 0) {
         AgentEllipse ei = ellipse_of(p, pvx[i], pvy[i], vdes[i]);
         double ax, ay;
@@ -975,7 +1366,7 @@ extern "C" int oc_wall_tiles(oc_ctx *ctx, const double *d_V, uint8_t *d_tiles, d
 static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins, Ws &w, int **pinned, cudaStream_t st) {
     size_t need = 0;
     auto al = [&](size_t b) { need += ((b + 255) / 256) * 256; };
-    for (int q = 0; q < 9; q++) al(sizeof(double) * N);
+    for (int q = 0; q < 10; q++) al(sizeof(double) * N);
     al(sizeof(double4) * N);
     al(sizeof(double4) * N);
     al(sizeof(double4) * N);
@@ -988,6 +1379,9 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     al(N);
     al(sizeof(KeyDev) * std::max(n_keys, 1));
     al(sizeof(int) * 8);
+    al(sizeof(int2) * N);
+    al(sizeof(double4) * N);
+    al(sizeof(int2) * (size_t)N * LIST_CAP);
     if (ctx->gcfm_ws_bytes < need) {
         if (ctx->gcfm_ws) cudaFree(ctx->gcfm_ws);
         ctx->gcfm_ws = nullptr;
@@ -1011,6 +1405,7 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.x0 = carve<double>(p, N); w.y0 = carve<double>(p, N); w.vx0 = carve<double>(p, N); w.vy0 = carve<double>(p, N);
     w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
     w.time0 = carve<double>(p, N);
+    w.wall_ind = carve<long long>(p, N);
     w.noise = carve<double>(p, 2 * (size_t)N);
     w.doors = carve<double>(p, 4 * (size_t)std::max(n_doors, 1));
     w.perm = carve<int>(p, N); w.rank = carve<int>(p, N); w.nzidx = carve<int>(p, N);
@@ -1019,6 +1414,9 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.status0 = carve<uint8_t>(p, N);
     w.keys = carve<KeyDev>(p, std::max(n_keys, 1));
     w.counters = carve<int>(p, 8);
+    w.lhdr = carve<int2>(p, N);
+    w.ell = carve<double4>(p, N);
+    w.lst = carve<int2>(p, (size_t)N * LIST_CAP);
     size_t pin = sizeof(int) * ((size_t)N + OUT_HDR + 8);
     if (ctx->gcfm_pinned_bytes < pin) {
         if (ctx->gcfm_pinned) cudaFreeHost(ctx->gcfm_pinned);
@@ -1040,11 +1438,53 @@ struct GcfmLaunch {
     const int *key;
     Ws w;
     int *pinned;
+    double margin;  // displacement margin of the fast attempt in flight
+    int simu_step;
 };
+
+// displacement margin of the next fast attempt: the small one (oc_ctx_set_int "gcfm_margin_mm", default 0.25 m: no agent
+// moves more than 12.5 cm per axis and step) unless a recent step overflowed it, then DISP_MARGIN for a while
+double gcfm_fast_margin(oc_ctx *ctx) {
+    if (ctx->gcfm_margin_hold > 0) { ctx->gcfm_margin_hold--; return DISP_MARGIN; }
+    return std::min(DISP_MARGIN, std::max(0.02, ctx->gcfm_margin_mm * 1e-3));
+}
+// bin table size that fits every margin a fast or slow attempt may use (smaller margin = smaller cells = more bins)
+int gcfm_max_bins(const oc_ctx *ctx, double cutoff, int *nbx_out = nullptr, int *nby_out = nullptr) {
+    const double reach = cutoff + std::min(DISP_MARGIN, std::max(0.02, ctx->gcfm_margin_mm * 1e-3));
+    const double inv_cs = 2.0 / reach;
+    const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
+              nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
+    if (nbx_out) *nbx_out = nbx;
+    if (nby_out) *nby_out = nby;
+    return nbx * nby;
+}
+
+// fork / join of the side stream that runs the per-agent terms (wall search, sampler, wall force: they only need the
+// step-start snapshot) next to the cell-list kernels of the main stream
+int gcfm_fork(oc_ctx *ctx, cudaStream_t st, cudaStream_t *side) {
+    *side = st;
+    if (!ctx->gcfm_overlap) return OC_OK;
+    if (!ctx->gcfm_side) {
+        OC_CUDA(cudaStreamCreateWithFlags(&ctx->gcfm_side, cudaStreamNonBlocking));
+        OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_fork, cudaEventDisableTiming));
+        OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_join, cudaEventDisableTiming));
+    }
+    OC_CUDA(cudaEventRecord(ctx->gcfm_ev_fork, st));
+    OC_CUDA(cudaStreamWaitEvent(ctx->gcfm_side, ctx->gcfm_ev_fork, 0));
+    *side = ctx->gcfm_side;
+    return OC_OK;
+}
+int gcfm_join(oc_ctx *ctx, cudaStream_t st, cudaStream_t side) {
+    if (side == st) return OC_OK;
+    OC_CUDA(cudaEventRecord(ctx->gcfm_ev_join, side));
+    OC_CUDA(cudaStreamWaitEvent(st, ctx->gcfm_ev_join, 0));
+    return OC_OK;
+}
 
 // bins + cell list of one attempt of the current step; returns the attempt's done-flag generation (tag) or an error.
 // margin: displacement (2 x per axis) the candidate search allows for.  first = false: the state is restored first.
-int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, bool first) {
+int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, bool first, bool terms = false,
+                       bool split = false) {
     const int N = L.N;
     Ws &w = L.w;
     const double reach = L.prm.cutoff + margin;
@@ -1065,9 +1505,30 @@ int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margi
     if (++ctx->gcfm_tag >= 0x3fffffff) ctx->gcfm_tag = 1;  // per context: the done-flags live in the context's workspace
     const int tag = ctx->gcfm_tag;
     setup_kernel<<<nb, 256, 0, st>>>(N, L.x, L.y, L.vx, L.vy, L.tim, L.status, w, inv_cs, nbx, nby);
+    cudaStream_t side = st;
+    if (terms) {  // per-agent terms of the step (not repeated by a redo: they depend on the step-start state only)
+        int rc = gcfm_fork(ctx, st, &side);
+        if (rc) return rc;
+        if (ctx->gcfm_ws_pair) wall_search_kernel<true><<<(N * 32 + 127) / 128, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.key);
+        else wall_search_kernel<false><<<(N * 32 + 127) / 128, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.key);
+        agent_terms_kernel<<<nb * 2, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.vdes, L.key, L.simu_step);
+        oc::count_launch(2);
+    }
     scan_kernel<<<1, 1024, 0, st>>>(w.bin_start, nbins + 1);
     scatter_kernel<<<nb, 256, 0, st>>>(N, w);
     oc::count_launch(3);
+    if (split) {  // two-kernel sweep: candidate lists of all agents, next to the wall search on the side stream
+        OC_CUDA(cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+        cand_kernel<<<(N + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, CAND_SMEM, st>>>(L.prm, N, w, L.vdes, inv_cs, nbx, nby,
+                                                                                             margin, ctx->gcfm_fov_cull);
+        oc::count_launch();
+    }
+    if (terms) {
+        noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
+        oc::count_launch();
+        int rc = gcfm_join(ctx, st, side);
+        if (rc) return rc;
+    }
     return tag;
 }
 }  // namespace
@@ -1083,8 +1544,23 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
 }
 
 // the sweep launch of one attempt (fast: shared-memory lists of CAND_CAP slots; slow: global-memory lists of `cap` slots)
-static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int tag, double margin, int cap, bool slow) {
+static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int tag, double margin, int cap, bool slow,
+                             bool split = false) {
     const int N = L.N;
+    if (split && !slow) {  // the chain kernel of the two-kernel sweep (cand_kernel ran in gcfm_sweep_attempt)
+        int n_sm = 0, occ = 0;
+        OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+        OC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+        OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chain_kernel, SWEEP_WARPS * 32, CHAIN_SMEM));
+        int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
+        if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
+        chain_kernel<<<grid, SWEEP_WARPS * 32, CHAIN_SMEM, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes,
+                                                                L.key, tag, (unsigned)ctx->gcfm_poll_ns, margin);
+        exit_compact_kernel<<<1, 1024, 0, st>>>(N, L.w, L.pinned);
+        oc::count_launch(2);
+        OC_CUDA(cudaGetLastError());
+        return OC_OK;
+    }
     const double reach = L.prm.cutoff + margin, inv_cs = 2.0 / reach;
     const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
               nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
@@ -1118,7 +1594,8 @@ static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int ta
         glists = (unsigned char *)ctx->gcfm_glist;
     }
     sweep_kernel<<<grid, SWEEP_WARPS * 32, smem, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes, L.key, tag,
-                                                      inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns, margin, cap, glists);
+                                                      inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns, margin, cap, glists,
+                                                      ctx->gcfm_fov_cull);
     exit_compact_kernel<<<1, 1024, 0, st>>>(N, L.w, L.pinned);
     oc::count_launch(2);
     OC_CUDA(cudaGetLastError());
@@ -1135,12 +1612,8 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
     OC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    // the bin table is sized for the fast path's cells (the slow path only ever uses larger cells, i.e. fewer bins)
-    const double reach = prm->cutoff + DISP_MARGIN;
-    const double inv_cs = 2.0 / reach;
-    const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
-              nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
-    const int nbins = nbx * nby;
+    // the bin table is sized for the smallest cells any attempt uses (a wider margin means larger cells, i.e. fewer bins)
+    const int nbins = gcfm_max_bins(ctx, prm->cutoff);
     int n_doors = 0;
     for (int k = 0; k < n_keys; k++) n_doors += keys[k].n_doors;
     if (!ctx->gcfm_last) ctx->gcfm_last = new GcfmLaunch();
@@ -1172,11 +1645,11 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     OC_CUDA(cudaMemcpyAsync(w.doors, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
     OC_CUDA(cudaMemcpyAsync(w.perm, perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
     if (n_noise) OC_CUDA(cudaMemcpyAsync(w.noise, noise, sizeof(double) * 2 * n_noise, cudaMemcpyHostToDevice, st));
-    const int tag = gcfm_sweep_attempt(ctx, L, st, DISP_MARGIN, true);
+    L.margin = gcfm_fast_margin(ctx);
+    L.simu_step = simu_step;
+    const bool split = ctx->gcfm_split != 0;
+    const int tag = gcfm_sweep_attempt(ctx, L, st, L.margin, true, true, split);
     if (tag < 0) return tag;
-    noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
-    prepare_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(*prm, N, w, ctx->d_X, ctx->d_Y, d_vdes, d_key, simu_step);
-    oc::count_launch(2);
     if ((prm->own1 > prm->own0 || prm->key_mod > 0) && ctx->nccl_comm && ctx->nranks > 1) {
         // merge the per-agent terms over the ranks: des_x, des_y, wfx, wfy are carved back to back (padding is zero),
         // every agent was written by exactly one rank and is all-zero bits elsewhere; the sampler-range flag likewise
@@ -1184,7 +1657,7 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
         if ((rc = oc_dist_allreduce_max_u64(ctx, w.des_x, words, st))) return rc;
         if ((rc = oc_dist_allreduce_max_u64(ctx, w.counters, 4, st))) return rc;  // 8 ints
     }
-    if ((rc = gcfm_launch_sweep(ctx, L, st, tag, DISP_MARGIN, CAND_CAP, false))) return rc;
+    if ((rc = gcfm_launch_sweep(ctx, L, st, tag, L.margin, CAND_CAP, false, split))) return rc;
     OC_CUDA(cudaEventRecord(ctx->ev1, st));
     // hk / hd are pageable: cudaMemcpyAsync has already staged them when it returned
     ctx->gcfm_stream = st;
@@ -1206,14 +1679,33 @@ static int gcfm_finish_member(oc_ctx *ctx, int *exit_log, int *n_exit, bool sync
     // the step is redone with global-memory lists sized from the measured candidate count and with a margin that
     // covers the measured displacement, until an attempt is self-consistent.  The reference has neither limit
     // (simulations.py:285-303: all pairs, repulsions add to the velocity unclipped).
-    double margin = DISP_MARGIN;
+    double margin = L.margin;
     int cap = CAND_CAP;
     ctx->gcfm_redos = 0;
     for (int redo = 0; (pinned[1] & 6) != 0; redo++) {
         const double room_diag = std::sqrt(ctx->room_length * ctx->room_length + ctx->room_height * ctx->room_height);
-        if (redo >= 12 || margin > 4.0 * room_diag + 8.0) {
+        if (redo >= 14 || margin > 4.0 * room_diag + 8.0) {
             oc::set_error("GCFM step: no self-consistent candidate search (displacement %g m, %d candidates)", margin * 0.5, cap);
             return OC_ERR_ARG;
+        }
+        if ((pinned[1] & 6) == 4 && margin < DISP_MARGIN && cap == CAND_CAP) {
+            // only the SMALL margin of the fast path was exceeded: redo on the fast path with the full DISP_MARGIN, and
+            // keep that margin for the next steps (a crowd that kicks an agent > margin/2 once tends to do it again)
+            double disp;
+            memcpy(&disp, pinned + 4, sizeof(double));
+            if (disp == disp && disp <= 0.45 * DISP_MARGIN) {
+                margin = DISP_MARGIN;
+                ctx->gcfm_margin_hold = 64;
+                const bool split = ctx->gcfm_split != 0;
+                const int tag = gcfm_sweep_attempt(ctx, L, st, margin, false, false, split);
+                if (tag < 0) return tag;
+                int rc = gcfm_launch_sweep(ctx, L, st, tag, margin, CAND_CAP, false, split);
+                if (rc) return rc;
+                if (timed) OC_CUDA(cudaEventRecord(ctx->ev1, st));
+                OC_CUDA(cudaStreamSynchronize(st));
+                ctx->gcfm_redos = redo + 1;
+                continue;
+            }
         }
         if (pinned[1] & 4) {
             double disp;
@@ -1306,18 +1798,19 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         const oc_gcfm_params *prm = prms[m];
         const int N = Ns[m];
         OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
-        const double reach = prm->cutoff + DISP_MARGIN, inv_cs = 2.0 / reach;
+        const double margin = gcfm_fast_margin(ctx);
+        const double reach = prm->cutoff + margin, inv_cs = 2.0 / reach;
         const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
                   nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
-        const int nbins = nbx * nby;
+        const int nbins = nbx * nby, nbins_alloc = gcfm_max_bins(ctx, prm->cutoff);
         int n_doors = 0;
         for (int k = 0; k < n_keys[m]; k++) n_doors += keys[m][k].n_doors;
         if (!ctx->gcfm_last) ctx->gcfm_last = new GcfmLaunch();
         GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
         int *pinned = nullptr;
-        int rc = gcfm_workspace(ctx, N, n_keys[m], n_doors, nbins, L.w, &pinned, st);
+        int rc = gcfm_workspace(ctx, N, n_keys[m], n_doors, nbins_alloc, L.w, &pinned, st);
         if (rc) return rc;
-        L.prm = *prm; L.N = N; L.n_keys = n_keys[m]; L.n_doors = n_doors; L.nbins_alloc = nbins;
+        L.prm = *prm; L.N = N; L.n_keys = n_keys[m]; L.n_doors = n_doors; L.nbins_alloc = nbins_alloc; L.margin = margin;
         L.x = x[m]; L.y = y[m]; L.vx = vx[m]; L.vy = vy[m]; L.tim = tim[m]; L.status = status[m]; L.vdes = vdes[m];
         L.key = key[m]; L.pinned = pinned;
         // target-set descriptors: uploaded only when they changed (a re-solve changes nt_opt)
@@ -1349,7 +1842,7 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         r.prm = *prm; r.w = L.w; r.x = x[m]; r.y = y[m]; r.vx = vx[m]; r.vy = vy[m]; r.tim = tim[m]; r.status = status[m];
         r.vdes = vdes[m]; r.X = ctx->d_X; r.Y = ctx->d_Y; r.key = key[m]; r.out = pinned; r.N = N;
         r.simu_step = simu_step[m]; r.tag = ctx->gcfm_tag; r.nbx = nbx; r.nby = nby; r.nbins = nbins; r.inv_cs = inv_cs;
-        r.poll_ns = (unsigned)ctx->gcfm_poll_ns;
+        r.poll_ns = (unsigned)ctx->gcfm_poll_ns; r.fov_cull = ctx->gcfm_fov_cull; r.margin = margin;
         max_bins = std::max(max_bins, nbins);
         ctx->gcfm_stream = st;
         ctx->gcfm_pending = true;
@@ -1378,13 +1871,31 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
     const int ctas = std::max(1, std::min(sweep_ctas > 0 ? sweep_ctas : 8, (max_N + SWEEP_WARPS - 1) / SWEEP_WARPS));
     clear_multi_kernel<<<dim3(std::max(1, std::min(8, (std::max(max_N, max_bins) + 255) / 256)), n), 256, 0, st>>>(recs_dev);
     setup_multi_kernel<<<dim3(nb, n), 256, 0, st>>>(recs_dev);
+    cudaStream_t side = st;
+    {
+        int rc = gcfm_fork(c0, st, &side);
+        if (rc) return rc;
+    }
+    if (c0->gcfm_ws_pair) wall_search_multi_kernel<true><<<dim3((max_N * 32 + 127) / 128, n), 128, 0, side>>>(recs_dev);
+    else wall_search_multi_kernel<false><<<dim3((max_N * 32 + 127) / 128, n), 128, 0, side>>>(recs_dev);
+    agent_terms_multi_kernel<<<dim3(nb * 2, n), 128, 0, side>>>(recs_dev);
     scan_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
     scatter_multi_kernel<<<dim3(nb, n), 256, 0, st>>>(recs_dev);
+    const bool split = c0->gcfm_split != 0;
+    if (split) {
+        OC_CUDA(cudaFuncSetAttribute(cand_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+        OC_CUDA(cudaFuncSetAttribute(chain_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+        cand_multi_kernel<<<dim3((max_N + SWEEP_WARPS - 1) / SWEEP_WARPS, n), SWEEP_WARPS * 32, CAND_SMEM, st>>>(recs_dev);
+    }
     noise_index_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
-    prepare_multi_kernel<<<dim3((max_N * 32 + 127) / 128, n), 128, 0, st>>>(recs_dev);
-    sweep_multi_kernel<<<dim3(ctas, n), SWEEP_WARPS * 32, SWEEP_SMEM, st>>>(recs_dev);
+    {
+        int rc = gcfm_join(c0, st, side);
+        if (rc) return rc;
+    }
+    if (split) chain_multi_kernel<<<dim3(ctas, n), SWEEP_WARPS * 32, CHAIN_SMEM, st>>>(recs_dev);
+    else sweep_multi_kernel<<<dim3(ctas, n), SWEEP_WARPS * 32, SWEEP_SMEM, st>>>(recs_dev);
     exit_compact_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
-    oc::count_launch(8);
+    oc::count_launch(split ? 10 : 9);
     OC_CUDA(cudaGetLastError());
     OC_CUDA(cudaEventRecord(c0->ev1, st));
     return OC_OK;

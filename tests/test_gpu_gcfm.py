@@ -431,15 +431,21 @@ def _run_both(ctx, co, prm, P, kdev, kcpu, cpu, vdes, steps, rng):
     return redos
 
 
-def test_dense_jam_more_than_512_candidates_is_exact(cfg):
+@pytest.mark.parametrize("wide", [True, False])
+def test_dense_jam_more_than_512_candidates_is_exact(cfg, wide):
     """8 ped/m^2: more agents within cutoff + 1 m of one agent than the shared-memory lists hold.  The reference has no
     such limit (simulations.py:285-295 visits all pairs); the step is redone on the exact slow path (global-memory
-    candidate lists) and must equal the sequential CPU sweep bit for bit."""
+    candidate lists) and must equal the sequential CPU sweep bit for bit.  wide: the round-1 candidate search (1 m
+    displacement margin, no field-of-view culling), which overflows the lists on every step; otherwise the default
+    search (0.25 m margin, candidates that cannot enter the field of view dropped), which mostly fits them."""
     from oracle import cpu_oracle as co
     from optimal_crowds_b200 import _lib
     L = H = 12.0
     rng = np.random.RandomState(8)
     ctx = _lib.Context(L, H, 0.05)
+    if wide:
+        ctx.set_int("gcfm_margin_mm", 1000)
+        ctx.set_int("gcfm_fov_cull", 0)
     prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
     P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
     kdev, kcpu = _one_key_room(ctx, co, L, H, 6)
@@ -450,8 +456,60 @@ def test_dense_jam_more_than_512_candidates_is_exact(cfg):
     cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=rng.normal(0, 0.4, N), vy=rng.normal(0, 0.4, N),
                time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
     redos = _run_both(ctx, co, prm, P, kdev, kcpu, cpu, rng.normal(1.34, 0.26, N), 3, rng)
-    assert redos >= 3          # every step overflowed the fast path and was redone
-    assert ctx.gcfm_last_pairs() > 100000
+    if wide:
+        assert redos >= 3          # every step overflowed the fast path and was redone
+        assert ctx.gcfm_last_pairs() > 100000
+    ctx.close()
+
+
+@pytest.mark.parametrize("knobs", [dict(gcfm_fov_cull=0), dict(gcfm_margin_mm=1000), dict(gcfm_margin_mm=60),
+                                   dict(gcfm_overlap=0, gcfm_ws_pair=0)])
+def test_candidate_search_variants_are_exact(cfg, knobs):
+    """the pruning of the candidate search (small displacement margin with a fast redo on the full one, field-of-view
+    culling) and the side-stream overlap change no bit: 700 agents at 3.5 ped/m^2, 6 steps, against the sequential sweep"""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    L, H = 16.0, 12.5
+    rng = np.random.RandomState(21)
+    ctx = _lib.Context(L, H, 0.05)
+    for k, v in knobs.items():
+        ctx.set_int(k, v)
+    prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    kdev, kcpu = _one_key_room(ctx, co, L, H, 6)
+    pos = _random_crowd(rng, 700, L, H, margin=0.6, min_dist=0.25)
+    pos = pos[np.hypot(pos[:, 0] - L / 2, pos[:, 1] - H / 2) > 0.7]
+    N = len(pos)
+    vx, vy = rng.normal(0, 0.7, N), rng.normal(0, 0.7, N)
+    vx[:5] = 0.0
+    vy[:5] = 0.0                                   # agents at rest: k = 0 whatever the neighbour does
+    cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=vx, vy=vy, time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    redos = _run_both(ctx, co, prm, P, kdev, kcpu, cpu, rng.normal(1.34, 0.26, N), 6, rng)
+    if knobs.get("gcfm_margin_mm") == 60:
+        assert redos >= 1                          # 3 cm per axis is exceeded at once: redone on the full margin
+    ctx.close()
+
+
+def test_small_margin_overflow_is_redone_on_the_fast_path(cfg):
+    """agents moving 0.16 .. 0.28 m per step exceed the default 0.25 m margin (12.5 cm per axis) but not the full one:
+    the step is redone with the 1 m margin, which is then kept for the following steps (no further redo)."""
+    from oracle import cpu_oracle as co
+    from optimal_crowds_b200 import _lib
+    L, H = 30.0, 20.0
+    rng = np.random.RandomState(5)
+    ctx = _lib.Context(L, H, 0.05)
+    prm = _lib.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    P = co.gcfm_params(cfg, L, H, ctx.Ny, ctx.Nx)
+    kdev, kcpu = _one_key_room(ctx, co, L, H, 8)
+    pos = _random_crowd(rng, 400, L, H, margin=2.0)
+    pos = pos[np.hypot(pos[:, 0] - L / 2, pos[:, 1] - H / 2) > 1.0]
+    N = len(pos)
+    vx, vy = rng.normal(0, 0.5, N), rng.normal(0, 0.5, N)
+    fast = rng.choice(N, 10, replace=False)
+    vx[fast] = rng.choice([-1, 1], 10) * rng.uniform(8, 14, 10)
+    cpu = dict(x=pos[:, 0].copy(), y=pos[:, 1].copy(), vx=vx, vy=vy, time=np.zeros(N), status=np.ones(N, dtype=np.uint8))
+    redos = _run_both(ctx, co, prm, P, kdev, kcpu, cpu, rng.normal(1.34, 0.26, N), 4, rng)
+    assert 1 <= redos <= 2     # (the speed clip brings the fast agents back to v_max after their first step)
     ctx.close()
 
 
