@@ -208,6 +208,10 @@ class Context:
                                 float(room_height), _hp(self.X), _hp(self.Y), C.byref(h)))
         self.h = h
         self.torch_device = torch.device("cuda", self.device)
+        # development aid: OC_KNOBS="gcfm_graph=0,gcfm_split=0" presets oc_ctx_set_int options of every context
+        for kv in filter(None, os.environ.get("OC_KNOBS", "").split(",")):
+            k, v = kv.split("=")
+            self.set_int(k.strip(), int(v))
 
     def set_int(self, key: str, value: int):
         check(load().oc_ctx_set_int(self.h, key.encode(), int(value)))

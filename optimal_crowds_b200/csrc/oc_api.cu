@@ -88,6 +88,10 @@ extern "C" int oc_ctx_set_int(oc_ctx *ctx, const char *key, int value) {
         ctx->gcfm_split = value != 0;
         return OC_OK;
     }
+    if (!strcmp(key, "gcfm_graph")) {
+        ctx->gcfm_use_graph = value != 0;
+        return OC_OK;
+    }
     if (!strcmp(key, "gcfm_overlap")) {
         ctx->gcfm_overlap = value != 0;
         return OC_OK;
@@ -119,9 +123,14 @@ extern "C" void oc_ctx_destroy(oc_ctx *c) {
     if (c->batch_pinned) cudaFreeHost(c->batch_pinned);
     for (auto s : c->batch_streams) cudaStreamDestroy(s);
     for (auto e : c->batch_events) cudaEventDestroy(e);
+    if (c->gcfm_graph) cudaGraphExecDestroy(c->gcfm_graph);
     if (c->gcfm_side) cudaStreamDestroy(c->gcfm_side);
+    if (c->gcfm_side2) cudaStreamDestroy(c->gcfm_side2);
+    if (c->gcfm_cap) cudaStreamDestroy(c->gcfm_cap);
     if (c->gcfm_ev_fork) cudaEventDestroy(c->gcfm_ev_fork);
     if (c->gcfm_ev_join) cudaEventDestroy(c->gcfm_ev_join);
+    if (c->gcfm_ev_join2) cudaEventDestroy(c->gcfm_ev_join2);
+    if (c->gcfm_stage) cudaFreeHost(c->gcfm_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;

@@ -60,8 +60,15 @@ struct oc_ctx {
     int gcfm_overlap = 1;      // oc_ctx_set_int("gcfm_overlap"): wall search / sampler on a side stream next to the cell list
     int gcfm_ws_pair = 1;      // oc_ctx_set_int("gcfm_ws_pair"): wall search scans two tiles per memory round trip
     int gcfm_split = 1;        // oc_ctx_set_int("gcfm_split"): two-kernel sweep (candidate lists, then the dependency chain)
-    cudaStream_t gcfm_side = nullptr;
-    cudaEvent_t gcfm_ev_fork = nullptr, gcfm_ev_join = nullptr;
+    int gcfm_use_graph = 1;    // oc_ctx_set_int("gcfm_graph"): replay the step's launches as one CUDA graph
+    cudaStream_t gcfm_side = nullptr, gcfm_side2 = nullptr, gcfm_cap = nullptr;  // side streams of a step, capture stream
+    cudaEvent_t gcfm_ev_fork = nullptr, gcfm_ev_join = nullptr, gcfm_ev_join2 = nullptr;
+    void *gcfm_stage = nullptr;       // pinned staging of one step's header (tag, simu_step), permutation and normal pairs
+    size_t gcfm_stage_bytes = 0;
+    cudaGraphExec_t gcfm_graph = nullptr;  // the captured fast attempt of a step ...
+    std::vector<char> gcfm_graph_key;      // ... and everything its nodes depend on (pointers, sizes, margin, options)
+    int gcfm_graph_launches = 0;           // kernels per replay (launch counter)
+    int gcfm_grid_chain = 0, gcfm_grid_sweep = 0, gcfm_grid_sweep_slow = 0;  // resident grids of the sweep kernels on this device
     // in-kernel final reduction of the fused step (oc_hjb_fused.cuh): ticket counters on the device, results in
     // mapped page-locked host memory (slot b: value at [2b], sequence number at [2b+1])
     unsigned *fr_ticket = nullptr;

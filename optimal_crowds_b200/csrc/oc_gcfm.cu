@@ -64,6 +64,9 @@ struct Ws {  // device workspace carved out of ctx->gcfm_ws
     // LIST_CAP entries; (candidates, of which later in the sweep); (|v|, a_i, b_i, beta_i) of pedestrians.py:242-243,267
     int2 *lst, *lhdr;
     double4 *ell;
+    // [0] done-flag generation (tag) of the attempt [1] simu_step; uploaded in front of perm / noise in one copy, so that a
+    // captured graph of the step has no per-step kernel arguments
+    int *hdr;
     double *time0;   // per-agent clock at step start (restored when a step is redone on the exact slow path)
     KeyDev *keys;
     // [0] ticket [1] flags: bit0 sampler range, bit1 list overflow, bit2 displacement > margin [2] interacting pairs
@@ -1168,15 +1171,15 @@ wall_search_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X, 
 }
 __global__ void __launch_bounds__(128) agent_terms_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ X,
                                                           const double *__restrict__ Y, const double *__restrict__ vdes,
-                                                          const int *__restrict__ key_id, int simu_step) {
-    agent_terms_body(p, N, w, X, Y, vdes, key_id, simu_step);
+                                                          const int *__restrict__ key_id) {
+    agent_terms_body(p, N, w, X, Y, vdes, key_id, w.hdr[1]);
 }
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
              double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
-             const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, double inv_cs, int nbx, int nby,
+             const double *__restrict__ vdes, const int *__restrict__ key_id, double inv_cs, int nbx, int nby,
              unsigned poll_ns, double margin, int cap, unsigned char *glists, int fov_cull) {
-    sweep_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, inv_cs, nbx, nby, poll_ns, margin, cap, glists,
+    sweep_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, w.hdr[0], inv_cs, nbx, nby, poll_ns, margin, cap, glists,
                fov_cull);
 }
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
@@ -1187,8 +1190,8 @@ cand_kernel(oc_gcfm_params p, int N, Ws w, const double *__restrict__ vdes, doub
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 chain_kernel(oc_gcfm_params p, int N, Ws w, double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
              double *__restrict__ vy, double *__restrict__ tim, uint8_t *__restrict__ status,
-             const double *__restrict__ vdes, const int *__restrict__ key_id, int tag, unsigned poll_ns, double margin) {
-    chain_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, tag, poll_ns, margin);
+             const double *__restrict__ vdes, const int *__restrict__ key_id, unsigned poll_ns, double margin) {
+    chain_body(p, N, w, x, y, vx, vy, tim, status, vdes, key_id, w.hdr[0], poll_ns, margin);
 }
 __global__ void __launch_bounds__(1024) exit_compact_kernel(int N, Ws w, int *__restrict__ out) {
     exit_compact_body(N, w, out);
@@ -1379,6 +1382,7 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     al(N);
     al(sizeof(KeyDev) * std::max(n_keys, 1));
     al(sizeof(int) * 8);
+    al(sizeof(int) * 16);
     al(sizeof(int2) * N);
     al(sizeof(double4) * N);
     al(sizeof(int2) * (size_t)N * LIST_CAP);
@@ -1391,8 +1395,10 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
         // against kernels of a non-blocking stream (ensembles step every member on its own stream)
         OC_CUDA(cudaMemsetAsync(ctx->gcfm_ws, 0, need, st));
         ctx->gcfm_ws_bytes = need;
+        ctx->gcfm_keys_dev = nullptr;  // the cached key descriptors are gone
     } else if (ctx->gcfm_N != N || ctx->gcfm_nbins != nbins || ctx->gcfm_nkeys != n_keys || ctx->gcfm_ndoors != n_doors) {
         OC_CUDA(cudaMemsetAsync(ctx->gcfm_ws, 0, ctx->gcfm_ws_bytes, st));  // layout changes: done-flags must restart at 0
+        ctx->gcfm_keys_dev = nullptr;
     }
     ctx->gcfm_N = N; ctx->gcfm_nbins = nbins; ctx->gcfm_nkeys = n_keys; ctx->gcfm_ndoors = n_doors;
     char *p = (char *)ctx->gcfm_ws;
@@ -1406,14 +1412,17 @@ static int gcfm_workspace(oc_ctx *ctx, int N, int n_keys, int n_doors, int nbins
     w.des_x = carve<double>(p, N); w.des_y = carve<double>(p, N); w.wfx = carve<double>(p, N); w.wfy = carve<double>(p, N);
     w.time0 = carve<double>(p, N);
     w.wall_ind = carve<long long>(p, N);
+    w.hdr = carve<int>(p, 16);   // hdr | perm | noise: one host-to-device copy per step (gcfm_stage mirrors the layout)
+    w.perm = carve<int>(p, N);
     w.noise = carve<double>(p, 2 * (size_t)N);
     w.doors = carve<double>(p, 4 * (size_t)std::max(n_doors, 1));
-    w.perm = carve<int>(p, N); w.rank = carve<int>(p, N); w.nzidx = carve<int>(p, N);
-    w.exit_mark = carve<int>(p, N); w.agent_bin = carve<int>(p, N); w.cell_agents = carve<int>(p, N);
+    w.rank = carve<int>(p, N); w.nzidx = carve<int>(p, N);
+    w.agent_bin = carve<int>(p, N); w.cell_agents = carve<int>(p, N);
+    w.counters = carve<int>(p, 8);   // counters | bin_start | bin_cursor | exit_mark: one memset per attempt
     w.bin_start = carve<int>(p, nbins + 1); w.bin_cursor = carve<int>(p, nbins + 1);
+    w.exit_mark = carve<int>(p, N);
     w.status0 = carve<uint8_t>(p, N);
     w.keys = carve<KeyDev>(p, std::max(n_keys, 1));
-    w.counters = carve<int>(p, 8);
     w.lhdr = carve<int2>(p, N);
     w.ell = carve<double4>(p, N);
     w.lst = carve<int2>(p, (size_t)N * LIST_CAP);
@@ -1459,32 +1468,67 @@ int gcfm_max_bins(const oc_ctx *ctx, double cutoff, int *nbx_out = nullptr, int 
     return nbx * nby;
 }
 
-// fork / join of the side stream that runs the per-agent terms (wall search, sampler, wall force: they only need the
-// step-start snapshot) next to the cell-list kernels of the main stream
-int gcfm_fork(oc_ctx *ctx, cudaStream_t st, cudaStream_t *side) {
-    *side = st;
-    if (!ctx->gcfm_overlap) return OC_OK;
-    if (!ctx->gcfm_side) {
-        OC_CUDA(cudaStreamCreateWithFlags(&ctx->gcfm_side, cudaStreamNonBlocking));
-        OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_fork, cudaEventDisableTiming));
-        OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_join, cudaEventDisableTiming));
-    }
-    OC_CUDA(cudaEventRecord(ctx->gcfm_ev_fork, st));
-    OC_CUDA(cudaStreamWaitEvent(ctx->gcfm_side, ctx->gcfm_ev_fork, 0));
-    *side = ctx->gcfm_side;
+// side streams of a step: the per-agent terms (wall search, sampler, wall force) and the noise index only need the
+// step-start snapshot and run next to the cell-list / candidate-list kernels of the main stream
+int gcfm_streams(oc_ctx *ctx) {
+    if (ctx->gcfm_side) return OC_OK;
+    OC_CUDA(cudaStreamCreateWithFlags(&ctx->gcfm_side, cudaStreamNonBlocking));
+    OC_CUDA(cudaStreamCreateWithFlags(&ctx->gcfm_side2, cudaStreamNonBlocking));
+    OC_CUDA(cudaStreamCreateWithFlags(&ctx->gcfm_cap, cudaStreamNonBlocking));
+    OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_fork, cudaEventDisableTiming));
+    OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_join, cudaEventDisableTiming));
+    OC_CUDA(cudaEventCreateWithFlags(&ctx->gcfm_ev_join2, cudaEventDisableTiming));
     return OC_OK;
 }
-int gcfm_join(oc_ctx *ctx, cudaStream_t st, cudaStream_t side) {
+int gcfm_fork(oc_ctx *ctx, cudaStream_t st, cudaStream_t *side, cudaStream_t *side2) {
+    *side = *side2 = st;
+    if (!ctx->gcfm_overlap) return OC_OK;
+    int rc = gcfm_streams(ctx);
+    if (rc) return rc;
+    OC_CUDA(cudaEventRecord(ctx->gcfm_ev_fork, st));
+    OC_CUDA(cudaStreamWaitEvent(ctx->gcfm_side, ctx->gcfm_ev_fork, 0));
+    OC_CUDA(cudaStreamWaitEvent(ctx->gcfm_side2, ctx->gcfm_ev_fork, 0));
+    *side = ctx->gcfm_side;
+    *side2 = ctx->gcfm_side2;
+    return OC_OK;
+}
+int gcfm_join(oc_ctx *ctx, cudaStream_t st, cudaStream_t side, cudaStream_t side2) {
     if (side == st) return OC_OK;
     OC_CUDA(cudaEventRecord(ctx->gcfm_ev_join, side));
+    OC_CUDA(cudaEventRecord(ctx->gcfm_ev_join2, side2));
     OC_CUDA(cudaStreamWaitEvent(st, ctx->gcfm_ev_join, 0));
+    OC_CUDA(cudaStreamWaitEvent(st, ctx->gcfm_ev_join2, 0));
     return OC_OK;
 }
 
-// bins + cell list of one attempt of the current step; returns the attempt's done-flag generation (tag) or an error.
-// margin: displacement (2 x per axis) the candidate search allows for.  first = false: the state is restored first.
-int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, bool first, bool terms = false,
-                       bool split = false) {
+// per device and context, once: dynamic shared memory limits and the resident grids of the sweep kernels (kept out of
+// the per-step path, and out of stream capture)
+int gcfm_device_setup(oc_ctx *ctx) {
+    if (ctx->gcfm_grid_chain) return OC_OK;
+    int n_sm = 0, occ = 0;
+    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    OC_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    OC_CUDA(cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+    OC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, SWEEP_SMEM));
+    ctx->gcfm_grid_sweep = n_sm * std::max(occ, 1);
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, 0));
+    ctx->gcfm_grid_sweep_slow = n_sm * std::max(occ, 1);
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chain_kernel, SWEEP_WARPS * 32, CHAIN_SMEM));
+    ctx->gcfm_grid_chain = n_sm * std::max(occ, 1);
+    return OC_OK;
+}
+
+int gcfm_next_tag(oc_ctx *ctx) {  // per context: the done-flags live in the context's workspace
+    if (++ctx->gcfm_tag >= 0x3fffffff) ctx->gcfm_tag = 1;
+    return ctx->gcfm_tag;
+}
+
+// bins + cell list (+ the candidate lists of the two-kernel sweep) of one attempt of the current step.
+// margin: displacement (2 x per axis) the candidate search allows for.  first = true: the step's first attempt (the done-flag
+// generation and simu_step are already in w.hdr, uploaded with perm / noise; the per-agent terms run on the side streams);
+// first = false: the state is restored, a new generation is uploaded, the per-agent terms are kept.
+int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, bool first, bool split) {
     const int N = L.N;
     Ws &w = L.w;
     const double reach = L.prm.cutoff + margin;
@@ -1495,41 +1539,44 @@ int gcfm_sweep_attempt(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margi
     if (nbins > L.nbins_alloc) { oc::set_error("internal: GCFM bin table too small"); return OC_ERR_ARG; }
     const int nb = (N + 255) / 256;
     if (!first) {
+        if (!ctx->gcfm_stage) {  // (a member of a batched step: its first attempt was staged by the batch)
+            OC_CUDA(cudaMallocHost(&ctx->gcfm_stage, 64));
+            ctx->gcfm_stage_bytes = 64;
+        }
+        int *hs = static_cast<int *>(ctx->gcfm_stage);  // (the previous attempt has been synchronised: the staging is free)
+        hs[1] = L.simu_step;
+        hs[0] = gcfm_next_tag(ctx);
+        OC_CUDA(cudaMemcpyAsync(w.hdr, hs, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
         restore_kernel<<<nb, 256, 0, st>>>(N, w, L.x, L.y, L.vx, L.vy, L.tim, L.status);
         oc::count_launch();
     }
-    OC_CUDA(cudaMemsetAsync(w.bin_start, 0, sizeof(int) * (nbins + 1), st));
-    OC_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int) * (nbins + 1), st));
-    OC_CUDA(cudaMemsetAsync(w.exit_mark, 0, sizeof(int) * N, st));
-    if (first) OC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * 8, st));  // (a redo resets them in restore_kernel)
-    if (++ctx->gcfm_tag >= 0x3fffffff) ctx->gcfm_tag = 1;  // per context: the done-flags live in the context's workspace
-    const int tag = ctx->gcfm_tag;
+    // counters | bin_start | bin_cursor | exit_mark are carved back to back (a redo resets the counters in restore_kernel)
+    char *z0 = reinterpret_cast<char *>(first ? w.counters : w.bin_start);
+    OC_CUDA(cudaMemsetAsync(z0, 0, reinterpret_cast<char *>(w.exit_mark + N) - z0, st));
     setup_kernel<<<nb, 256, 0, st>>>(N, L.x, L.y, L.vx, L.vy, L.tim, L.status, w, inv_cs, nbx, nby);
-    cudaStream_t side = st;
-    if (terms) {  // per-agent terms of the step (not repeated by a redo: they depend on the step-start state only)
-        int rc = gcfm_fork(ctx, st, &side);
+    cudaStream_t side = st, side2 = st;
+    if (first) {  // per-agent terms of the step (not repeated by a redo: they depend on the step-start state only)
+        int rc = gcfm_fork(ctx, st, &side, &side2);
         if (rc) return rc;
         if (ctx->gcfm_ws_pair) wall_search_kernel<true><<<(N * 32 + 127) / 128, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.key);
         else wall_search_kernel<false><<<(N * 32 + 127) / 128, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.key);
-        agent_terms_kernel<<<nb * 2, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.vdes, L.key, L.simu_step);
-        oc::count_launch(2);
+        agent_terms_kernel<<<nb * 2, 128, 0, side>>>(L.prm, N, w, ctx->d_X, ctx->d_Y, L.vdes, L.key);
+        noise_index_kernel<<<1, 1024, 0, side2>>>(N, w);
+        oc::count_launch(3);
     }
     scan_kernel<<<1, 1024, 0, st>>>(w.bin_start, nbins + 1);
     scatter_kernel<<<nb, 256, 0, st>>>(N, w);
     oc::count_launch(3);
     if (split) {  // two-kernel sweep: candidate lists of all agents, next to the wall search on the side stream
-        OC_CUDA(cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
         cand_kernel<<<(N + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, CAND_SMEM, st>>>(L.prm, N, w, L.vdes, inv_cs, nbx, nby,
                                                                                              margin, ctx->gcfm_fov_cull);
         oc::count_launch();
     }
-    if (terms) {
-        noise_index_kernel<<<1, 1024, 0, st>>>(N, w);
-        oc::count_launch();
-        int rc = gcfm_join(ctx, st, side);
+    if (first) {
+        int rc = gcfm_join(ctx, st, side, side2);
         if (rc) return rc;
     }
-    return tag;
+    return OC_OK;
 }
 }  // namespace
 
@@ -1543,19 +1590,23 @@ extern "C" int oc_gcfm_step(oc_ctx *ctx, const oc_gcfm_params *prm, int N, doubl
     return oc_gcfm_step_finish(ctx, exit_log, n_exit);
 }
 
-// the sweep launch of one attempt (fast: shared-memory lists of CAND_CAP slots; slow: global-memory lists of `cap` slots)
-static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int tag, double margin, int cap, bool slow,
-                             bool split = false) {
+// the sweep launch of one attempt.  fast + split: the chain kernel of the two-kernel sweep (cand_kernel ran in
+// gcfm_sweep_attempt); fast: one-kernel sweep with shared-memory lists of CAND_CAP slots; slow: one-kernel sweep with
+// global-memory lists of `cap` slots
+static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, double margin, int cap, bool slow, bool split) {
     const int N = L.N;
-    if (split && !slow) {  // the chain kernel of the two-kernel sweep (cand_kernel ran in gcfm_sweep_attempt)
-        int n_sm = 0, occ = 0;
-        OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-        OC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
-        OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chain_kernel, SWEEP_WARPS * 32, CHAIN_SMEM));
-        int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
-        if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
-        chain_kernel<<<grid, SWEEP_WARPS * 32, CHAIN_SMEM, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes,
-                                                                L.key, tag, (unsigned)ctx->gcfm_poll_ns, margin);
+    const int want = (N + SWEEP_WARPS - 1) / SWEEP_WARPS;
+    // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
+    // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
+    // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
+    auto capped = [&](int resident) {
+        int g = std::max(1, std::min(resident, want));
+        if (ctx->gcfm_sweep_ctas > 0) g = std::min(g, ctx->gcfm_sweep_ctas);
+        return g;
+    };
+    if (split && !slow) {
+        chain_kernel<<<capped(ctx->gcfm_grid_chain), SWEEP_WARPS * 32, CHAIN_SMEM, st>>>(
+            L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes, L.key, (unsigned)ctx->gcfm_poll_ns, margin);
         exit_compact_kernel<<<1, 1024, 0, st>>>(N, L.w, L.pinned);
         oc::count_launch(2);
         OC_CUDA(cudaGetLastError());
@@ -1564,17 +1615,8 @@ static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int ta
     const double reach = L.prm.cutoff + margin, inv_cs = 2.0 / reach;
     const int nbx = std::max(1, (int)std::ceil(ctx->room_length * inv_cs)),
               nby = std::max(1, (int)std::ceil(ctx->room_height * inv_cs));
-    int n_sm = 0, occ = 0;
-    OC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-    // per device, so set on every launch path (a second context on another GPU of the same process needs it too)
-    OC_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
     const size_t smem = slow ? 0 : SWEEP_SMEM;
-    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, SWEEP_WARPS * 32, smem));
-    int grid = std::max(1, std::min(n_sm * std::max(occ, 1), (N + SWEEP_WARPS - 1) / SWEEP_WARPS));
-    // ensembles: many small crowds sweep concurrently, each with far fewer runnable agents than the GPU has warp slots
-    // (the sweep's dependency DAG is ~200 deep for 1000 agents at 2.5 ped/m^2); a capped grid lets them share the SMs.
-    // Tickets are drawn in sweep order by resident warps only, so any grid size >= 1 is deadlock-free.
-    if (ctx->gcfm_sweep_ctas > 0) grid = std::min(grid, ctx->gcfm_sweep_ctas);
+    int grid = capped(slow ? ctx->gcfm_grid_sweep_slow : ctx->gcfm_grid_sweep);
     unsigned char *glists = nullptr;
     if (slow) {
         const size_t per_warp = (size_t)cap * SWEEP_SLOT_BYTES;
@@ -1593,13 +1635,32 @@ static int gcfm_launch_sweep(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, int ta
         }
         glists = (unsigned char *)ctx->gcfm_glist;
     }
-    sweep_kernel<<<grid, SWEEP_WARPS * 32, smem, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes, L.key, tag,
+    sweep_kernel<<<grid, SWEEP_WARPS * 32, smem, st>>>(L.prm, N, L.w, L.x, L.y, L.vx, L.vy, L.tim, L.status, L.vdes, L.key,
                                                       inv_cs, nbx, nby, (unsigned)ctx->gcfm_poll_ns, margin, cap, glists,
                                                       ctx->gcfm_fov_cull);
     exit_compact_kernel<<<1, 1024, 0, st>>>(N, L.w, L.pinned);
     oc::count_launch(2);
     OC_CUDA(cudaGetLastError());
     return OC_OK;
+}
+
+// everything the first (fast) attempt of a step enqueues after the key descriptors: the staged header / permutation /
+// normal pairs in one copy, bins, cell list, per-agent terms, candidate lists, sweep, exit log.  Run directly, or captured
+// once into a CUDA graph and replayed (the step is ~13 launches of 3-150 us: enqueueing them costs the host more than
+// the small ones take to run)
+static int gcfm_enqueue_first(oc_ctx *ctx, GcfmLaunch &L, cudaStream_t st, size_t stage_bytes, bool split, bool dist) {
+    Ws &w = L.w;
+    OC_CUDA(cudaMemcpyAsync(w.hdr, ctx->gcfm_stage, stage_bytes, cudaMemcpyHostToDevice, st));
+    int rc = gcfm_sweep_attempt(ctx, L, st, L.margin, true, split);
+    if (rc) return rc;
+    if (dist) {
+        // merge the per-agent terms over the ranks: des_x, des_y, wfx, wfy are carved back to back (padding is zero),
+        // every agent was written by exactly one rank and is all-zero bits elsewhere; the sampler-range flag likewise
+        const size_t words = (size_t)((w.wfy + L.N) - w.des_x);
+        if ((rc = oc_dist_allreduce_max_u64(ctx, w.des_x, words, st))) return rc;
+        if ((rc = oc_dist_allreduce_max_u64(ctx, w.counters, 4, st))) return rc;  // 8 ints
+    }
+    return gcfm_launch_sweep(ctx, L, st, L.margin, CAND_CAP, false, split);
 }
 
 extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y,
@@ -1610,8 +1671,11 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
            "NULL argument");
     OC_ARG(N >= 1 && n_keys >= 1 && n_noise >= 0 && n_noise <= N, "bad sizes");
     OC_ARG(prm->Ny == ctx->Ny && prm->Nx == ctx->Nx, "params grid != context grid");
+    OC_ARG(!ctx->gcfm_pending, "the previous GCFM step has not been finished (oc_gcfm_step_finish)");
     OC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = gcfm_device_setup(ctx);
+    if (rc) return rc;
     // the bin table is sized for the smallest cells any attempt uses (a wider margin means larger cells, i.e. fewer bins)
     const int nbins = gcfm_max_bins(ctx, prm->cutoff);
     int n_doors = 0;
@@ -1620,46 +1684,105 @@ extern "C" int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N
     GcfmLaunch &L = *static_cast<GcfmLaunch *>(ctx->gcfm_last);
     Ws &w = L.w;
     int *pinned = nullptr;
-    int rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned, st);
+    rc = gcfm_workspace(ctx, N, n_keys, n_doors, nbins, w, &pinned, st);
     if (rc) return rc;
     L.prm = *prm; L.N = N; L.n_keys = n_keys; L.n_doors = n_doors; L.nbins_alloc = nbins;
     L.x = d_x; L.y = d_y; L.vx = d_vx; L.vy = d_vy; L.tim = d_time; L.status = d_status; L.vdes = d_vdes; L.key = d_key;
     L.pinned = pinned;
-    // upload keys, doors, perm, noise
-    std::vector<KeyDev> hk(n_keys);
-    std::vector<double> hd(4 * (size_t)std::max(n_doors, 1));
-    int off = 0;
-    for (int k = 0; k < n_keys; k++) {
-        OC_ARG(keys[k].d_V && keys[k].d_wall_tiles, "key without potential / wall tiles");
-        OC_ARG(!keys[k].d_vx == !keys[k].d_vy, "d_vx and d_vy must be given together");
-        hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy,
-                       keys[k].d_vx ? nullptr : keys[k].d_phi, keys[k].nt_opt, keys[k].d_vx ? keys[k].n_slices : 0, off,
-                       keys[k].n_doors, (keys[k].d_vx || !keys[k].d_phi) ? 0 : keys[k].n_phi, keys[k].v_min * 10e3,
-                       keys[k].mu, keys[k].lim, keys[k].phi_row0, keys[k].phi_rows};
-        OC_ARG(keys[k].phi_rows >= 0 && (keys[k].phi_rows == 0 || !keys[k].d_vx), "row-band storage needs phi samples");
-        for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
-        off += keys[k].n_doors;
+    // target-set descriptors (KeyDev records + door rectangles): uploaded only when they changed (a re-solve changes nt_opt)
+    std::vector<char> sig(sizeof(KeyDev) * n_keys + sizeof(double) * 4 * std::max(n_doors, 1), 0);
+    {
+        KeyDev *hk = reinterpret_cast<KeyDev *>(sig.data());
+        double *hd = reinterpret_cast<double *>(sig.data() + sizeof(KeyDev) * n_keys);
+        int off = 0;
+        for (int k = 0; k < n_keys; k++) {
+            OC_ARG(keys[k].d_V && keys[k].d_wall_tiles, "key without potential / wall tiles");
+            OC_ARG(!keys[k].d_vx == !keys[k].d_vy, "d_vx and d_vy must be given together");
+            hk[k] = KeyDev{keys[k].d_V, keys[k].d_wall_tiles, keys[k].d_vx, keys[k].d_vy,
+                           keys[k].d_vx ? nullptr : keys[k].d_phi, keys[k].nt_opt, keys[k].d_vx ? keys[k].n_slices : 0, off,
+                           keys[k].n_doors, (keys[k].d_vx || !keys[k].d_phi) ? 0 : keys[k].n_phi, keys[k].v_min * 10e3,
+                           keys[k].mu, keys[k].lim, keys[k].phi_row0, keys[k].phi_rows};
+            OC_ARG(keys[k].phi_rows >= 0 && (keys[k].phi_rows == 0 || !keys[k].d_vx), "row-band storage needs phi samples");
+            for (int d = 0; d < 4 * keys[k].n_doors; d++) hd[4 * (size_t)off + d] = keys[k].doors[d];
+            off += keys[k].n_doors;
+        }
     }
     OC_CUDA(cudaEventRecord(ctx->ev0, st));
-    OC_CUDA(cudaMemcpyAsync(w.keys, hk.data(), sizeof(KeyDev) * n_keys, cudaMemcpyHostToDevice, st));
-    OC_CUDA(cudaMemcpyAsync(w.doors, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
-    OC_CUDA(cudaMemcpyAsync(w.perm, perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
-    if (n_noise) OC_CUDA(cudaMemcpyAsync(w.noise, noise, sizeof(double) * 2 * n_noise, cudaMemcpyHostToDevice, st));
+    if (ctx->gcfm_keys_sig != sig || ctx->gcfm_keys_dev != (void *)w.keys) {
+        ctx->gcfm_keys_sig = sig;  // the vector stays alive: pageable source of the asynchronous copies below
+        ctx->gcfm_keys_dev = (void *)w.keys;
+        OC_CUDA(cudaMemcpyAsync(w.keys, ctx->gcfm_keys_sig.data(), sizeof(KeyDev) * n_keys, cudaMemcpyHostToDevice, st));
+        OC_CUDA(cudaMemcpyAsync(w.doors, ctx->gcfm_keys_sig.data() + sizeof(KeyDev) * n_keys,
+                                sizeof(double) * 4 * std::max(n_doors, 1), cudaMemcpyHostToDevice, st));
+    }
     L.margin = gcfm_fast_margin(ctx);
     L.simu_step = simu_step;
-    const bool split = ctx->gcfm_split != 0;
-    const int tag = gcfm_sweep_attempt(ctx, L, st, L.margin, true, true, split);
-    if (tag < 0) return tag;
-    if ((prm->own1 > prm->own0 || prm->key_mod > 0) && ctx->nccl_comm && ctx->nranks > 1) {
-        // merge the per-agent terms over the ranks: des_x, des_y, wfx, wfy are carved back to back (padding is zero),
-        // every agent was written by exactly one rank and is all-zero bits elsewhere; the sampler-range flag likewise
-        const size_t words = (size_t)((w.wfy + N) - w.des_x);
-        if ((rc = oc_dist_allreduce_max_u64(ctx, w.des_x, words, st))) return rc;
-        if ((rc = oc_dist_allreduce_max_u64(ctx, w.counters, 4, st))) return rc;  // 8 ints
+    // staging: header, permutation, normal pairs, laid out like w.hdr .. w.noise
+    const size_t off_perm = (size_t)(reinterpret_cast<char *>(w.perm) - reinterpret_cast<char *>(w.hdr)),
+                 off_noise = (size_t)(reinterpret_cast<char *>(w.noise) - reinterpret_cast<char *>(w.hdr));
+    const size_t stage_full = off_noise + sizeof(double) * 2 * (size_t)N;
+    if (ctx->gcfm_stage_bytes < stage_full) {
+        if (ctx->gcfm_stage) cudaFreeHost(ctx->gcfm_stage);
+        ctx->gcfm_stage = nullptr; ctx->gcfm_stage_bytes = 0;
+        OC_CUDA(cudaMallocHost(&ctx->gcfm_stage, stage_full));
+        memset(ctx->gcfm_stage, 0, stage_full);
+        ctx->gcfm_stage_bytes = stage_full;
     }
-    if ((rc = gcfm_launch_sweep(ctx, L, st, tag, L.margin, CAND_CAP, false, split))) return rc;
+    {
+        char *hs = static_cast<char *>(ctx->gcfm_stage);
+        int *hh = reinterpret_cast<int *>(hs);
+        hh[0] = gcfm_next_tag(ctx);
+        hh[1] = simu_step;
+        memcpy(hs + off_perm, perm, sizeof(int) * (size_t)N);
+        if (n_noise) memcpy(hs + off_noise, noise, sizeof(double) * 2 * (size_t)n_noise);
+    }
+    const bool split = ctx->gcfm_split != 0;
+    const bool dist = (prm->own1 > prm->own0 || prm->key_mod > 0) && ctx->nccl_comm && ctx->nranks > 1;
+    if (ctx->gcfm_use_graph && !dist) {
+        // everything a node of the captured graph depends on
+        struct Key {
+            oc_gcfm_params prm;
+            const void *p[12];
+            int N, n_keys, nbins, knobs[8];
+            double margin;
+            size_t stage;
+        } key;
+        memset(&key, 0, sizeof(key));
+        key.prm = *prm;
+        const void *ptrs[12] = {d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key, ctx->gcfm_ws, pinned, ctx->gcfm_stage, ctx->d_X};
+        memcpy(key.p, ptrs, sizeof(ptrs));
+        key.N = N; key.n_keys = n_keys; key.nbins = nbins;
+        const int knobs[8] = {ctx->gcfm_split, ctx->gcfm_fov_cull, ctx->gcfm_ws_pair, ctx->gcfm_overlap, ctx->gcfm_poll_ns,
+                              ctx->gcfm_sweep_ctas, n_doors, 0};
+        memcpy(key.knobs, knobs, sizeof(knobs));
+        key.margin = L.margin;
+        key.stage = stage_full;
+        std::vector<char> kb(reinterpret_cast<char *>(&key), reinterpret_cast<char *>(&key) + sizeof(key));
+        if (!ctx->gcfm_graph || kb != ctx->gcfm_graph_key) {
+            if (ctx->gcfm_graph) { cudaGraphExecDestroy(ctx->gcfm_graph); ctx->gcfm_graph = nullptr; }
+            if ((rc = gcfm_streams(ctx))) return rc;
+            const long long l0 = oc::g_launches.load();
+            OC_CUDA(cudaStreamBeginCapture(ctx->gcfm_cap, cudaStreamCaptureModeRelaxed));
+            rc = gcfm_enqueue_first(ctx, L, ctx->gcfm_cap, stage_full, split, false);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ctx->gcfm_cap, &g);
+            const int per_replay = (int)(oc::g_launches.load() - l0);
+            oc::g_launches.fetch_add(-per_replay);  // (captured, not launched)
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            OC_CUDA(e);
+            e = cudaGraphInstantiate(&ctx->gcfm_graph, g, 0);
+            cudaGraphDestroy(g);
+            OC_CUDA(e);
+            ctx->gcfm_graph_key = kb;
+            ctx->gcfm_graph_launches = per_replay;
+        }
+        OC_CUDA(cudaGraphLaunch(ctx->gcfm_graph, st));
+        oc::count_launch(ctx->gcfm_graph_launches);
+    } else {
+        const size_t used = off_noise + sizeof(double) * 2 * (size_t)n_noise;
+        if ((rc = gcfm_enqueue_first(ctx, L, st, used, split, dist))) return rc;
+    }
     OC_CUDA(cudaEventRecord(ctx->ev1, st));
-    // hk / hd are pageable: cudaMemcpyAsync has already staged them when it returned
     ctx->gcfm_stream = st;
     ctx->gcfm_pending = true;
     return OC_OK;
@@ -1697,10 +1820,9 @@ static int gcfm_finish_member(oc_ctx *ctx, int *exit_log, int *n_exit, bool sync
                 margin = DISP_MARGIN;
                 ctx->gcfm_margin_hold = 64;
                 const bool split = ctx->gcfm_split != 0;
-                const int tag = gcfm_sweep_attempt(ctx, L, st, margin, false, false, split);
-                if (tag < 0) return tag;
-                int rc = gcfm_launch_sweep(ctx, L, st, tag, margin, CAND_CAP, false, split);
+                int rc = gcfm_sweep_attempt(ctx, L, st, margin, false, split);
                 if (rc) return rc;
+                if ((rc = gcfm_launch_sweep(ctx, L, st, margin, CAND_CAP, false, split))) return rc;
                 if (timed) OC_CUDA(cudaEventRecord(ctx->ev1, st));
                 OC_CUDA(cudaStreamSynchronize(st));
                 ctx->gcfm_redos = redo + 1;
@@ -1724,10 +1846,9 @@ static int gcfm_finish_member(oc_ctx *ctx, int *exit_log, int *n_exit, bool sync
             }
             cap = c2;
         }
-        const int tag = gcfm_sweep_attempt(ctx, L, st, margin, false);
-        if (tag < 0) return tag;
-        int rc = gcfm_launch_sweep(ctx, L, st, tag, margin, cap, true);
+        int rc = gcfm_sweep_attempt(ctx, L, st, margin, false, false);
         if (rc) return rc;
+        if ((rc = gcfm_launch_sweep(ctx, L, st, margin, cap, true, false))) return rc;
         if (timed) OC_CUDA(cudaEventRecord(ctx->ev1, st));
         OC_CUDA(cudaStreamSynchronize(st));
         ctx->gcfm_redos = redo + 1;
@@ -1811,6 +1932,7 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         int rc = gcfm_workspace(ctx, N, n_keys[m], n_doors, nbins_alloc, L.w, &pinned, st);
         if (rc) return rc;
         L.prm = *prm; L.N = N; L.n_keys = n_keys[m]; L.n_doors = n_doors; L.nbins_alloc = nbins_alloc; L.margin = margin;
+        L.simu_step = simu_step[m];
         L.x = x[m]; L.y = y[m]; L.vx = vx[m]; L.vy = vy[m]; L.tim = tim[m]; L.status = status[m]; L.vdes = vdes[m];
         L.key = key[m]; L.pinned = pinned;
         // target-set descriptors: uploaded only when they changed (a re-solve changes nt_opt)
@@ -1871,11 +1993,12 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
     const int ctas = std::max(1, std::min(sweep_ctas > 0 ? sweep_ctas : 8, (max_N + SWEEP_WARPS - 1) / SWEEP_WARPS));
     clear_multi_kernel<<<dim3(std::max(1, std::min(8, (std::max(max_N, max_bins) + 255) / 256)), n), 256, 0, st>>>(recs_dev);
     setup_multi_kernel<<<dim3(nb, n), 256, 0, st>>>(recs_dev);
-    cudaStream_t side = st;
+    cudaStream_t side = st, side2 = st;
     {
-        int rc = gcfm_fork(c0, st, &side);
+        int rc = gcfm_fork(c0, st, &side, &side2);
         if (rc) return rc;
     }
+    noise_index_multi_kernel<<<dim3(1, n), 1024, 0, side2>>>(recs_dev);
     if (c0->gcfm_ws_pair) wall_search_multi_kernel<true><<<dim3((max_N * 32 + 127) / 128, n), 128, 0, side>>>(recs_dev);
     else wall_search_multi_kernel<false><<<dim3((max_N * 32 + 127) / 128, n), 128, 0, side>>>(recs_dev);
     agent_terms_multi_kernel<<<dim3(nb * 2, n), 128, 0, side>>>(recs_dev);
@@ -1887,9 +2010,8 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         OC_CUDA(cudaFuncSetAttribute(chain_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
         cand_multi_kernel<<<dim3((max_N + SWEEP_WARPS - 1) / SWEEP_WARPS, n), SWEEP_WARPS * 32, CAND_SMEM, st>>>(recs_dev);
     }
-    noise_index_multi_kernel<<<dim3(1, n), 1024, 0, st>>>(recs_dev);
     {
-        int rc = gcfm_join(c0, st, side);
+        int rc = gcfm_join(c0, st, side, side2);
         if (rc) return rc;
     }
     if (split) chain_multi_kernel<<<dim3(ctas, n), SWEEP_WARPS * 32, CHAIN_SMEM, st>>>(recs_dev);
