@@ -228,7 +228,10 @@ class ensemble:
                 for o in s.targets.values():
                     o.d_phi = o.d_vx = o.d_vy = None
                 s._ctx.close()
+                s.__dict__.clear()   # marshalled key descriptors, state tensors, agents <-> simulation reference cycles
             del sims
+            import gc
+            gc.collect()             # (a wave holds tens of GB of field samples: do not wait for the cyclic collector)
             torch.cuda.empty_cache()
 
     def run(self, gather=True):
