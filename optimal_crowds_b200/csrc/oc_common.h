@@ -52,7 +52,7 @@ struct oc_ctx {
     void *gcfm_keys_dev = nullptr;    //   and where they were uploaded to
     void *multi_pinned = nullptr, *multi_dev = nullptr;  // batched step: staging arena (perm, noise, member records)
     size_t multi_bytes = 0;
-    int gcfm_poll_ns = 20;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
+    int gcfm_poll_ns = 100;    // oc_ctx_set_int("gcfm_poll_ns"): back-off between polls of a neighbour's done-flag
     int gcfm_sweep_ctas = 0;  // oc_ctx_set_int("gcfm_sweep_ctas"): cap of the sweep grid (0 = fill the GPU)
     int gcfm_margin_mm = 250;  // oc_ctx_set_int("gcfm_margin_mm"): displacement margin (2 x per-axis bound) of the fast attempt
     int gcfm_margin_hold = 0;  // steps left on the full margin after a step that exceeded the small one

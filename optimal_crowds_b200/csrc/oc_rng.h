@@ -11,9 +11,104 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace ocrng {
+
+// Persistent helper threads for the Box-Muller transform of gauss_fill.  The rejection loop that advances the generator
+// is inherently serial; f = sqrt(-2 log(r2) / r2) of the accepted events is not, and costs twice as much.  The producer
+// (the thread inside gauss_fill) publishes how many events it has accepted so far; the helpers -- parked on a condition
+// variable between calls, so that a call costs a wake-up and not a thread creation -- transform blocks of EV_BLOCK events
+// behind it, the producer joins in once the generator is done.  Every value is computed by the same scalar expression
+// whoever evaluates it: the stream is bit-identical to the serial one (tests/test_cpu_host.py).
+// Threads: OC_RNG_THREADS (default: min(3, hardware threads per local process - 2)); 0 = serial.
+class TransformPool {
+  public:
+    static constexpr long long EV_BLOCK = 512;
+    static TransformPool &get() {
+        // never destroyed: the helpers stay parked on the condition variable until the process exits, and destroying a
+        // condition variable with waiters blocks (glibc) -- the process would hang in its static destructors
+        static TransformPool *p = new TransformPool();
+        return *p;
+    }
+    int threads() const { return (int)workers_.size(); }
+    // returns false if the pool is absent or busy (another generator is using it): the caller transforms inline
+    bool begin(const double *X1, const double *X2, const double *R2, double *out, long long idx, long long n, long long n_ev) {
+        if (workers_.empty() || !busy_.try_lock()) return false;
+        X1_ = X1; X2_ = X2; R2_ = R2; out_ = out; idx_ = idx; n_ = n; n_ev_ = n_ev;
+        n_blocks_ = (n_ev + EV_BLOCK - 1) / EV_BLOCK;
+        next_.store(0, std::memory_order_relaxed);
+        done_.store(0, std::memory_order_relaxed);
+        produced_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_++;
+        }
+        cv_.notify_all();
+        return true;
+    }
+    void publish(long long produced) { produced_.store(produced, std::memory_order_release); }
+    void finish() {  // producer: all events are accepted; help, then wait for the helpers' last blocks
+        produced_.store(n_ev_, std::memory_order_release);
+        work();
+        while (done_.load(std::memory_order_acquire) < n_blocks_) std::this_thread::yield();
+        busy_.unlock();
+    }
+
+  private:
+    TransformPool() {
+        int n = -1;
+        if (const char *e = std::getenv("OC_RNG_THREADS")) n = std::atoi(e);
+        if (n < 0) {
+            // leave two cores per process to its main thread and the look-ahead thread that calls gauss_fill; under
+            // torchrun (LOCAL_WORLD_SIZE processes share the host) the cores are divided first
+            int procs = 1;
+            if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) procs = std::max(1, std::atoi(e));
+            n = std::max(0, std::min(3, (int)std::thread::hardware_concurrency() / procs - 2));
+        }
+        for (int t = 0; t < n; t++) workers_.emplace_back([this] { loop(); });
+        for (auto &w : workers_) w.detach();  // parked for the life of the process
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return job_ != seen; });
+                seen = job_;
+            }
+            work();
+        }
+    }
+    void work() {
+        for (;;) {
+            const long long b = next_.fetch_add(1, std::memory_order_relaxed);
+            if (b >= n_blocks_) return;
+            const long long e0 = b * EV_BLOCK, e1 = std::min(n_ev_, e0 + EV_BLOCK);
+            while (produced_.load(std::memory_order_acquire) < e1) std::this_thread::yield();
+            for (long long e = e0; e < e1; e++) {
+                const double f = std::sqrt(-2.0 * std::log(R2_[e]) / R2_[e]);
+                out_[idx_ + 2 * e] = f * X2_[e];
+                if (idx_ + 2 * e + 1 < n_) out_[idx_ + 2 * e + 1] = f * X1_[e];
+            }
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, busy_;
+    std::condition_variable cv_;
+    unsigned long long job_ = 0;
+    const double *X1_ = nullptr, *X2_ = nullptr, *R2_ = nullptr;
+    double *out_ = nullptr;
+    long long idx_ = 0, n_ = 0, n_ev_ = 0, n_blocks_ = 0;
+    std::atomic<long long> next_{0}, done_{0}, produced_{0};
+};
+
 
 struct Mt {
     uint32_t *key;   // 624 words (np.random.get_state()[1]), advanced in place
@@ -37,14 +132,25 @@ struct Mt {
         key[623] = key[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MAT);
         pos = 0;
     }
+    // tempered copy of key[from .. 624): the output transform of a whole block in one vectorisable loop instead of word
+    // by word (the serial generator is what bounds a step's draw: 5 words per agent)
+    uint32_t tb[624];
+    bool tb_valid = false;
+    void temper_block(int from) {
+        for (int i = from; i < 624; i++) {
+            uint32_t y = key[i];
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            tb[i] = y;
+        }
+        tb_valid = true;
+    }
     uint32_t next32() {
-        if (pos == 624) gen();
-        uint32_t y = key[pos++];
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        return y;
+        if (pos == 624) { gen(); temper_block(0); }
+        else if (!tb_valid) temper_block(pos);
+        return tb[pos++];
     }
     double next_double() {
         const int32_t a = next32() >> 5, b = next32() >> 6;
@@ -111,6 +217,10 @@ struct Mt {
         long long first_ck_ev = n_ev;
         for (int q = 0; q < n_ckpt; q++)
             if (ev_of[q] >= 0) first_ck_ev = std::min(first_ck_ev, ev_of[q]);
+        // the transform runs behind the generator on the pool's helper threads (large draws only: a wake-up costs ~30 us)
+        TransformPool *pool = nullptr;
+        if (n_ev >= 8 * TransformPool::EV_BLOCK && TransformPool::get().begin(X1.data(), X2.data(), R2.data(), out, idx, n, n_ev))
+            pool = &TransformPool::get();
         for (long long e = 0; e < n_ev; e++) {
             double x1, x2, r2;
             do {
@@ -119,16 +229,19 @@ struct Mt {
                 r2 = x1 * x1 + x2 * x2;
             } while (r2 >= 1.0 || r2 == 0.0);
             X1[e] = x1; X2[e] = x2; R2[e] = r2;
+            if (pool && ((e + 1) & (TransformPool::EV_BLOCK - 1)) == 0) pool->publish(e + 1);
             if (e >= first_ck_ev)   // the snapshots sit at the last n_ckpt events
                 for (int q = 0; q < n_ckpt; q++)
                     if (ev_of[q] == e) snap(q);
         }
-        // the transform, one event at a time (measured: helper threads / OpenMP teams cost more per call than the ~0.3 ms
-        // they could save at 12.5 k pairs; the run loop overlaps this whole function with the GPU step instead)
-        for (long long e = 0; e < n_ev; e++) {
-            const double f = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]);
-            out[idx + 2 * e] = f * X2[e];
-            if (idx + 2 * e + 1 < n) out[idx + 2 * e + 1] = f * X1[e];
+        if (pool) {
+            pool->finish();
+        } else {
+            for (long long e = 0; e < n_ev; e++) {
+                const double f = std::sqrt(-2.0 * std::log(R2[e]) / R2[e]);
+                out[idx + 2 * e] = f * X2[e];
+                if (idx + 2 * e + 1 < n) out[idx + 2 * e + 1] = f * X1[e];
+            }
         }
         // cache flag / value as they are after v values (v = n for the generator itself, n - 2q for the snapshots)
         auto cached_after = [&](long long v, int *has, double *cv) {

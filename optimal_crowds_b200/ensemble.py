@@ -18,6 +18,7 @@ i % world, no data-path collective) and, inside a batch, run concurrently on one
 from __future__ import annotations
 
 import contextlib
+import os
 import io
 
 import numpy as np
@@ -38,6 +39,9 @@ def field_bytes_per_member(Ny: int, Nx: int, T: float, dt: float, n_keys: int = 
     n = Ny * Nx
     field = nt * n * 8 if field_storage == "phi" else 2 * max(nt - 1, 0) * (Ny - 2) * (Nx - 2) * 8
     return n_keys * (field + 2 * n * 8) + 6 * n * 8
+
+
+_SOLVER_CTX = {}   # (device, room size, grid step) -> Context owning the batched-solve workspace
 
 
 def plan_waves(members, bytes_per_member: int, budget_bytes: int, max_wave: int = 256):
@@ -97,15 +101,44 @@ class ensemble:
 
     # ---------------------------------------------------------------------------------------------
     def _build(self, idx):
-        with contextlib.redirect_stdout(io.StringIO()):
-            return simulations.simulation(self.rooms[idx], self.T, recompute=self.recompute, record=self.record,
-                                          field_storage=self.field_storage, fused=1, lookahead=False,
-                                          rng=np.random.RandomState(self.seeds[idx]), chunk_rows=self.chunk_rows)
+        return simulations.simulation(self.rooms[idx], self.T, recompute=self.recompute, record=self.record,
+                                      field_storage=self.field_storage, fused=1, lookahead=False,
+                                      rng=np.random.RandomState(self.seeds[idx]), chunk_rows=self.chunk_rows)
+
+    def _build_wave(self, wave):
+        """the members of a wave, constructed by a few host threads: a member's crowd placement (oc_place_box: sequential
+        rejection sampling on the member's own RandomState, ~5 ms per 1000 agents), rasterisation and allocations are
+        independent of the other members', and the C calls release the GIL"""
+        n_thr = int(os.environ.get("OC_ENSEMBLE_BUILD_THREADS", "8"))
+        with contextlib.redirect_stdout(io.StringIO()):   # (one redirection around the pool: sys.stdout is process-wide)
+            if n_thr <= 1 or len(wave) < 4:
+                return [self._build(i) for i in wave]
+            from concurrent.futures import ThreadPoolExecutor
+            import torch
+            dev = torch.cuda.current_device()
+
+            def build(i):
+                torch.cuda.set_device(dev)
+                return self._build(i)
+            with ThreadPoolExecutor(max_workers=n_thr, thread_name_prefix="oc-build") as ex:
+                return list(ex.map(build, wave))
+
+    def _solver_ctx(self, first):
+        """the context whose batch workspace (5 arrays per room, 32 streams, one event and one result slot per room) the
+        batched solves of this process use: kept across waves and ensembles of the same grid, so that a wave does not
+        pay ~50 ms of allocations in front of a ~40 ms solve"""
+        import torch
+        key = (torch.cuda.current_device(), first.room_length, first.room_height, first._ctx.dx)
+        ctx = _SOLVER_CTX.get(key)
+        if ctx is None or not getattr(ctx, "h", None):
+            ctx = _SOLVER_CTX[key] = _lib.Context(first.room_length, first.room_height, first._ctx.dx)
+        return ctx
 
     def _solve_wave(self, sims):
         """simulation._solve_all for every member of the wave in one batched call per target set"""
         import torch
         first = sims[0]
+        sctx = self._solver_ctx(first)
         d_ms = None
         if first.simu_step > 0:
             d_ms = [s._density_device(s.sigma_convolution) for s in sims]
@@ -124,13 +157,16 @@ class ensemble:
                 # GPU; 64 rooms side by side fill it with 64-row chunks and recompute far fewer halo rows).  The chunking
                 # fixes the error-norm summation order: a stand-alone run reproduces a member bit for bit when it is
                 # given the same chunk_rows (ensemble.chunk_rows_used).
-                self.chunk_rows_used = first._ctx.plan_chunk_rows(len(sims))
+                self.chunk_rows_used = sctx.plan_chunk_rows(len(sims))
                 prm.chunk_rows = self.chunk_rows_used
             vel = self.field_storage == "velocity"
-            res = first._ctx.hjb_solve_batch([o.d_V for o in opts], d_ms, prm, self.T, nt,
+            import time as _t
+            _t0 = _t.perf_counter()
+            res = sctx.hjb_solve_batch([o.d_V for o in opts], d_ms, prm, self.T, nt,
                                              out_phi=None if vel else [o.d_phi for o in opts],
                                              out_vx=[o.d_vx for o in opts] if vel else None,
                                              out_vy=[o.d_vy for o in opts] if vel else None)
+            self.stats["hjb_call_ms"] = self.stats.get("hjb_call_ms", 0.0) + (_t.perf_counter() - _t0) * 1e3
             for o, r, s in zip(opts, res, sims):
                 o.t, o.nt_opt, o.last_stats = s.time, nt, r["stats"]
                 o._h_vx = o._h_vy = None
@@ -144,7 +180,7 @@ class ensemble:
         import time
         import torch
         t0 = time.perf_counter()
-        sims = [self._build(i) for i in wave]
+        sims = self._build_wave(wave)
         shape = {(s.Ny, s.Nx, tuple(s.targets)) for s in sims}
         if len({sh[:2] for sh in shape}) != 1 or len({len(sh[2]) for sh in shape}) != 1:
             raise ValueError("ensemble members must share the grid shape and the number of target sets")
@@ -169,7 +205,7 @@ class ensemble:
                 s._cuda_stream = main
             # a room's sweep is a dependency chain with ~5 agents runnable at a time (1000 agents, depth ~200): a few warps per
             # room suffice, and every CTA slot given to one room is a slot another room of the wave cannot use
-            ctas_b = self.sweep_ctas or max(2, min(8, (n_sm * 4) // len(sims)))
+            ctas_b = self.sweep_ctas or int(os.environ.get("OC_ENSEMBLE_CTAS", "0")) or max(2, min(8, (n_sm * 4) // len(sims)))
             batch = _lib.GcfmBatch([dict(ctx=s._ctx, prm=s._gcfm_prm, state=s._state, vdes=s._d_vdes, key_id=s._d_key,
                                          keys=s._keys(), rng=s._np_random) for s in sims], sweep_ctas=ctas_b)
         while live:

@@ -338,9 +338,10 @@ class simulation:
             # np.random.choice(np.arange(N), N, replace=False) (simulations.py:271) and one normal pair per active
             # agent in sweep order == N calls of normal(size=2) (simulations.py:303)
             perm, noise = self._rng.draw(self.N, n_active)
+            # next step's draws on the helper thread, while this thread enqueues the step and the GPU sweeps
+            self._rng.lookahead(self.N, n_active)
             pending = self._ctx.gcfm_step_launch(prm, self._state, self._d_vdes, self._d_key, self._keys(), perm,
                                                  noise, self.simu_step, stream=self._cuda_stream)
-            self._rng.lookahead(self.N, n_active)   # next step's draws while the GPU sweeps
         return dt, pending
 
     def _step_finish(self, launched, verbose=False):

@@ -233,7 +233,7 @@ def run_ensemble(args, world, rank, local_rank):
         for k in ("hjb_ms", "gcfm_ms", "build_ms", "agent_steps", "cell_updates"):
             acc[k] += ens.stats[k]
         acc["wall_ms"] += wall
-        note("pass: " + ", ".join(f"{k} {ens.stats[k]:.0f}" for k in ("build_ms", "hjb_ms", "gcfm_ms", "launch_ms", "finish_ms"))
+        note("pass: " + ", ".join(f"{k} {ens.stats[k]:.0f}" for k in ("build_ms", "hjb_ms", "hjb_call_ms", "gcfm_ms", "launch_ms", "finish_ms"))
              + f", wall {wall:.0f} ms")
     barrier()
     total_ms = (time.perf_counter() - t0) * 1e3
