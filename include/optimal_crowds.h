@@ -276,6 +276,21 @@ int oc_gcfm_step_launch(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d
                         int simu_step, void *stream);
 int oc_gcfm_step_finish(oc_ctx *ctx, int *exit_log, int *n_exit);
 
+/* The body of simulations.run()'s loop (simulations.py:427-441: history row, step; the periodic re-solve stays with the
+ * caller) for up to n_steps consecutive steps in one call.  Per step the permutation and the normal pairs are drawn in C
+ * from the caller's legacy MT19937 state (np.random.get_state()[1:5]: mt_key 624 words, *mt_pos, *has_gauss,
+ * *cached_gauss; advanced in place exactly as the reference's draws would), with the next step's draws made while the
+ * GPU runs the current one (speculation on "nobody leaves" + generator snapshots, see oc_rng.h).  n_active0: agents
+ * inside at the start; d_rows (nullable): n_steps device pointers, d_rows[k] receives the packed state after step k
+ * (oc_state_pack).  Stops early when nobody is inside.  exit_agent / exit_step (host, capacity N): agents in exit order
+ * and the step (0-based within the call) they left in; *steps_done: steps executed; *device_ms: sum of their CUDA-event
+ * times; *pairs: interacting pairs.  Returns OC_ERR_SAMPLER_RANGE like oc_gcfm_step (the offending step counts). */
+int oc_gcfm_run(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx, double *d_vy,
+                double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key, const oc_key *keys, int n_keys,
+                uint32_t *mt_key, int *mt_pos, int *has_gauss, double *cached_gauss, int n_steps, int simu_step0,
+                int n_active0, double *const *d_rows, int *exit_agent, int *exit_step, int *n_exits, int *steps_done,
+                double *device_ms, long long *pairs, void *stream);
+
 /* Batched step for ensembles of independent rooms (BASELINE configs[4]): ONE launch per kernel for all n members
  * (blockIdx.y = member) instead of 7 launches per member, and the members' per-step randomness drawn in C from their own
  * legacy MT19937 states (mt_key[m]: 624 words; mt_pos, has_gauss, cached_gauss: arrays of n = get_state()[2:5]; all

@@ -83,7 +83,7 @@ EXPORTS = ["oc_abi_version", "oc_last_error", "oc_launch_count", "oc_ctx_create"
            "oc_hjb_solve", "oc_hjb_rhs", "oc_hjb_vels", "oc_wall_tiles_bytes", "oc_wall_tiles", "oc_gcfm_step",
            "oc_wall_force", "oc_pair_force", "oc_density", "oc_gcfm_last_ms", "oc_dist_unique_id", "oc_dist_init",
            "oc_dist_finalize", "oc_dist_p2p_export", "oc_dist_p2p_import", "oc_dist_p2p_enabled", "oc_dist_p2p_disable", "oc_hjb_solve_band", "oc_rasterise_band", "oc_upload", "oc_hjb_solve_batch", "oc_gcfm_step_launch",
-           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows", "oc_rng_step_draw", "oc_rng_step_draw_ckpt", "oc_gcfm_step_multi_launch", "oc_gcfm_step_multi_finish"]
+           "oc_gcfm_step_finish", "oc_gcfm_last_pairs", "oc_gcfm_last_redos", "oc_state_pack", "oc_fp64_peak", "oc_place_box", "oc_hjb_plan_chunk_rows", "oc_rng_step_draw", "oc_rng_step_draw_ckpt", "oc_gcfm_step_multi_launch", "oc_gcfm_step_multi_finish", "oc_gcfm_run"]
 
 
 def load():
@@ -110,6 +110,9 @@ def load():
     lib.oc_gcfm_step_multi_launch.argtypes = [C.c_int, vpp_, vpp_, ip] + [vpp_] * 9 + [ip, vpp_, ip, ip, dp, ip, ip,
                                                                                      C.c_int, C.c_void_p]
     lib.oc_gcfm_step_multi_finish.argtypes = [C.c_int, vpp_, vpp_, ip, ip]
+    lib.oc_gcfm_run.argtypes = [C.c_void_p, C.POINTER(GcfmParams), C.c_int] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int,
+                                C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, C.c_int, vpp_, ip, ip, ip, ip, dp,
+                                C.POINTER(C.c_longlong), C.c_void_p]
     lib.oc_rng_step_draw.argtypes = [C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, ip, dp]
     lib.oc_rng_step_draw_ckpt.argtypes = [C.POINTER(C.c_uint32), ip, ip, dp, C.c_int, C.c_int, ip, dp, C.c_int,
                                           C.POINTER(C.c_uint32), ip, ip, dp]
@@ -451,6 +454,34 @@ class Context:
         rc = load().oc_gcfm_step_finish(self.h, exit_log.ctypes.data_as(ip), C.byref(n_exit))
         check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
         return exit_log[: n_exit.value].copy(), rc
+
+    def gcfm_run(self, prm: GcfmParams, state, vdes, key_id, keys, rng_state, n_steps, simu_step0, n_active, rows=None,
+                 stream=None):
+        """up to n_steps steps of the run loop in one call (oc_gcfm_run): randomness drawn in C from the legacy MT19937
+        state tuple `rng_state` (np.random.get_state()), next step's draws overlapped with the GPU.  rows: optional list of
+        n_steps (N,4) CUDA tensors receiving the packed state after each step.  Returns dict(steps, exits (agent ids in
+        exit order), exit_step (0-based step within the call), rc, rng_state (to be set_state()d), device_ms, pairs)."""
+        N = state["x"].numel()
+        karr, keep = keys if isinstance(keys, tuple) else self.make_keys(keys)
+        key = np.ascontiguousarray(rng_state[1], dtype=np.uint32).copy()
+        pos, has, cached = C.c_int(int(rng_state[2])), C.c_int(int(rng_state[3])), C.c_double(float(rng_state[4]))
+        rows_arr = None
+        if rows is not None:
+            rows_arr = (C.c_void_p * n_steps)()
+            for q, r in enumerate(rows):
+                assert r.is_cuda and r.is_contiguous() and r.numel() == 4 * N
+                rows_arr[q] = r.data_ptr()
+        ex_a, ex_s = np.empty(max(N, 1), dtype=np.int32), np.empty(max(N, 1), dtype=np.int32)
+        n_ex, done, ms, pairs = C.c_int(), C.c_int(), C.c_double(), C.c_longlong()
+        rc = load().oc_gcfm_run(self.h, C.byref(prm), N, _dev(state["x"]), _dev(state["y"]), _dev(state["vx"]),
+                                _dev(state["vy"]), _dev(state["time"]), _dev(state["status"]), _dev(vdes), _dev(key_id), karr,
+                                len(karr), key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(has),
+                                C.byref(cached), int(n_steps), int(simu_step0), int(n_active), rows_arr,
+                                ex_a.ctypes.data_as(ip), ex_s.ctypes.data_as(ip), C.byref(n_ex), C.byref(done), C.byref(ms),
+                                C.byref(pairs), _stream() if stream is None else C.c_void_p(stream))
+        check(rc, allow=(OC_ERR_SAMPLER_RANGE,))
+        return dict(steps=done.value, exits=ex_a[: n_ex.value].copy(), exit_step=ex_s[: n_ex.value].copy(), rc=rc,
+                    rng_state=("MT19937", key, pos.value, has.value, cached.value), device_ms=ms.value, pairs=pairs.value)
 
     def gcfm_last_ms(self):
         return float(load().oc_gcfm_last_ms(self.h))

@@ -2040,6 +2040,91 @@ extern "C" int oc_gcfm_step_multi_finish(int n, oc_ctx *const *ctxs, int *const 
     return worst;
 }
 
+// ------------------------------------------------------------------------------------------------ run loop
+// Up to n_steps consecutive steps of simulations.run()'s loop body (simulations.py:427-441 minus the periodic re-solve)
+// without returning to the host language between them.  Per step: the permutation and the normal pairs of the agents
+// inside from the caller's legacy MT19937 state (np.random.get_state()[1:5], advanced in place; oc_rng.h), the step,
+// the exit bookkeeping and -- when d_rows is given -- one row of the trajectory record (oc_state_pack into d_rows[k]).
+// While the GPU runs step k this thread draws step k+1's randomness from a COPY of the generator state for the upper
+// bound "nobody leaves", with snapshots of the state after n - q pairs (q < 64): when step k's exit count q is known,
+// the first n - q pairs are exactly the reference's draws and the generator continues from snapshot q; otherwise the
+// step is drawn afresh.  The stream of random numbers is the reference's whatever happens.
+// Stops early when nobody is inside (the reference's loop condition) or on an error; *steps_done steps were executed
+// (on OC_ERR_SAMPLER_RANGE including the offending one, as oc_gcfm_step).  exit_agent / exit_step (capacity N): agents in
+// exit order and the index (0-based within this call) of the step they left in.  *device_ms: sum of the steps' CUDA-event
+// times; *pairs: interacting pairs evaluated.
+extern "C" int oc_gcfm_run(oc_ctx *ctx, const oc_gcfm_params *prm, int N, double *d_x, double *d_y, double *d_vx,
+                           double *d_vy, double *d_time, uint8_t *d_status, const double *d_vdes, const int *d_key,
+                           const oc_key *keys, int n_keys, uint32_t *mt_key, int *mt_pos, int *has_gauss,
+                           double *cached_gauss, int n_steps, int simu_step0, int n_active0, double *const *d_rows,
+                           int *exit_agent, int *exit_step, int *n_exits, int *steps_done, double *device_ms,
+                           long long *pairs, void *stream) {
+    OC_ARG(ctx && prm && mt_key && mt_pos && has_gauss && cached_gauss && exit_agent && exit_step && n_exits && steps_done,
+           "NULL argument");
+    OC_ARG(N >= 1 && n_steps >= 0 && n_active0 >= 0 && n_active0 <= N && *mt_pos >= 0 && *mt_pos <= 624, "bad sizes");
+    constexpr int N_CKPT = 64;
+    *n_exits = 0;
+    *steps_done = 0;
+    if (device_ms) *device_ms = 0.0;
+    if (pairs) *pairs = 0;
+    std::vector<int> perm(N), perm2(N), log_(N);
+    std::vector<double> noise(2 * (size_t)N), noise2(2 * (size_t)N);
+    std::vector<uint32_t> ck_key((size_t)N_CKPT * 624), key2(624);
+    int ck_pos[N_CKPT], ck_has[N_CKPT];
+    double ck_cached[N_CKPT];
+    bool spec = false;   // perm2 / noise2 / snapshots hold a look-ahead draw for n_spec pairs
+    int n_spec = 0, n_ckpt = 0;
+    int n_active = n_active0;
+    int rc = OC_OK;
+    for (int k = 0; k < n_steps && n_active > 0; k++) {
+        // ---- this step's randomness (simulations.py:271,303)
+        const int q = n_spec - n_active;
+        if (spec && q >= 0 && q < n_ckpt) {
+            perm.swap(perm2);
+            noise.swap(noise2);
+            memcpy(mt_key, ck_key.data() + (size_t)624 * q, 624 * sizeof(uint32_t));
+            *mt_pos = ck_pos[q]; *has_gauss = ck_has[q]; *cached_gauss = ck_cached[q];
+        } else {
+            ocrng::Mt mt{mt_key, *mt_pos, *has_gauss, *cached_gauss};
+            mt.permutation(N, perm.data());
+            mt.gauss_fill(noise.data(), 2ll * n_active);
+            *mt_pos = mt.pos; *has_gauss = mt.has_gauss; *cached_gauss = mt.gauss_;
+        }
+        spec = false;
+        rc = oc_gcfm_step_launch(ctx, prm, N, d_x, d_y, d_vx, d_vy, d_time, d_status, d_vdes, d_key, keys, n_keys, perm.data(),
+                                 noise.data(), n_active, simu_step0 + k, stream);
+        if (rc) return rc;
+        // ---- look-ahead: the next step's draws while the GPU sweeps (not after the last step of this call)
+        if (k + 1 < n_steps) {
+            memcpy(key2.data(), mt_key, 624 * sizeof(uint32_t));
+            ocrng::Mt mt2{key2.data(), *mt_pos, *has_gauss, *cached_gauss};
+            mt2.permutation(N, perm2.data());
+            n_spec = n_active;
+            n_ckpt = std::min(N_CKPT, n_spec + 1);
+            mt2.gauss_fill(noise2.data(), 2ll * n_spec, n_ckpt, ck_key.data(), ck_pos, ck_has, ck_cached);
+            spec = true;
+        }
+        int ne = 0;
+        rc = oc_gcfm_step_finish(ctx, log_.data(), &ne);
+        if (rc != OC_OK && rc != OC_ERR_SAMPLER_RANGE) return rc;
+        for (int e = 0; e < ne; e++) {
+            exit_agent[*n_exits] = log_[e];
+            exit_step[*n_exits] = k;
+            (*n_exits)++;
+        }
+        n_active -= ne;
+        if (device_ms) *device_ms += ctx->gcfm_last_ms;
+        if (pairs) *pairs += ctx->gcfm_last_pairs;
+        if (d_rows && d_rows[k]) {
+            int r2 = oc_state_pack(ctx, N, d_x, d_y, d_vx, d_vy, d_rows[k], stream);
+            if (r2) return r2;
+        }
+        (*steps_done)++;
+        if (rc == OC_ERR_SAMPLER_RANGE) return rc;
+    }
+    return OC_OK;
+}
+
 extern "C" double oc_gcfm_last_ms(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_ms : 0.0; }
 extern "C" long long oc_gcfm_last_pairs(oc_ctx *ctx) { return ctx ? ctx->gcfm_last_pairs : 0; }
 extern "C" int oc_gcfm_last_redos(oc_ctx *ctx) { return ctx ? ctx->gcfm_redos : 0; }

@@ -16,6 +16,8 @@ from __future__ import annotations
 import json
 import warnings
 
+import os
+
 import numpy as np
 
 from . import _crowd, _lib, _rng, optimals, pedestrians
@@ -131,6 +133,9 @@ class simulation:
             if field_storage != "phi":
                 raise ValueError("band=True stores the field as phi samples: pass field_storage='phi'")
         self._cuda_stream = None   # raw CUDA stream handle of this simulation's steps (None: torch's current stream)
+        # run() / advance() execute blocks of steps inside one library call (oc_gcfm_run); OC_FAST_RUN=0 keeps the
+        # step-by-step Python loop (same results)
+        self._fast_run = lookahead and os.environ.get("OC_FAST_RUN", "1") != "0"
         self._key_shard = None
         if shard_keys:
             import torch.distributed as tdist
@@ -344,6 +349,57 @@ class simulation:
                                                  noise, self.simu_step, stream=self._cuda_stream)
         return dt, pending
 
+    def advance(self, n_steps, verbose=False):
+        """Up to n_steps iterations of run()'s loop body -- history frame, step -- stopping when nobody is inside; returns
+        the number of steps done.  Plain single-GPU simulations on the legacy MT19937 stream run them inside ONE library
+        call (oc_gcfm_run: randomness drawn in C, the next step's draws overlapped with the GPU, no return to Python
+        between steps); results, RNG stream, history frames and records are those of the step-by-step loop."""
+        n_steps = int(n_steps)
+        fast = (n_steps > 1 and self.N > 0 and not verbose and self._record and not self._band and self._key_shard is None
+                and self._fast_run)
+        st = self._rng.rng.get_state() if fast else None
+        if not fast or st[0] != "MT19937":
+            done = 0
+            while done < n_steps and self.inside > 0:
+                self.write_history(self.time)
+                self.step(self.dt, verbose=verbose)
+                done += 1
+            return done
+        import torch
+        self._rng._spec = None   # (a look-ahead drawn for the step-by-step path is simply not used)
+        # rows of the device-resident record for the steps to come
+        rows = []
+        for k in range(self._n_rows - 1, self._n_rows - 1 + n_steps):
+            blk, off = divmod(k, self.TRACK_CHUNK)
+            while blk >= len(self._d_track):
+                self._d_track.append(torch.empty((self.TRACK_CHUNK, max(self.N, 1), 4), dtype=torch.float64,
+                                                 device=self._ctx.torch_device))
+            rows.append(self._d_track[blk][off])
+        n_active = int(self._h_status.sum())
+        res = self._ctx.gcfm_run(self._gcfm_prm, self._state, self._d_vdes, self._d_key, self._keys(), st, n_steps,
+                                 self.simu_step, n_active, rows=rows, stream=self._cuda_stream)
+        self._rng.rng.set_state(res["rng_state"])
+        self.last_run_stats = dict(steps=res["steps"], device_ms=res["device_ms"], pairs=res["pairs"])
+        ex, exs = res["exits"], res["exit_step"]
+        e = 0
+        for k in range(res["steps"]):
+            self.write_history(self.time)          # lazy frame: a view of record row simu_step
+            while e < len(ex) and exs[e] == k:
+                a = int(ex[e])
+                self._h_status[a] = 0
+                self._exit_step[a] = self.simu_step
+                self._exit_order.append(a)
+                self.inside += -1
+                e += 1
+            self._n_rows += 1
+            self.time += self.dt
+            self.simu_step += 1
+        self._host_dirty = True
+        if res["rc"] == _lib.OC_ERR_SAMPLER_RANGE:
+            raise IndexError("agent position outside the velocity field's index range "
+                             "(numpy raises IndexError in the reference's sampler too: optimals.py:247)")
+        return res["steps"]
+
     def _step_finish(self, launched, verbose=False):
         dt, pending = launched
         if pending is not None:
@@ -393,8 +449,15 @@ class simulation:
             if self.recompute and (self.simu_step % self.recompute_step == 0) and self.simu_step > 0:
                 print(f"Computing trajectories at time {self.time}")
                 self._solve_all()
-            self.write_history(self.time)
-            self.step(self.dt, verbose=verbose)
+            # the iterations up to the next re-solve / drawing / the end of the horizon run as one block (advance)
+            n, t = 0, self.time
+            while t < self.T:
+                t += self.dt
+                n += 1
+                k = self.simu_step + n
+                if (self.recompute and k % self.recompute_step == 0) or (draw and k % 10 == 0):
+                    break
+            self.advance(n, verbose=verbose)
             if draw and (self.simu_step % 10) == 0:
                 import matplotlib.pyplot as plt
                 self.draw(mode)

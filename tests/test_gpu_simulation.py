@@ -346,3 +346,39 @@ def test_c_drawn_and_lookahead_randomness_do_not_change_a_run():
         assert np.array_equal(o[0], outs[0][0])
         assert np.array_equal(o[1][1], outs[0][1][1]) and o[1][2:] == outs[0][1][2:]
     assert outs[2][2] >= 10 and outs[1][2] == 0
+
+
+@pytest.mark.parametrize("recompute", [False, True])
+def test_block_run_equals_step_by_step_run(in_repo_cwd, recompute, monkeypatch):
+    """run() executes blocks of steps inside one library call (simulation.advance -> oc_gcfm_run: randomness drawn in C
+    with in-loop look-ahead, exits and record rows handled in the library) == the step-by-step Python loop
+    (OC_FAST_RUN=0): states, clocks, exit steps and ORDER, trajectories, history frames, printed messages and the
+    generator state afterwards; agents leave during the run, so the look-ahead snapshots are exercised"""
+    from optimal_crowds_b200 import simulations, synthetic
+    room = synthetic.parity_room(1024, 512, 2)     # boxes of agents next to doors: exits from the first second on
+    outs = []
+    for fast in ("1", "0"):
+        monkeypatch.setenv("OC_FAST_RUN", fast)
+        np.random.seed(5)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            s = simulations.simulation(room, 2.6, recompute)
+            if recompute:
+                s.recompute_step = 40
+            s.run()
+        assert s._fast_run == (fast == "1")
+        frames = sorted(s.history)
+        f_mid = s.history[frames[len(frames) // 2]]
+        outs.append(dict(now=np.array(s._h_now), tv=np.array(s._h_timev), order=list(s._exit_order),
+                         estep=s._exit_step.copy(), rng=np.random.get_state(), msg=buf.getvalue(), frames=frames,
+                         traj=[np.array(p.traj) for p in s.agents[:5]], n_mid=len(f_mid) - 1,
+                         mid0=np.array(f_mid[0][0]), time=s.time, steps=s.simu_step, inside=s.inside))
+    a, b = outs
+    assert a["steps"] == b["steps"] and a["time"] == b["time"] and a["inside"] == b["inside"] and a["steps"] > 100
+    assert len(a["order"]) > 3 and a["order"] == b["order"] and np.array_equal(a["estep"], b["estep"])
+    assert np.array_equal(a["now"], b["now"]) and np.array_equal(a["tv"], b["tv"])
+    assert np.array_equal(a["rng"][1], b["rng"][1]) and a["rng"][2:] == b["rng"][2:]
+    assert a["msg"] == b["msg"] and a["frames"] == b["frames"] and a["n_mid"] == b["n_mid"]
+    assert np.array_equal(a["mid0"], b["mid0"])
+    for ta, tb in zip(a["traj"], b["traj"]):
+        assert np.array_equal(ta, tb)
