@@ -435,7 +435,7 @@ def run_slalom(args, world, rank, local_rank):
         ex = simu._exit_step[simu._exit_step >= s0]
         agent_steps = sum(n0 - int((ex < s0 + k).sum()) for k in range(done))
         dev_ms, pairs = simu.last_run_stats["device_ms"], simu.last_run_stats["pairs"]
-        args.gcfm_steps = done
+        args.gcfm_steps = max(done, 1)
     else:
         for _ in range(3):
             simu.step(simu.dt)
@@ -551,7 +551,7 @@ def main():
     ap.add_argument("--band-ny", type=int, default=BAND_NY)
     ap.add_argument("--nx", type=int, default=BAND_NX)
     ap.add_argument("--agents", type=int, default=BAND_AGENTS)
-    ap.add_argument("--gcfm-steps", type=int, default=20)
+    ap.add_argument("--gcfm-steps", type=int, default=50)
     ap.add_argument("--rooms", type=int, default=1024, help="ensemble: members in total (sharded over the GPUs)")
     ap.add_argument("--fused", type=int, default=int(os.environ.get("OC_FUSED", "1")),
                     help="1: stage-fused RK45 step kernel (default), 0: one kernel per RK stage")
