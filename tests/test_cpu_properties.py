@@ -158,3 +158,82 @@ def test_density_equals_numpy_statement(L, H, seed, sigma):
     d[Vg < 0] = 0
     got = co.density(X, Y, Vg, x, y, status, sigma)
     np.testing.assert_allclose(got, d, rtol=2e-15, atol=1e-300)      # own exp: <= 1-2 ulp from numpy's
+
+
+# ---- round 2: the conservative pruning rules of the GCFM candidate search and of the nearest-wall search, restated in
+# numpy (csrc/oc_gcfm.cu: CandSearch::gather, WallSearch::tile_lb).  The kernels are compared with the sequential sweep
+# bit for bit on the GPU box; these check the geometry behind the rules on the whole input space.
+def _fov_cull(vx, vy, ox, oy, margin, cos_fov):
+    """the kernel's predicate: a candidate whose OLD offset from agent i is (ox, oy) cannot enter i's field of view
+    wherever it moves within rho = margin / sqrt(2)"""
+    rho_s = margin * 0.70710678118654757 * (1.0 + 1e-6) + 1e-12
+    sin_fov = np.sqrt(max(1.0 - cos_fov * cos_fov, 0.0))
+    ni = np.sqrt(vy * vy + vx * vx)
+    if ni == 0.0:
+        return True
+    d = np.sqrt(ox * ox + oy * oy)
+    if d == 0.0:
+        return False
+    sn = rho_s / d
+    if not sn < 0.999 * sin_fov:
+        return False
+    cs = np.sqrt(1.0 - sn * sn)
+    cos_lim = cos_fov * cs - sin_fov * sn
+    return (vx * ox + vy * oy) / (ni * d) < cos_lim - 1e-9
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.floats(-2.0, 2.0), st.floats(-2.0, 2.0), st.floats(0.05, 5.0), st.floats(0.0, 2 * np.pi),
+       st.floats(0.0, 1.0), st.floats(0.0, 2 * np.pi), st.sampled_from([0.06, 0.25, 1.0]))
+def test_field_of_view_culling_is_conservative(vx, vy, d, ang, frac, dang, margin):
+    """whenever the rule drops a candidate, the reference's k (pedestrians.py:259-262) is exactly 0 for EVERY position
+    the candidate can reach in the step (displacement <= margin/2 per axis, i.e. <= margin/sqrt(2)), so its force is
+    -+0.0 and skipping it changes no bit of the agent's sum"""
+    cos_fov = np.cos(0.7 * np.pi)
+    ox, oy = d * np.cos(ang), d * np.sin(ang)
+    if not _fov_cull(vx, vy, ox, oy, margin, cos_fov):
+        return
+    rho = margin / np.sqrt(2.0)
+    for f in (frac, 1.0):                       # a random displacement and one on the boundary of the disc
+        Rx, Ry = ox + f * rho * np.cos(dang), oy + f * rho * np.sin(dang)
+        nR = np.sqrt(Ry * Ry + Rx * Rx)
+        ni = np.sqrt(vy * vy + vx * vx)
+        k = 0.0
+        if ni > 0:
+            ex, ey = Rx / nR, Ry / nR
+            k = np.maximum((vx * ex + vy * ey) / ni - cos_fov, 0) / (1 - cos_fov)
+        assert k == 0.0
+
+
+def test_field_of_view_culling_is_not_vacuous():
+    """the rule drops about a quarter of uniformly placed candidates at the default margin (0.7 pi half-angle)"""
+    rng = np.random.RandomState(0)
+    cos_fov = np.cos(0.7 * np.pi)
+    n = hit = 0
+    for _ in range(4000):
+        th, r = rng.uniform(0, 2 * np.pi), 4.2 * np.sqrt(rng.uniform(0.01, 1))
+        hit += _fov_cull(1.2, 0.3, r * np.cos(th), r * np.sin(th), 0.25, cos_fov)
+        n += 1
+    assert 0.2 < hit / n < 0.3
+
+
+@settings(**SET)
+@given(st.floats(3.0, 9.0), st.floats(2.0, 6.0), st.integers(0, 10 ** 6))
+def test_wall_tile_lower_bound_holds_in_floating_point(L, H, seed):
+    """WallSearch::tile_lb: for every node of a 16 x 16 tile the COMPUTED distance sqrt(ddx*ddx + ddy*ddy) is >= the
+    bound sqrt(gx*gx + gy*gy) with gx = max(X[ix0] - x, x - X[ix1], 0) evaluated with the same operations (rounding is
+    monotonic), so a tile whose bound exceeds the best key cannot hold the argmin nor a tie"""
+    X, Y = _grid(L, H)
+    rng = np.random.RandomState(seed)
+    WT = 16
+    for _ in range(20):
+        x, y = rng.uniform(-0.5, L + 0.5), rng.uniform(-0.5, H + 0.5)
+        tx, ty = rng.randint(0, (len(X) + WT - 1) // WT), rng.randint(0, (len(Y) + WT - 1) // WT)
+        ix0, iy0 = tx * WT, ty * WT
+        ix1, iy1 = min(ix0 + WT - 1, len(X) - 1), min(iy0 + WT - 1, len(Y) - 1)
+        gx = max(max(X[ix0] - x, x - X[ix1]), 0.0)
+        gy = max(max(Y[iy0] - y, y - Y[iy1]), 0.0)
+        lb = np.sqrt(gx * gx + gy * gy)
+        ddx = X[ix0:ix1 + 1][None, :] - x
+        ddy = Y[iy0:iy1 + 1][:, None] - y
+        assert (np.sqrt(ddx * ddx + ddy * ddy) >= lb).all()
