@@ -146,7 +146,19 @@ extern "C" int oc_upload(oc_ctx *ctx, const void *host, void *d_dst, long long b
     OC_ARG(ctx && (bytes == 0 || (host && d_dst)) && bytes >= 0, "NULL argument");
     if (bytes == 0) return OC_OK;
     OC_CUDA(cudaSetDevice(ctx->device));
-    OC_CUDA(cudaMemcpyAsync(d_dst, host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    // OC_UPLOAD_CHUNK_MB > 0: the copy is issued in pieces, so that launches of a solve running on another stream can
+    // slip in between them instead of queueing behind one 268 MB transfer (prefetch of the next solve's density)
+    static const long long chunk = [] {
+        const char *e = getenv("OC_UPLOAD_CHUNK_MB");
+        return e ? (long long)atoll(e) << 20 : 0ll;
+    }();
+    if (chunk <= 0 || bytes <= chunk) {
+        OC_CUDA(cudaMemcpyAsync(d_dst, host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        return OC_OK;
+    }
+    for (long long off = 0; off < bytes; off += chunk)
+        OC_CUDA(cudaMemcpyAsync((char *)d_dst + off, (const char *)host + off, (size_t)std::min(chunk, bytes - off),
+                                cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return OC_OK;
 }
 
