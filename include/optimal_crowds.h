@@ -52,9 +52,17 @@ long long oc_launch_count(int reset);
 int oc_ctx_create(int device, int Ny, int Nx, double dx, double dy, double room_length, double room_height,
                   const double *X, const double *Y, oc_ctx **out);
 void oc_ctx_destroy(oc_ctx *ctx);
-/* Integer tuning options of a context.  "gcfm_sweep_ctas": upper bound of the GCFM sweep kernel's grid (0 = fill the
- * GPU, the default); ensembles set it so that the concurrent sweeps of many small crowds share the SMs.  Results do
- * not depend on it. */
+/* Integer tuning options of a context.  No result depends on any of them.
+ *   "gcfm_sweep_ctas"  upper bound of the GCFM sweep kernel's grid (0 = fill the GPU, the default); ensembles set it so
+ *                      that the concurrent sweeps of many small crowds share the SMs
+ *   "gcfm_poll_ns"     back-off between polls of a neighbour's done-flag (default 100)
+ *   "gcfm_margin_mm"   displacement margin (2 x the per-axis bound) of the first attempt of a step, in mm (default 250;
+ *                      a step that exceeds it is redone with 1000, then on the exact slow path)
+ *   "gcfm_fov_cull"    1 (default): candidates that cannot enter the agent's field of view are not waited for
+ *   "gcfm_split"       1 (default): sweep = candidate-list kernel + dependency-chain kernel; 0: one-kernel sweep
+ *   "gcfm_graph"       1 (default): a step's launches are replayed as one CUDA graph
+ *   "gcfm_overlap"     1 (default): wall search / sampler / noise index on side streams next to the cell list
+ *   "gcfm_ws_pair"     1 (default): the wall search scans two tiles per memory round trip */
 int oc_ctx_set_int(oc_ctx *ctx, const char *key, int value);
 
 /* Host -> device copy of a caller-owned input array (e.g. the density `m` that
@@ -313,10 +321,11 @@ double oc_gcfm_last_ms(oc_ctx *ctx);
 /* Interacting pairs of the last step: calls of ped.agents_repulsion the reference would have made
  * (simulations.py:291-295) -- the work unit of the pair-force roofline (bench.py "gcfm.roofline"). */
 long long oc_gcfm_last_pairs(oc_ctx *ctx);
-/* How many times the last step was redone on the exact slow path.  The fast path keeps at most 512 candidates per
- * agent in shared memory and assumes that no agent moves more than 0.5 m per axis in one step; a step that breaks
- * either assumption is restored from its snapshot and redone with global-memory candidate lists and a search
- * radius covering the measured displacement (the reference has neither limit: simulations.py:285-303). */
+/* How many times the last step was redone.  The fast path keeps at most 512 candidates per agent and assumes that no
+ * agent moves more than 12.5 cm per axis in one step; a step that moves an agent further is restored from its snapshot
+ * and redone with a 0.5 m bound, and a step that breaks that bound or the candidate limit is redone with global-memory
+ * candidate lists and a search radius covering the measured displacement, until self-consistent (the reference has
+ * neither limit: simulations.py:285-303). */
 int oc_gcfm_last_redos(oc_ctx *ctx);
 /* Packed copy of the crowd state, d_out (N,4) = x,y,vx,vy (32-byte aligned): one row of the device-resident record
  * behind ped.traj / ped.vels (pedestrians.py:106-110,189-190) and simulation.history (simulations.py:579-589). */

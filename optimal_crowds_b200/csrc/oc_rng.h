@@ -134,7 +134,7 @@ struct Mt {
     }
     // tempered copy of key[from .. 624): the output transform of a whole block in one vectorisable loop instead of word
     // by word (the serial generator is what bounds a step's draw: 5 words per agent)
-    uint32_t tb[624];
+    uint32_t tb[624] = {};
     bool tb_valid = false;
     void temper_block(int from) {
         for (int i = from; i < 624; i++) {
