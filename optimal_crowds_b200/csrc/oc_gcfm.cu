@@ -15,6 +15,7 @@
 // (release/acquire).  A warp only ever waits on lower tickets, which are held by resident warps or
 // finished, so the schedule cannot deadlock.  The pair sum runs in ascending agent index like the
 // reference's `for j in range(N)` loop (simulations.py:287-295).
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <algorithm>
@@ -1891,6 +1892,12 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
     OC_CUDA(cudaSetDevice(c0->device));
     cudaStream_t st = (cudaStream_t)stream;
     // ---- staging arena: per member perm (N ints, padded to 8 bytes) + noise (2 n_active doubles)
+    // OC_DEBUG_TIMING=1: host time of the three parts of a batched launch, printed every 100 calls
+    static const bool dbg_t = getenv("OC_DEBUG_TIMING") != nullptr;
+    static double dbg_acc[3] = {0, 0, 0};
+    static int dbg_n = 0;
+    auto dbg_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double dbg_t0 = dbg_t ? dbg_now() : 0.0;
     std::vector<size_t> off(n + 1, 0);
     int max_N = 0;
     for (int m = 0; m < n; m++) {
@@ -1969,6 +1976,7 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         ctx->gcfm_stream = st;
         ctx->gcfm_pending = true;
     }
+    const double dbg_t1 = dbg_t ? dbg_now() : 0.0;
     {   // the members' streams are independent: draw them in parallel (simulations.py:271,303 per member)
         const int n_thr = std::max(1, std::min({n, 8, (int)std::thread::hardware_concurrency()}));
         auto work = [&](int t) {
@@ -1987,6 +1995,7 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
         work(0);
         for (auto &th : pool) th.join();
     }
+    const double dbg_t2 = dbg_t ? dbg_now() : 0.0;
     OC_CUDA(cudaMemcpyAsync(dp, hp, ((arena + 63) / 64) * 64 + rec_bytes, cudaMemcpyHostToDevice, st));
     OC_CUDA(cudaFuncSetAttribute(sweep_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
     const int nb = (max_N + 255) / 256;
@@ -2020,6 +2029,15 @@ extern "C" int oc_gcfm_step_multi_launch(int n, oc_ctx *const *ctxs, const oc_gc
     oc::count_launch(split ? 10 : 9);
     OC_CUDA(cudaGetLastError());
     OC_CUDA(cudaEventRecord(c0->ev1, st));
+    if (dbg_t) {
+        const double t3 = dbg_now();
+        dbg_acc[0] += dbg_t1 - dbg_t0; dbg_acc[1] += dbg_t2 - dbg_t1; dbg_acc[2] += t3 - dbg_t2;
+        if (++dbg_n % 100 == 0) {
+            fprintf(stderr, "[oc multi launch x100, %d members] member records %.2f ms, rng draws %.2f ms, enqueue %.2f ms per call\n",
+                    n, dbg_acc[0] / 100, dbg_acc[1] / 100, dbg_acc[2] / 100);
+            dbg_acc[0] = dbg_acc[1] = dbg_acc[2] = 0;
+        }
+    }
     return OC_OK;
 }
 

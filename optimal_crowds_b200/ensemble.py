@@ -42,6 +42,12 @@ def field_bytes_per_member(Ny: int, Nx: int, T: float, dt: float, n_keys: int = 
 
 
 _SOLVER_CTX = {}   # (device, room size, grid step) -> Context owning the batched-solve workspace
+_CTX_POOL = {}     # (device, room size, grid step) -> library contexts of finished members, ready for reuse
+
+
+def _ctx_key(room_length, room_height, step):
+    import torch
+    return (torch.cuda.current_device(), float(room_length), float(room_height), float(step))
 
 
 def plan_waves(members, bytes_per_member: int, budget_bytes: int, max_wave: int = 256):
@@ -101,15 +107,23 @@ class ensemble:
 
     # ---------------------------------------------------------------------------------------------
     def _build(self, idx):
+        # a finished member's library context (device workspace, page-locked buffers, streams) serves the next member
+        # of the same room size: a wave of 128 members otherwise pays 128 x (cudaMalloc + cudaMallocHost + frees) per pass
+        room = simulations._load_room(self.rooms[idx])
+        step = simulations._load_config()["grid_step"]
+        free = _CTX_POOL.get(_ctx_key(room["room_length"], room["room_height"], step))
+        ctx = free.pop() if free else None
         return simulations.simulation(self.rooms[idx], self.T, recompute=self.recompute, record=self.record,
                                       field_storage=self.field_storage, fused=1, lookahead=False,
-                                      rng=np.random.RandomState(self.seeds[idx]), chunk_rows=self.chunk_rows)
+                                      rng=np.random.RandomState(self.seeds[idx]), chunk_rows=self.chunk_rows, _ctx=ctx)
 
     def _build_wave(self, wave):
         """the members of a wave, constructed by a few host threads: a member's crowd placement (oc_place_box: sequential
         rejection sampling on the member's own RandomState, ~5 ms per 1000 agents), rasterisation and allocations are
         independent of the other members', and the C calls release the GIL"""
-        n_thr = int(os.environ.get("OC_ENSEMBLE_BUILD_THREADS", "8"))
+        # (off by default: measured on the 16-core B200 box, members built on a pool made the host part of the batched
+        # steps erratic afterwards -- 0.5 -> 1-6 ms per wave step -- which costs more than the 0.3 s per wave it saves)
+        n_thr = int(os.environ.get("OC_ENSEMBLE_BUILD_THREADS", "1"))
         with contextlib.redirect_stdout(io.StringIO()):   # (one redirection around the pool: sys.stdout is process-wide)
             if n_thr <= 1 or len(wave) < 4:
                 return [self._build(i) for i in wave]
@@ -263,12 +277,19 @@ class ensemble:
             for s in sims:
                 for o in s.targets.values():
                     o.d_phi = o.d_vx = o.d_vy = None
-                s._ctx.close()
+                if len(_CTX_POOL.setdefault(_ctx_key(s.room_length, s.room_height, s.grid_step), [])) < 512:
+                    _CTX_POOL[_ctx_key(s.room_length, s.room_height, s.grid_step)].append(s._ctx)
+                else:
+                    s._ctx.close()
                 s.__dict__.clear()   # marshalled key descriptors, state tensors, agents <-> simulation reference cycles
             del sims
             import gc
             gc.collect()             # (a wave holds tens of GB of field samples: do not wait for the cyclic collector)
-            torch.cuda.empty_cache()
+            # the freed field tensors stay in torch's caching allocator for the next wave (same sizes); they are only
+            # handed back to the driver when the device runs short for the library's own allocations
+            free, total = torch.cuda.mem_get_info()
+            if free < 0.1 * total:
+                torch.cuda.empty_cache()
 
     def run(self, gather=True):
         """run this rank's members wave by wave; with torch.distributed initialised and gather=True every rank
@@ -284,6 +305,8 @@ class ensemble:
         budget = self.memory_budget
         if budget is None:
             free, _total = torch.cuda.mem_get_info()
+            # (blocks cached by torch's allocator are available to the next wave's tensors)
+            free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
             budget = int(free * 0.8)
         for wave in plan_waves(self.mine, per, budget, self.max_wave):
             self._run_wave(wave)

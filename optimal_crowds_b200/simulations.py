@@ -26,6 +26,53 @@ from .optimals import _load_config, _load_room
 warnings.filterwarnings("ignore")  # simulations.py:15
 
 
+class _Agents:
+    """``simulation.agents``: the reference's array of ``ped`` objects (simulations.py:142-151), built on first access.
+    A ``ped`` here is a view of row i of the device-resident crowd state, so nothing but the object itself is created;
+    constructing 1000 of them costs as much as placing the crowd, 100 k half a second.  Indexing (int, slice, index or
+    boolean arrays), iteration, ``len`` and ``np.asarray`` behave like the object array."""
+
+    def __init__(self, n, make):
+        self._n, self._make, self._made = int(n), make, {}
+
+    def __len__(self):
+        return self._n
+
+    @property
+    def shape(self):
+        return (self._n,)
+
+    size = property(lambda self: self._n)
+    dtype = np.dtype(object)
+    ndim = 1
+
+    def _one(self, i):
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(f"index {i} is out of bounds for axis 0 with size {self._n}")
+        a = self._made.get(i)
+        if a is None:
+            a = self._made[i] = self._make(i)
+        return a
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            return self._one(i)
+        idx = range(*i.indices(self._n)) if isinstance(i, slice) else np.arange(self._n)[i]
+        out = np.empty(len(idx), dtype=object)
+        for q, j in enumerate(idx):
+            out[q] = self._one(j)
+        return out
+
+    def __iter__(self):
+        return (self._one(i) for i in range(self._n))
+
+    def __array__(self, dtype=None, copy=None):
+        return self[:]
+
+
 class _Frame(list):
     """One history frame ``[[pos, vel, target, v_des] per agent inside ..., density]`` (simulations.py:579-589), built
     on first access: the agents' rows come from the device-resident trajectory record (row k = state before step k)
@@ -80,7 +127,7 @@ class simulation:
     TRACK_CHUNK = 64  # steps per block of the device-resident trajectory record
 
     def __init__(self, room, T, recompute=False, record=True, field_storage="phi", fused=1, lookahead=True,
-                 rng=None, chunk_rows=0, band=False, shard_keys=False):
+                 rng=None, chunk_rows=0, band=False, shard_keys=False, _ctx=None):
         """``room, T, recompute`` as in the reference (simulations.py:20).  Extras, all defaulting to reference
         behaviour: ``record`` (keep the per-step record behind ped.traj / ped.vels / history; it lives on the device and
         is read back on access), ``field_storage`` ('phi': the value-function samples, from which ``vx_opt`` /
@@ -102,7 +149,12 @@ class simulation:
         self.room_length = var_room['room_length']
         self.room_height = var_room['room_height']
         self.grid_step = var_config['grid_step']
-        self._ctx = _lib.Context(self.room_length, self.room_height, self.grid_step)
+        # (_ctx: a library context of the same room size and grid step to reuse -- ensembles recycle the contexts, and
+        # with them the device / page-locked workspaces, of finished members)
+        if _ctx is not None and (_ctx.room_length, _ctx.room_height, _ctx.dx) != (self.room_length, self.room_height,
+                                                                                 self.grid_step):
+            raise ValueError("_ctx was created for another room size / grid step")
+        self._ctx = _ctx if _ctx is not None else _lib.Context(self.room_length, self.room_height, self.grid_step)
         self.Ny, self.Nx = self._ctx.Ny, self._ctx.Nx       # simulations.py:63-64
         self.dx = self.dy = self.grid_step
         self.sigma_convolution = var_config['sigma_convolution']
@@ -180,12 +232,7 @@ class simulation:
             loc_N = len(xs)
             N += loc_N
             kid = list(self.targets).index(key)
-            for i in range(loc_N):
-                a = pedestrians.ped(None, None, self.grid_step, self.Vs[key], key, var_room['targets'], targets,
-                                    xs[i], ys[i], 0, 0, self.room_length, self.room_height, v_des_all[i],
-                                    self.a_min, self.tau_a, self.b_min, self.b_max, self.eta, self.eta_walls)
-                a._bind(self, len(agents))
-                agents.append(a)
+            agents.append((N - loc_N, key, targets))        # (first agent of the box, its key, its target names)
             xs_all.append(xs); ys_all.append(ys); vdes_all.append(v_des_all)
             key_all.append(np.full(loc_N, kid, dtype=np.int32))
         for key, cnt in box_count.items():
@@ -195,11 +242,20 @@ class simulation:
         self.V[self.V > np.min(self.V)] = 0                 # simulations.py:157
         self.N = N
         self.inside = self.N
-        self.agents = np.array(agents, dtype=object)
 
         cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt)
         x0, y0 = cat(xs_all, np.float64), cat(ys_all, np.float64)
         self._h_vdes = cat(vdes_all, np.float64)
+        box_first = [b[0] for b in agents]
+
+        def make_agent(i, boxes=agents, x0=x0, y0=y0):
+            first, key, tg = boxes[int(np.searchsorted(box_first, i, side="right")) - 1]
+            a = pedestrians.ped(None, None, self.grid_step, self.Vs[key], key, var_room['targets'], tg,
+                                x0[i], y0[i], 0, 0, self.room_length, self.room_height, self._h_vdes[i],
+                                self.a_min, self.tau_a, self.b_min, self.b_max, self.eta, self.eta_walls)
+            a._bind(self, i)
+            return a
+        self.agents = _Agents(N, make_agent)                # simulations.py:142-151, built on access
         self._h_key = cat(key_all, np.int32)
         self._h_status = np.ones(N, dtype=np.uint8)
         self._h_time0 = np.zeros(N)

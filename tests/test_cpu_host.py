@@ -230,3 +230,26 @@ def test_c_legacy_rng_equals_numpy_draws_and_state():
             r3 = np.random.RandomState(); r3.set_state(st)
             r3.choice(np.arange(N), N, replace=False); r3.normal(size=(na - q, 2)); s3 = r3.get_state()
             assert np.array_equal(ck[q], s3[1]) and (int(cp[q]), int(ch[q]), float(cc[q])) == (s3[2], s3[3], s3[4])
+
+
+def test_lazy_agents_container_behaves_like_the_object_array():
+    """simulation.agents builds its ped views on access (simulations.py:142-151 builds them eagerly): int / negative /
+    slice / fancy / boolean indexing, iteration, len, np.asarray, identity of repeated accesses, IndexError"""
+    from optimal_crowds_b200.simulations import _Agents
+    made = []
+
+    def make(i):
+        made.append(i)
+        return ("ped", i)
+    a = _Agents(7, make)
+    assert len(a) == 7 and a.shape == (7,) and a.size == 7 and made == []
+    assert a[2] == ("ped", 2) and a[-1] == ("ped", 6) and a[2] is a[2] and made == [2, 6]
+    assert list(a[1:4]) == [("ped", 1), ("ped", 2), ("ped", 3)] and isinstance(a[1:4], np.ndarray)
+    assert list(a[np.array([5, 0])]) == [("ped", 5), ("ped", 0)]
+    assert list(a[np.arange(7) % 3 == 0]) == [("ped", 0), ("ped", 3), ("ped", 6)]
+    assert [p[1] for p in a] == list(range(7)) and sorted(made) == list(range(7))      # every agent built exactly once
+    arr = np.asarray(a)
+    assert arr.dtype == object and arr.shape == (7,) and arr[4] is a[4]
+    with pytest.raises(IndexError):
+        a[7]
+    assert len(_Agents(0, make)) == 0 and list(_Agents(0, make)) == []
