@@ -253,3 +253,46 @@ def test_lazy_agents_container_behaves_like_the_object_array():
     with pytest.raises(IndexError):
         a[7]
     assert len(_Agents(0, make)) == 0 and list(_Agents(0, make)) == []
+
+
+@pytest.mark.parametrize("T,recompute,draw", [(2.0, False, False), (3.1, True, False), (1.0, True, True), (0.05, False, False)])
+def test_run_blocks_follow_the_reference_loop(T, recompute, draw, monkeypatch):
+    """run() hands blocks of iterations to advance() (simulations.py:427-441 runs them one by one): the blocks must end
+    exactly where the reference loop re-solves (every recompute_frequency steps) or draws (every 10th step) and at the
+    end of the horizon, with the time accumulated by repeated `time += dt` as in the reference"""
+    import sys
+    import types
+    from optimal_crowds_b200 import simulations
+    plt = types.SimpleNamespace(show=lambda: None)
+    monkeypatch.setitem(sys.modules, "matplotlib", types.SimpleNamespace(pyplot=plt))
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    s = object.__new__(simulations.simulation)
+    s.inside, s.time, s.T, s.dt, s.simu_step = 5, 0.0, T, 0.02, 0
+    s.recompute, s.recompute_step = recompute, 50
+    events = []
+    s._solve_all = lambda: events.append(("solve", s.simu_step))
+    s.draw = lambda mode: events.append(("draw", s.simu_step))
+
+    def advance(n, verbose=False):
+        assert n >= 1
+        events.append(("block", s.simu_step, n))
+        for _ in range(n):
+            s.time += s.dt
+            s.simu_step += 1
+    s.advance = advance
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        s.run(draw=draw)
+    # the reference loop
+    ref, t, k = [("solve", 0)], 0.0, 0
+    while t < T:
+        if recompute and k % 50 == 0 and k > 0:
+            ref.append(("solve", k))
+        t += 0.02
+        k += 1
+        if draw and k % 10 == 0:
+            ref.append(("draw", k))
+    assert s.simu_step == k and s.time == t
+    assert [e for e in events if e[0] != "block"] == ref
+    blocks = [e for e in events if e[0] == "block"]
+    assert sum(b[2] for b in blocks) == k and all(b[2] <= 50 for b in blocks if recompute)
