@@ -121,9 +121,8 @@ class ensemble:
         """the members of a wave, constructed by a few host threads: a member's crowd placement (oc_place_box: sequential
         rejection sampling on the member's own RandomState, ~5 ms per 1000 agents), rasterisation and allocations are
         independent of the other members', and the C calls release the GIL"""
-        # (off by default: measured on the 16-core B200 box, members built on a pool made the host part of the batched
-        # steps erratic afterwards -- 0.5 -> 1-6 ms per wave step -- which costs more than the 0.3 s per wave it saves)
-        n_thr = int(os.environ.get("OC_ENSEMBLE_BUILD_THREADS", "1"))
+        # (measured on the 16-core B200 box, 128 members: 0.52 s on one thread, 0.22 s on 8)
+        n_thr = int(os.environ.get("OC_ENSEMBLE_BUILD_THREADS", "8"))
         with contextlib.redirect_stdout(io.StringIO()):   # (one redirection around the pool: sys.stdout is process-wide)
             if n_thr <= 1 or len(wave) < 4:
                 return [self._build(i) for i in wave]
