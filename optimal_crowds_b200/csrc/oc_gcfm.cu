@@ -1,4 +1,5 @@
-// oc_gcfm.cu -- GCFM pedestrian update on sm_100a (K4 wall search, K5 per-agent prepare, K6 sweep) and the
+// oc_gcfm.cu -- GCFM pedestrian update on sm_100a (K4 wall search, K5 per-agent terms, K6 sweep = candidate-list
+// kernel + dependency-chain kernel; one CUDA graph per step; oc_gcfm_run: blocks of run-loop steps) and the
 // Gaussian density splat (K7).  Compile with -fmad=false: every formula is evaluated with exactly the
 // operations written here, in the reference's order, so results are bit-identical to the CPU restatement
 // used by the tests (two-oracle protocol).
