@@ -296,3 +296,31 @@ def test_run_blocks_follow_the_reference_loop(T, recompute, draw, monkeypatch):
     assert [e for e in events if e[0] != "block"] == ref
     blocks = [e for e in events if e[0] == "block"]
     assert sum(b[2] for b in blocks) == k and all(b[2] <= 50 for b in blocks if recompute)
+
+
+def test_c_legacy_rng_is_exact_under_concurrent_draws():
+    """four threads draw large steps at the same time: one of them gets the transform pool (oc_rng.h TransformPool, parked
+    helper threads), the others find it busy and transform inline -- every stream still equals numpy's"""
+    import threading
+    from optimal_crowds_b200 import _rng
+    N, out = 20000, {}
+
+    def work(seed):
+        st = np.random.RandomState(seed).get_state()
+        res = []
+        for rep in range(3):
+            perm, Z, st, _ = _rng._c_draw(st, N, N - 7 * rep, 8)
+            res.append((perm, Z))
+        out[seed] = (res, st)
+    ths = [threading.Thread(target=work, args=(s,)) for s in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for seed in range(4):
+        ref = np.random.RandomState(seed)
+        for rep, (perm, Z) in enumerate(out[seed][0]):
+            assert np.array_equal(perm, ref.choice(np.arange(N), N, replace=False))
+            assert np.array_equal(Z, ref.normal(size=(N - 7 * rep, 2)))
+        s2, s1 = ref.get_state(), out[seed][1]
+        assert np.array_equal(s1[1], s2[1]) and tuple(s1[2:]) == tuple(s2[2:])
