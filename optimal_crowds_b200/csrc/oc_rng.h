@@ -40,11 +40,19 @@ class TransformPool {
     // returns false if the pool is absent or busy (another generator is using it): the caller transforms inline
     bool begin(const double *X1, const double *X2, const double *R2, double *out, long long idx, long long n, long long n_ev) {
         if (workers_.empty() || !busy_.try_lock()) return false;
+        // A helper that has just finished the previous job may still be on its way to its next ticket: everything it
+        // could read for a ticket of THIS job is in place before the ticket counter is reset (release / acq_rel pair),
+        // and the progress counter is zeroed first, so that it cannot run ahead of the producer.
+        produced_.store(0, std::memory_order_relaxed);
+        done_.store(0, std::memory_order_relaxed);
         X1_ = X1; X2_ = X2; R2_ = R2; out_ = out; idx_ = idx; n_ = n; n_ev_ = n_ev;
         n_blocks_ = (n_ev + EV_BLOCK - 1) / EV_BLOCK;
-        next_.store(0, std::memory_order_relaxed);
-        done_.store(0, std::memory_order_relaxed);
-        produced_.store(0, std::memory_order_relaxed);
+        // tickets and the job descriptor carry the job's generation: a ticket drawn from the previous job's counter can
+        // never be mistaken for a block of this one (it fails the generation test, or -- against the old descriptor --
+        // the range test)
+        gen_ = (gen_ + 1) & 0x7fffffffull;
+        desc_.store((gen_ << 32) | (unsigned long long)n_blocks_, std::memory_order_release);
+        next_.store((long long)(gen_ << 32), std::memory_order_release);
         {
             std::lock_guard<std::mutex> lk(m_);
             job_++;
@@ -87,8 +95,10 @@ class TransformPool {
     }
     void work() {
         for (;;) {
-            const long long b = next_.fetch_add(1, std::memory_order_relaxed);
-            if (b >= n_blocks_) return;
+            const unsigned long long t = (unsigned long long)next_.fetch_add(1, std::memory_order_acq_rel);
+            const unsigned long long d = desc_.load(std::memory_order_acquire);
+            if ((t >> 32) != (d >> 32) || (t & 0xffffffffull) >= (d & 0xffffffffull)) return;
+            const long long b = (long long)(t & 0xffffffffull);
             const long long e0 = b * EV_BLOCK, e1 = std::min(n_ev_, e0 + EV_BLOCK);
             while (produced_.load(std::memory_order_acquire) < e1) std::this_thread::yield();
             for (long long e = e0; e < e1; e++) {
@@ -107,6 +117,8 @@ class TransformPool {
     double *out_ = nullptr;
     long long idx_ = 0, n_ = 0, n_ev_ = 0, n_blocks_ = 0;
     std::atomic<long long> next_{0}, done_{0}, produced_{0};
+    std::atomic<unsigned long long> desc_{0};   // (generation << 32) | number of blocks of the current job
+    unsigned long long gen_ = 0;                // written by the producer that holds busy_
 };
 
 
